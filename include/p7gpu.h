@@ -1,0 +1,204 @@
+/* p7gpu.h — C ABI of libp7gpu.so: the B200 (sm_100a) engine behind HMMER3's impl_* operator API.
+ *
+ * Everything here is `extern "C"`, plain pointers and sizes, no torch/CUDA types.  Each entry point
+ * names the reference interface it replaces (paths relative to reiverjohn/biobench2, HMMER/src/...).
+ * INTEGRATION.md shows the reference-side stub (an `impl_b200/` directory beside impl_sse/) that binds
+ * these symbols under HMMER's own names (p7_MSVFilter, p7_ViterbiFilter, ...).
+ *
+ * Conventions (same as the reference):
+ *   - digital sequences are ESL_DSQ: dsq[0] = dsq[L+1] = 255 sentinels, residues dsq[1..L] in 0..Kp-1
+ *     (HMMER/easel/easel.h:308-313);
+ *   - return codes are easel's: P7GPU_OK 0, P7GPU_EMEM 5, P7GPU_EINVAL 11, P7GPU_ERANGE 16 (= overflow,
+ *     score already +inf, "certain hit"), P7GPU_ENORESULT 19 (only from the SSV stage),
+ *     P7GPU_ESYS 12 for CUDA runtime failures (text via p7gpu_last_error());
+ *   - the caller owns every host buffer; the library retains nothing but the handles it returns;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns P7GPU_ESYS.
+ */
+#ifndef P7GPU_H_INCLUDED
+#define P7GPU_H_INCLUDED
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P7GPU_OK         0
+#define P7GPU_EMEM       5
+#define P7GPU_EINVAL    11
+#define P7GPU_ESYS      12
+#define P7GPU_ERANGE    16
+#define P7GPU_ENORESULT 19
+
+#define P7GPU_KP        29   /* amino Kp (HMMER/easel/esl_alphabet.c:276)  */
+#define P7GPU_K         20
+#define P7GPU_NXCELLS    6   /* E,N,J,B,C,SCALE per row (impl_sse/impl_sse.h:172-173) */
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. The profile as the reference hands it over: a read-only *view* of a P7_OPROFILE
+ *    (impl_sse/impl_sse.h:76-143).  Pointers address the reference's own striped SSE arrays; nothing
+ *    is copied on the reference side.  p7gpu_profile_upload() de-stripes them into the GPU layout.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct p7gpu_oprofile_view {
+  int32_t M;                /* om->M                                                            */
+  int32_t Kp;               /* om->abc->Kp (29 for amino)                                       */
+  int32_t K;                /* om->abc->K  (20)                                                 */
+  int32_t mode;             /* om->mode (p7_LOCAL=1 / p7_UNILOCAL=3 ...; filters need local)    */
+  float   nj;               /* om->nj: expected # of J's (1.0 multihit, 0.0 unihit)             */
+  /* MSV/SSV part: 16 x u8 vectors, node k=q+1+z*Q16 in byte z of vector q (p7_oprofile.c:789-792) */
+  const uint8_t *rbv;       /* om->rbv[0]: [Kp][Q16][16]                                        */
+  const uint8_t *sbv;       /* om->sbv[0]: [Kp][Q16+17][16] (signed bytes); may be NULL         */
+  uint8_t tbm_b, tec_b, tjb_b, base_b, bias_b;  /* tjb_b is ignored: recomputed per target L   */
+  float   scale_b;
+  /* ViterbiFilter part: 8 x i16 vectors (p7_oprofile.c:816-912)                                  */
+  const int16_t *rwv;       /* om->rwv[0]: [Kp][Q8][8]                                          */
+  const int16_t *twv;       /* om->twv   : [7*Q8 interleaved BM,MM,IM,DM,MD,MI,II][8] then [Q8][8] DD */
+  int16_t xw[4][2];         /* om->xw[E,N,J,C][MOVE,LOOP]; N/C/J MOVE recomputed per target L    */
+  float   scale_w;
+  int16_t base_w, ddbound_w;
+  /* Forward/Backward part: 4 x f32 vectors (p7_oprofile.c:919-985)                               */
+  const float   *rfv;       /* om->rfv[0]: [Kp][Q4][4]                                          */
+  const float   *tfv;       /* om->tfv   : same interleaving as twv                             */
+  float   xf[4][2];         /* om->xf; N/C/J entries recomputed per target L                    */
+  /* statistics + bias-filter composition copied from the profile                                 */
+  float   evparam[6];       /* MMU, MLAMBDA, VMU, VLAMBDA, FTAU, FLAMBDA (hmmer.h:72)           */
+  float   compo[20];        /* om->compo (p7_bg_SetFilter input, p7_bg.c:430-453)               */
+} p7gpu_oprofile_view;
+
+typedef struct p7gpu_ctx     p7gpu_ctx;      /* one per worker thread / GPU (cf. hmmsearch.c:36-44 WORKER_INFO) */
+typedef struct p7gpu_profile p7gpu_profile;  /* GPU-resident repacked profile                                   */
+typedef struct p7gpu_seqdb   p7gpu_seqdb;    /* GPU-resident packed digital target database                     */
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Context
+ * ---------------------------------------------------------------------------------------------- */
+/* replaces impl_Init() (impl_sse/impl_sse.h:356-376) + per-worker setup (hmmsearch.c:505-516) */
+int         p7gpu_ctx_create (int device, p7gpu_ctx **ret_ctx);
+void        p7gpu_ctx_destroy(p7gpu_ctx *ctx);
+const char *p7gpu_last_error (void);                 /* thread-local text of the last failure */
+int         p7gpu_device_count(void);
+/* run later launches of this ctx on an externally owned cudaStream_t (e.g. torch's current stream) */
+int         p7gpu_ctx_set_stream(p7gpu_ctx *ctx, void *cuda_stream);
+/* number of kernel launches issued through this ctx so far (bench.py's gpu_launches claim) */
+int64_t     p7gpu_ctx_launch_count(const p7gpu_ctx *ctx);
+int         p7gpu_ctx_synchronize(p7gpu_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. Profile: replaces the consumer side of p7_oprofile_Convert()/p7_oprofile_Clone()
+ *    (impl_sse/p7_oprofile.c:1004-1041, :403-420).  Per-target p7_oprofile_ReconfigLength()
+ *    (:1061-1127) is folded into per-L tables built on the host with the host libm.
+ * ---------------------------------------------------------------------------------------------- */
+int  p7gpu_profile_upload (p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_profile **ret_prof);
+void p7gpu_profile_destroy(p7gpu_profile *prof);
+int  p7gpu_profile_M      (const p7gpu_profile *prof);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4. Target database: replaces ESL_SQ_BLOCK hand-off (easel/esl_sqio.c:1041; hmmsearch.c:1317-1361).
+ *    Packed form: `residues` holds every target's dsq[1..L] back to back with ONE 255 sentinel byte
+ *    before the first target and after every target, so residues + offsets[s] - 1 is a valid
+ *    sentinel-framed ESL_DSQ of length lengths[s] (offsets[s] = index of the target's first residue).
+ * ---------------------------------------------------------------------------------------------- */
+int  p7gpu_seqdb_upload (p7gpu_ctx *ctx, const uint8_t *residues, int64_t nbytes,
+                         const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                         p7gpu_seqdb **ret_db);
+/* same, for arrays that already live in this device's HBM (no copy; caller keeps them alive) */
+int  p7gpu_seqdb_adopt_device(p7gpu_ctx *ctx, const void *d_residues, int64_t nbytes,
+                              const void *d_offsets, const void *d_lengths, int64_t nseq,
+                              int32_t max_length, p7gpu_seqdb **ret_db);
+void    p7gpu_seqdb_destroy(p7gpu_seqdb *db);
+int64_t p7gpu_seqdb_nseq   (const p7gpu_seqdb *db);
+int64_t p7gpu_seqdb_nres   (const p7gpu_seqdb *db);
+
+/* ------------------------------------------------------------------------------------------------
+ * 5. Batched stages.  `idx` selects targets of `db` (NULL = all nseq targets, n ignored→nseq);
+ *    outputs are host arrays of n entries, in idx order.  Scores are nats exactly as the reference
+ *    returns them; status is the reference's return code per target.
+ * ---------------------------------------------------------------------------------------------- */
+/* p7_MSVFilter(dsq,L,om,ox,&sc) (impl_sse/msvfilter.c:75-210): SSV first (ssvfilter.c:877-926), the
+ * J-state recursion for targets where SSV answers eslENORESULT.                                     */
+int p7gpu_msvfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                          const int64_t *idx, int64_t n, float *sc, int32_t *status);
+/* p7_SSVFilter alone (ssvfilter.c:877-926); status may be P7GPU_ENORESULT */
+int p7gpu_ssvfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                          const int64_t *idx, int64_t n, float *sc, int32_t *status);
+/* p7_ViterbiFilter (impl_sse/vitfilter.c:83-249) */
+int p7gpu_vitfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                          const int64_t *idx, int64_t n, float *sc, int32_t *status);
+/* p7_ForwardParser (impl_sse/fwdback.c:133-144, 257-465).  If xmx != NULL it receives, for target j,
+ * (lengths+1)*6 floats {E,N,J,B,C,SCALE} per row at xmx + xmx_offsets[j] (floats); totscale[j] optional. */
+int p7gpu_forward_batch  (p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                          const int64_t *idx, int64_t n, float *sc, int32_t *status,
+                          float *xmx, const int64_t *xmx_offsets, float *totscale);
+/* p7_BackwardParser (impl_sse/fwdback.c:237-249, 469-735): consumes the forward specials (scale factors) */
+int p7gpu_backward_batch (p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                          const int64_t *idx, int64_t n, const float *fwd_xmx, const int64_t *xmx_offsets,
+                          float *sc, int32_t *status, float *bck_xmx, float *bck_totscale);
+
+/* device-resident variant of the MSV stage for throughput measurement: results stay in HBM
+ * (d_sc: n floats, d_status: n int32, both device pointers owned by the caller).                 */
+int p7gpu_msvfilter_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                           void *d_sc, void *d_status);
+
+/* ------------------------------------------------------------------------------------------------
+ * 6. Signature-level wrappers: one target per call, same argument meaning as impl_sse.h:309-344
+ *    (P7_OPROFILE* -> p7gpu_profile*, P7_OMX* -> the xmx array it would have filled).
+ * ---------------------------------------------------------------------------------------------- */
+int p7gpu_SSVFilter     (p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om, float *ret_sc);
+int p7gpu_MSVFilter     (p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om, float *ret_sc);
+int p7gpu_ViterbiFilter (p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om, float *ret_sc);
+int p7gpu_ForwardParser (p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
+                         float *fwd_xmx /* (L+1)*6 or NULL */, float *fwd_totscale, float *opt_sc);
+int p7gpu_BackwardParser(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
+                         const float *fwd_xmx, float *bck_xmx /* (L+1)*6 or NULL */,
+                         float *bck_totscale, float *opt_sc);
+
+/* ------------------------------------------------------------------------------------------------
+ * 7. The batched pipeline: what the loop body at hmmsearch.c:1399-1411 does per target
+ *    (p7_pli_NewSeq; p7_bg_SetLength; p7_oprofile_ReconfigLength; p7_Pipeline; Reuse), for a whole
+ *    packed database, stage-major (SURVEY.md §8b "stage-major reordering is legal").
+ *    It stops where north_star stops: after p7_BackwardParser (p7_pipeline.c:735).  Survivors come
+ *    back as records carrying everything p7_domaindef_ByPosteriorHeuristics()+hit creation
+ *    (p7_pipeline.c:737-898, unchanged host code) need.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct p7gpu_pipeline_opts {   /* the fields of P7_PIPELINE the path reads (hmmer.h:1175-1250) */
+  double  F1, F2, F3;                  /* p7_pipeline.c:214-216 defaults 0.02, 1e-3, 1e-5            */
+  int32_t do_biasfilter;               /* pli->do_biasfilter                                          */
+  int32_t do_max;                      /* --max: F1=F2=F3=1, bias off (p7_pipeline.c:222-229)         */
+  int32_t want_specials;               /* 1: return fwd/bck xmx for Forward survivors                  */
+} p7gpu_pipeline_opts;
+
+typedef struct p7gpu_pipeline_counters { /* P7_PIPELINE accounting (hmmer.h:1224-1231), merged like p7_pipeline_Merge */
+  uint64_t nseqs, nres, n_past_msv, n_past_bias, n_past_vit, n_past_fwd;
+} p7gpu_pipeline_counters;
+
+typedef struct p7gpu_survivor {        /* one per target that passed the Forward filter (p7_pipeline.c:731) */
+  int64_t seqidx;                      /* index into the database                                     */
+  int32_t L;
+  int32_t msv_status, vit_status;      /* reference return codes of the two filters                   */
+  float   usc, vfsc, fwdsc, bcksc;     /* nats; vfsc = NaN when the Viterbi stage was skipped (:716)  */
+  float   nullsc, filtersc;            /* p7_bg_NullOne / p7_bg_FilterScore                            */
+  float   fwd_totscale, bck_totscale;
+  int64_t xmx_offset;                  /* float offset of this target's (L+1)*6 block in fwd_xmx/bck_xmx, or -1 */
+} p7gpu_survivor;
+
+typedef struct p7gpu_pipeline_result p7gpu_pipeline_result;
+
+int  p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                        const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+const p7gpu_pipeline_counters *p7gpu_result_counters (const p7gpu_pipeline_result *res);
+int64_t                        p7gpu_result_nsurvivors(const p7gpu_pipeline_result *res);
+const p7gpu_survivor          *p7gpu_result_survivors (const p7gpu_pipeline_result *res);
+const float                   *p7gpu_result_fwd_xmx  (const p7gpu_pipeline_result *res);
+const float                   *p7gpu_result_bck_xmx  (const p7gpu_pipeline_result *res);
+void                           p7gpu_result_destroy  (p7gpu_pipeline_result *res);
+
+/* host-side helpers restating the reference's per-target scalar arithmetic (host libm, bit-exact):
+ * p7_bg_NullOne (p7_bg.c:358-363) and the MSV P-value test of p7_pipeline.c:691-693. */
+float  p7gpu_nullsc(int L);
+double p7gpu_msv_pvalue(float usc, float nullsc_or_filtersc, float mmu, float mlambda);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P7GPU_H_INCLUDED */
