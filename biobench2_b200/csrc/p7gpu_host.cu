@@ -1,0 +1,600 @@
+// p7gpu_host.cu — host side of libp7gpu.so: context, profile repack, packed database, per-L tables and
+// the batched stage entry points of include/p7gpu.h.  No CPU compute fallback lives here: every stage
+// entry launches a CUDA kernel or fails with P7GPU_ESYS.
+#include "p7gpu_internal.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+
+namespace p7g {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+DiagGeom diag_geom(int M)
+{
+  DiagGeom g; g.M = M;
+  int Q = (M + 1 + 63) / 64;          // 64*Q >= M+1: at least one pad column
+  if ((Q & 1) == 0) Q++;              // odd lane stride -> conflict-free LDS.32
+  g.Q = Q; g.P = 64 * Q; g.rowWords = g.P + DIAG_CHUNK + Q;
+  return g;
+}
+
+int ensure_scratch(p7gpu_ctx *ctx, size_t bytes)
+{
+  if (bytes <= ctx->d_scratch_bytes) return P7GPU_OK;
+  if (ctx->d_scratch) { P7G_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->d_scratch_bytes = 0; }
+  size_t want = std::max(bytes, (size_t) 1 << 20);
+  P7G_CUDA(cudaMalloc(&ctx->d_scratch, want));
+  ctx->d_scratch_bytes = want;
+  return P7GPU_OK;
+}
+int ensure_scratch2(p7gpu_ctx *ctx, size_t bytes)
+{
+  if (bytes <= ctx->d_scratch2_bytes) return P7GPU_OK;
+  if (ctx->d_scratch2) { P7G_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_scratch2); ctx->d_scratch2 = nullptr; ctx->d_scratch2_bytes = 0; }
+  size_t want = std::max(bytes, (size_t) 1 << 20);
+  P7G_CUDA(cudaMalloc(&ctx->d_scratch2, want));
+  ctx->d_scratch2_bytes = want;
+  return P7GPU_OK;
+}
+int ensure_pinned(p7gpu_ctx *ctx, size_t bytes)
+{
+  if (bytes <= ctx->h_pinned_bytes) return P7GPU_OK;
+  if (ctx->h_pinned) { P7G_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0; }
+  size_t want = std::max(bytes, (size_t) 1 << 20);
+  P7G_CUDA(cudaMallocHost(&ctx->h_pinned, want));
+  ctx->h_pinned_bytes = want;
+  return P7GPU_OK;
+}
+
+// ---- per-L constants (host libm; p7_oprofile.c:676-699,1085-1127; p7_bg.c:190-199,358-363) ----------
+static uint8_t byteify_cost(float scale_b, float sc)
+{
+  sc = -1.0f * roundf(scale_b * sc);
+  return (sc > 255.) ? 255 : (uint8_t) sc;
+}
+static int16_t wordify(float scale_w, float sc)
+{
+  sc = roundf(scale_w * sc);
+  if      (sc >=  32767.0) return  32767;
+  else if (sc <= -32768.0) return -32768;
+  else return (int16_t) sc;
+}
+static LenConst len_const(const p7gpu_profile *prof, int L)
+{
+  LenConst c;
+  c.tjb_b   = byteify_cost(prof->scale_b, logf(3.0f / (float) (L + 3)));
+  c.pmove   = (2.0f + prof->nj) / ((float) L + 2.0f + prof->nj);
+  c.xw_move = wordify(prof->scale_w, logf(c.pmove));
+  float p1  = (float) L / (float) (L + 1);
+  c.nullsc  = (float) ((double) (float) L * log((double) p1) + log(1. - (double) p1));
+  c.pad = 0;
+  return c;
+}
+
+int ensure_len_table(const p7gpu_profile *prof, int Lmax)
+{
+  std::lock_guard<std::mutex> lock(prof->len_mutex);
+  if (Lmax < prof->len_cap) return P7GPU_OK;
+  int cap = std::max(Lmax + 1, std::max(4096, prof->len_cap * 2));
+  prof->h_len.resize(cap);
+  for (int L = prof->len_cap; L < cap; L++) prof->h_len[L] = len_const(prof, L);
+  LenConst *d_new = nullptr;
+  P7G_CUDA(cudaMalloc(&d_new, sizeof(LenConst) * cap));
+  P7G_CUDA(cudaMemcpyAsync(d_new, prof->h_len.data(), sizeof(LenConst) * cap, cudaMemcpyHostToDevice, prof->ctx->stream));
+  P7G_CUDA(cudaStreamSynchronize(prof->ctx->stream));
+  if (prof->d_len) cudaFree(prof->d_len);
+  prof->d_len = d_new;
+  prof->len_cap = cap;
+  return P7GPU_OK;
+}
+
+int dp_cells_per_lane(int M)
+{
+  static const int cs[] = {1,2,3,4,5,6,7,8,9,10,11,12,13,14,16,18,20,24,28,32,40,48,56,64,80,96,112,130};
+  for (int c : cs) if (32 * c >= M) return c;
+  return -1;
+}
+
+static int nq_of(int M, int w) { int q = (M - 1) / w + 1; return q < 2 ? 2 : q; }   // impl_sse.h:25-27
+
+}  // namespace p7g
+
+using namespace p7g;
+
+// =================================================================================================
+extern "C" {
+
+const char *p7gpu_last_error(void) { return g_err; }
+
+int p7gpu_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int p7gpu_ctx_create(int device, p7gpu_ctx **ret_ctx)
+{
+  if (!ret_ctx) return P7GPU_EINVAL;
+  *ret_ctx = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); libp7gpu has no CPU fallback", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    return P7GPU_ESYS;
+  }
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (0..%d)", device, ndev - 1); return P7GPU_EINVAL; }
+  P7G_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  P7G_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { set_error("device %d is sm_%d%d; libp7gpu is built for sm_100a only", device, prop.major, prop.minor); return P7GPU_ESYS; }
+  p7gpu_ctx *ctx = new p7gpu_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = (int) prop.sharedMemPerBlockOptin;
+  P7G_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = true;
+  P7G_CUDA(cudaMalloc(&ctx->d_counters, 16 * sizeof(unsigned int)));
+  P7G_CUDA(cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned int)));
+  *ret_ctx = ctx;
+  return P7GPU_OK;
+}
+
+void p7gpu_ctx_destroy(p7gpu_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int p7gpu_ctx_set_stream(p7gpu_ctx *ctx, void *cuda_stream)
+{
+  if (!ctx) return P7GPU_EINVAL;
+  P7G_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t) cuda_stream;
+  ctx->own_stream = false;
+  return P7GPU_OK;
+}
+
+int64_t p7gpu_ctx_launch_count(const p7gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int p7gpu_ctx_synchronize(p7gpu_ctx *ctx)
+{
+  if (!ctx) return P7GPU_EINVAL;
+  P7G_CUDA(cudaStreamSynchronize(ctx->stream));
+  return P7GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Profile upload: de-stripe the P7_OPROFILE arrays (node k -> vector q=(k-1)%Q, lane z=(k-1)/Q,
+// p7_oprofile.c:789-792,845-848,938-941) and build the GPU layouts.
+// ---------------------------------------------------------------------------------------------------
+int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_profile **ret_prof)
+{
+  if (!ctx || !om || !ret_prof) return P7GPU_EINVAL;
+  *ret_prof = nullptr;
+  if (om->M < 1 || om->Kp != P7GPU_KP || !om->rbv) { set_error("profile_upload: need an amino profile (Kp=29) with M>=1"); return P7GPU_EINVAL; }
+  if (om->M > 64 * MAX_Q - 1) { set_error("profile_upload: M=%d exceeds the supported maximum %d", om->M, 64 * MAX_Q - 1); return P7GPU_EINVAL; }
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  const int M = om->M, Kp = om->Kp;
+  const int Q16 = nq_of(M, 16), Q8 = nq_of(M, 8), Q4 = nq_of(M, 4);
+  p7gpu_profile *prof = new p7gpu_profile();
+  prof->ctx = ctx; prof->M = M; prof->Kp = Kp; prof->nj = om->nj;
+  memcpy(prof->evparam, om->evparam, sizeof(prof->evparam));
+  prof->msv.tbm_b = om->tbm_b; prof->msv.tec_b = om->tec_b; prof->msv.base_b = om->base_b; prof->msv.bias_b = om->bias_b;
+  prof->msv.scale_b = om->scale_b; prof->scale_b = om->scale_b;
+  prof->geom = diag_geom(M);
+  const DiagGeom &g = prof->geom;
+
+  // ---- SSV / MSV gain tables in the diagonal layout -------------------------------------------------
+  {
+    std::vector<int16_t> gs((size_t) NTABROWS * g.P), gm((size_t) NTABROWS * g.P);
+    for (int x = 0; x < NTABROWS; x++)
+      for (int col = 0; col < g.P; col++) {
+        int16_t vs = (int16_t) SSV_PADGAIN, vm = -255;        // pad column / pad residue row
+        if (x < Kp && col < M) {
+          int k = col + 1, q = (k - 1) % Q16, z = (k - 1) / Q16;
+          uint8_t rb = om->rbv[((size_t) x * Q16 + q) * 16 + z];
+          int8_t  sb;
+          if (om->sbv) sb = (int8_t) om->sbv[((size_t) x * (Q16 + 17) + q) * 16 + z];
+          else { int a = (127 + om->bias_b) - rb; if (a < 0) a = 0; sb = (int8_t) ((uint8_t) a ^ 127); }   // p7_oprofile.c:711-752
+          vs = (int16_t) (-(int) sb);
+          vm = (int16_t) (-(int) rb);
+        }
+        gs[(size_t) x * g.P + col] = vs;
+        gm[(size_t) x * g.P + col] = vm;
+      }
+    std::vector<uint32_t> ts((size_t) NTABROWS * g.rowWords), tm((size_t) NTABROWS * g.rowWords);
+    const int H = 32 * g.Q;                                   // column distance between the two halves
+    for (int x = 0; x < NTABROWS; x++)
+      for (int c = 0; c < g.rowWords; c++) {
+        int lo = c % g.P, hi = (c + H) % g.P;
+        ts[(size_t) x * g.rowWords + c] = (uint32_t) (uint16_t) gs[(size_t) x * g.P + lo] | ((uint32_t) (uint16_t) gs[(size_t) x * g.P + hi] << 16);
+        tm[(size_t) x * g.rowWords + c] = (uint32_t) (uint16_t) gm[(size_t) x * g.P + lo] | ((uint32_t) (uint16_t) gm[(size_t) x * g.P + hi] << 16);
+      }
+    P7G_CUDA(cudaMalloc(&prof->d_ssv_tab, ts.size() * 4));
+    P7G_CUDA(cudaMalloc(&prof->d_msv_tab, tm.size() * 4));
+    P7G_CUDA(cudaMemcpy(prof->d_ssv_tab, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice));
+    P7G_CUDA(cudaMemcpy(prof->d_msv_tab, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice));
+  }
+
+  // ---- Viterbi / Forward tables, lane-transposed [row][j][lane], node k = lane*C + j + 1 ----------------
+  if (om->rwv && om->twv && om->rfv && om->tfv) {
+    const int C = dp_cells_per_lane(M);
+    prof->dpC = C;
+    std::vector<int16_t> rw((size_t) NTABROWS * C * 32, (int16_t) -32768), tw((size_t) 8 * C * 32, (int16_t) -32768);
+    std::vector<float>   rf((size_t) NTABROWS * C * 32, 0.0f),            tf((size_t) 8 * C * 32, 0.0f);
+    for (int k = 1; k <= M; k++) {
+      const int lane = (k - 1) / C, j = (k - 1) % C;
+      const int q8 = (k - 1) % Q8, z8 = (k - 1) / Q8, q4 = (k - 1) % Q4, z4 = (k - 1) / Q4;
+      for (int x = 0; x < Kp; x++) {
+        rw[((size_t) x * C + j) * 32 + lane] = om->rwv[((size_t) x * Q8 + q8) * 8 + z8];
+        rf[((size_t) x * C + j) * 32 + lane] = om->rfv[((size_t) x * Q4 + q4) * 4 + z4];
+      }
+      for (int t = 0; t < 7; t++) {
+        tw[((size_t) t * C + j) * 32 + lane] = om->twv[((size_t) 7 * q8 + t) * 8 + z8];
+        tf[((size_t) t * C + j) * 32 + lane] = om->tfv[((size_t) 7 * q4 + t) * 4 + z4];
+      }
+      tw[((size_t) 7 * C + j) * 32 + lane] = om->twv[((size_t) 7 * Q8 + q8) * 8 + z8];
+      tf[((size_t) 7 * C + j) * 32 + lane] = om->tfv[((size_t) 7 * Q4 + q4) * 4 + z4];
+    }
+    P7G_CUDA(cudaMalloc(&prof->d_rw, rw.size() * 2)); P7G_CUDA(cudaMemcpy(prof->d_rw, rw.data(), rw.size() * 2, cudaMemcpyHostToDevice));
+    P7G_CUDA(cudaMalloc(&prof->d_tw, tw.size() * 2)); P7G_CUDA(cudaMemcpy(prof->d_tw, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
+    P7G_CUDA(cudaMalloc(&prof->d_rf, rf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rf, rf.data(), rf.size() * 4, cudaMemcpyHostToDevice));
+    P7G_CUDA(cudaMalloc(&prof->d_tf, tf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
+    prof->vit.xw_E_move = om->xw[0][0]; prof->vit.xw_E_loop = om->xw[0][1];
+    prof->vit.base_w = om->base_w; prof->vit.ddbound_w = om->ddbound_w; prof->vit.scale_w = om->scale_w;
+    prof->scale_w = om->scale_w;
+    prof->fwd.xf_E_move = om->xf[0][0]; prof->fwd.xf_E_loop = om->xf[0][1];
+  }
+  *ret_prof = prof;
+  return P7GPU_OK;
+}
+
+void p7gpu_profile_destroy(p7gpu_profile *prof)
+{
+  if (!prof) return;
+  cudaSetDevice(prof->ctx->device);
+  cudaStreamSynchronize(prof->ctx->stream);
+  cudaFree(prof->d_ssv_tab); cudaFree(prof->d_msv_tab);
+  cudaFree(prof->d_rw); cudaFree(prof->d_tw); cudaFree(prof->d_rf); cudaFree(prof->d_tf);
+  cudaFree(prof->d_len);
+  delete prof;
+}
+
+int p7gpu_profile_M(const p7gpu_profile *prof) { return prof ? prof->M : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// Target database
+// ---------------------------------------------------------------------------------------------------
+__global__ void iota_kernel(int32_t *v, int64_t n)
+{
+  int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (int32_t) i;
+}
+
+static int build_order(p7gpu_ctx *ctx, p7gpu_seqdb *db)
+{
+  const int64_t n = db->nseq;
+  if (n == 0) return P7GPU_OK;
+  if (n > 0x7fffffffLL) { set_error("seqdb: more than 2^31-1 targets per device"); return P7GPU_EINVAL; }
+  int32_t *d_keys_out = nullptr, *d_iota = nullptr; void *d_tmp = nullptr; size_t tmp_bytes = 0;
+  P7G_CUDA(cudaMalloc(&db->d_order, sizeof(int32_t) * n));
+  P7G_CUDA(cudaMalloc(&d_keys_out, sizeof(int32_t) * n));
+  P7G_CUDA(cudaMalloc(&d_iota, sizeof(int32_t) * n));
+  iota_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(d_iota, n);
+  P7G_CUDA(cudaGetLastError());
+  P7G_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, db->d_len, d_keys_out, d_iota, db->d_order, (int) n, 0, 32, ctx->stream));
+  P7G_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
+  P7G_CUDA(cub::DeviceRadixSort::SortPairsDescending(d_tmp, tmp_bytes, db->d_len, d_keys_out, d_iota, db->d_order, (int) n, 0, 32, ctx->stream));
+  P7G_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_tmp); cudaFree(d_keys_out); cudaFree(d_iota);
+  return P7GPU_OK;
+}
+
+int p7gpu_seqdb_upload(p7gpu_ctx *ctx, const uint8_t *residues, int64_t nbytes, const int64_t *offsets,
+                       const int32_t *lengths, int64_t nseq, p7gpu_seqdb **ret_db)
+{
+  if (!ctx || !ret_db || nseq < 0 || (nseq > 0 && (!residues || !offsets || !lengths))) return P7GPU_EINVAL;
+  *ret_db = nullptr;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  int32_t Lmax = 0; int64_t nres = 0;
+  for (int64_t s = 0; s < nseq; s++) {
+    if (lengths[s] < 0 || offsets[s] < 1 || offsets[s] + lengths[s] >= nbytes) {
+      set_error("seqdb_upload: target %lld (offset %lld, length %d) does not fit the packed array of %lld bytes",
+                (long long) s, (long long) offsets[s], lengths[s], (long long) nbytes);
+      return P7GPU_EINVAL;
+    }
+    Lmax = std::max(Lmax, lengths[s]); nres += lengths[s];
+  }
+  p7gpu_seqdb *db = new p7gpu_seqdb();
+  db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->nres = nres; db->max_length = Lmax; db->owns = true;
+  const size_t padded = ((size_t) nbytes + 15) / 16 * 16 + 32;
+  uint8_t *d_res = nullptr; int64_t *d_off = nullptr; int32_t *d_len = nullptr;
+  P7G_CUDA(cudaMalloc(&d_res, padded));
+  P7G_CUDA(cudaMemsetAsync(d_res, 0xff, padded, ctx->stream));
+  if (nbytes) P7G_CUDA(cudaMemcpyAsync(d_res, residues, (size_t) nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  P7G_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * std::max<int64_t>(nseq, 1)));
+  P7G_CUDA(cudaMalloc(&d_len, sizeof(int32_t) * std::max<int64_t>(nseq, 1)));
+  if (nseq) {
+    P7G_CUDA(cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * nseq, cudaMemcpyHostToDevice, ctx->stream));
+    P7G_CUDA(cudaMemcpyAsync(d_len, lengths, sizeof(int32_t) * nseq, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  db->d_res = d_res; db->d_off = d_off; db->d_len = d_len;
+  P7G_CUDA(cudaStreamSynchronize(ctx->stream));
+  int st = build_order(ctx, db);
+  if (st != P7GPU_OK) { p7gpu_seqdb_destroy(db); return st; }
+  *ret_db = db;
+  return P7GPU_OK;
+}
+
+int p7gpu_seqdb_adopt_device(p7gpu_ctx *ctx, const void *d_residues, int64_t nbytes, const void *d_offsets,
+                             const void *d_lengths, int64_t nseq, int32_t max_length, p7gpu_seqdb **ret_db)
+{
+  if (!ctx || !ret_db || !d_residues || !d_offsets || !d_lengths || nseq < 0) return P7GPU_EINVAL;
+  if (((uintptr_t) d_residues & 15) != 0) { set_error("seqdb_adopt_device: residue array must be 16-byte aligned"); return P7GPU_EINVAL; }
+  *ret_db = nullptr;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  p7gpu_seqdb *db = new p7gpu_seqdb();
+  db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->nres = nbytes - nseq - 1; db->max_length = max_length; db->owns = false;
+  db->d_res = (const uint8_t *) d_residues; db->d_off = (const int64_t *) d_offsets; db->d_len = (const int32_t *) d_lengths;
+  int st = build_order(ctx, db);
+  if (st != P7GPU_OK) { p7gpu_seqdb_destroy(db); return st; }
+  *ret_db = db;
+  return P7GPU_OK;
+}
+
+void p7gpu_seqdb_destroy(p7gpu_seqdb *db)
+{
+  if (!db) return;
+  cudaSetDevice(db->ctx->device);
+  cudaStreamSynchronize(db->ctx->stream);
+  if (db->owns) { cudaFree((void *) db->d_res); cudaFree((void *) db->d_off); cudaFree((void *) db->d_len); }
+  cudaFree(db->d_order);
+  delete db;
+}
+int64_t p7gpu_seqdb_nseq(const p7gpu_seqdb *db) { return db ? db->nseq : 0; }
+int64_t p7gpu_seqdb_nres(const p7gpu_seqdb *db) { return db ? db->nres : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// Batched stages
+// ---------------------------------------------------------------------------------------------------
+struct BatchBufs { int64_t *d_idx; float *d_sc; int32_t *d_st; int64_t *d_list; int64_t n; };
+
+// carve the device scratch: [idx n][sc n][status n][noresult list 2n]
+static int setup_batch(p7gpu_ctx *ctx, const p7gpu_seqdb *db, const int64_t *idx, int64_t n_in, BatchBufs *b)
+{
+  const int64_t n = idx ? n_in : db->nseq;
+  b->n = n;
+  const size_t a = ((size_t) std::max<int64_t>(n, 1) * 8 + 255) / 256 * 256;
+  P7G_CHECK(ensure_scratch(ctx, a * 5));
+  char *base = (char *) ctx->d_scratch;
+  b->d_idx = idx ? (int64_t *) base : nullptr;
+  b->d_sc  = (float *)   (base + a);
+  b->d_st  = (int32_t *) (base + 2 * a);
+  b->d_list = (int64_t *) (base + 3 * a);
+  if (idx && n) {
+    for (int64_t j = 0; j < n; j++)
+      if (idx[j] < 0 || idx[j] >= db->nseq) { set_error("batch: idx[%lld]=%lld out of range", (long long) j, (long long) idx[j]); return P7GPU_EINVAL; }
+    P7G_CUDA(cudaMemcpyAsync(base, idx, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return P7GPU_OK;
+}
+
+static int fetch_batch(p7gpu_ctx *ctx, const BatchBufs &b, float *sc, int32_t *status)
+{
+  if (b.n) {
+    if (sc)     P7G_CUDA(cudaMemcpyAsync(sc, b.d_sc, sizeof(float) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) P7G_CUDA(cudaMemcpyAsync(status, b.d_st, sizeof(int32_t) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  P7G_CUDA(cudaStreamSynchronize(ctx->stream));
+  return P7GPU_OK;
+}
+
+int p7gpu_ssvfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                          const int64_t *idx, int64_t n, float *sc, int32_t *status)
+{
+  if (!ctx || !prof || !db) return P7GPU_EINVAL;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  BatchBufs b;
+  P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
+  P7G_CHECK(launch_ssv(ctx, prof, db, b.d_idx, b.n, b.d_sc, b.d_st, nullptr, nullptr));
+  return fetch_batch(ctx, b, sc, status);
+}
+
+int p7gpu_msvfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                          const int64_t *idx, int64_t n, float *sc, int32_t *status)
+{
+  if (!ctx || !prof || !db) return P7GPU_EINVAL;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  BatchBufs b;
+  P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
+  P7G_CHECK(launch_ssv(ctx, prof, db, b.d_idx, b.n, b.d_sc, b.d_st, b.d_list, ctx->d_counters + 2));
+  P7G_CHECK(launch_msv_j(ctx, prof, db, b.d_list, ctx->d_counters + 2, b.n, false, nullptr, b.d_sc, b.d_st));
+  return fetch_batch(ctx, b, sc, status);
+}
+
+int p7gpu_msvfilter_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, void *d_sc, void *d_status)
+{
+  if (!ctx || !prof || !db || !d_sc || !d_status) return P7GPU_EINVAL;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = db->nseq;
+  P7G_CHECK(ensure_scratch2(ctx, (size_t) std::max<int64_t>(n, 1) * 16));
+  P7G_CHECK(launch_ssv(ctx, prof, db, nullptr, n, (float *) d_sc, (int32_t *) d_status, (int64_t *) ctx->d_scratch2, ctx->d_counters + 2));
+  P7G_CHECK(launch_msv_j(ctx, prof, db, (int64_t *) ctx->d_scratch2, ctx->d_counters + 2, n, false, nullptr, (float *) d_sc, (int32_t *) d_status));
+  return P7GPU_OK;
+}
+
+int p7gpu_vitfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                          const int64_t *idx, int64_t n, float *sc, int32_t *status)
+{
+  if (!ctx || !prof || !db) return P7GPU_EINVAL;
+  if (!prof->d_rw) { set_error("vitfilter: profile was uploaded without the Viterbi part"); return P7GPU_EINVAL; }
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  BatchBufs b;
+  P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
+  P7G_CHECK(launch_vit(ctx, prof, db, b.d_idx, b.n, b.d_sc, b.d_st));
+  return fetch_batch(ctx, b, sc, status);
+}
+
+// xmx blocks: target j gets (L_j+1)*6 floats at xmx + xmx_offsets[j]
+static int64_t xmx_extent(const p7gpu_seqdb *, const int64_t *xmx_offsets, int64_t n, const int32_t *h_len_of_j)
+{
+  int64_t ext = 0;
+  for (int64_t j = 0; j < n; j++) ext = std::max(ext, xmx_offsets[j] + (int64_t) (h_len_of_j[j] + 1) * P7GPU_NXCELLS);
+  return ext;
+}
+
+static int lengths_of(p7gpu_ctx *ctx, const p7gpu_seqdb *db, const int64_t *idx, int64_t n, std::vector<int32_t> &out)
+{
+  // host needs the lengths of the selected targets to size the specials; fetch them from the device copy
+  std::vector<int32_t> all;
+  out.resize(n);
+  if (!idx) { P7G_CUDA(cudaMemcpy(out.data(), db->d_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost)); return P7GPU_OK; }
+  for (int64_t j = 0; j < n; j++)
+    P7G_CUDA(cudaMemcpyAsync(&out[j], db->d_len + idx[j], sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  P7G_CUDA(cudaStreamSynchronize(ctx->stream));
+  return P7GPU_OK;
+}
+
+int p7gpu_forward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                        const int64_t *idx, int64_t n, float *sc, int32_t *status,
+                        float *xmx, const int64_t *xmx_offsets, float *totscale)
+{
+  if (!ctx || !prof || !db) return P7GPU_EINVAL;
+  if (!prof->d_rf) { set_error("forward: profile was uploaded without the Forward part"); return P7GPU_EINVAL; }
+  if (xmx && !xmx_offsets) return P7GPU_EINVAL;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  BatchBufs b;
+  P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
+  float *d_xmx = nullptr; int64_t *d_xoff = nullptr; float *d_tot = nullptr; int64_t ext = 0;
+  std::vector<int32_t> lens;
+  const size_t nb = (size_t) std::max<int64_t>(b.n, 1);
+  if (xmx) { P7G_CHECK(lengths_of(ctx, db, idx, b.n, lens)); ext = xmx_extent(db, xmx_offsets, b.n, lens.data()); }
+  const size_t off_bytes = (nb * 8 + 255) / 256 * 256, tot_bytes = (nb * 4 + 255) / 256 * 256;
+  P7G_CHECK(ensure_scratch2(ctx, off_bytes + tot_bytes + (size_t) ext * 4 + 256));
+  d_xoff = (int64_t *) ctx->d_scratch2; d_tot = (float *) ((char *) ctx->d_scratch2 + off_bytes);
+  if (xmx) {
+    d_xmx = (float *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes);
+    P7G_CUDA(cudaMemcpyAsync(d_xoff, xmx_offsets, sizeof(int64_t) * b.n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  P7G_CHECK(launch_fwd(ctx, prof, db, b.d_idx, b.n, b.d_sc, b.d_st, d_xmx, xmx ? d_xoff : nullptr, d_tot));
+  if (xmx && ext) P7G_CUDA(cudaMemcpyAsync(xmx, d_xmx, sizeof(float) * ext, cudaMemcpyDeviceToHost, ctx->stream));
+  if (totscale && b.n) P7G_CUDA(cudaMemcpyAsync(totscale, d_tot, sizeof(float) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
+  return fetch_batch(ctx, b, sc, status);
+}
+
+int p7gpu_backward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                         const int64_t *idx, int64_t n, const float *fwd_xmx, const int64_t *xmx_offsets,
+                         float *sc, int32_t *status, float *bck_xmx, float *bck_totscale)
+{
+  if (!ctx || !prof || !db || !fwd_xmx || !xmx_offsets) return P7GPU_EINVAL;
+  if (!prof->d_rf) { set_error("backward: profile was uploaded without the Forward part"); return P7GPU_EINVAL; }
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  BatchBufs b;
+  P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
+  std::vector<int32_t> lens;
+  P7G_CHECK(lengths_of(ctx, db, idx, b.n, lens));
+  const int64_t ext = xmx_extent(db, xmx_offsets, b.n, lens.data());
+  const size_t nb = (size_t) std::max<int64_t>(b.n, 1);
+  const size_t off_bytes = (nb * 8 + 255) / 256 * 256, tot_bytes = (nb * 4 + 255) / 256 * 256;
+  const size_t x_bytes = ((size_t) ext * 4 + 255) / 256 * 256;
+  P7G_CHECK(ensure_scratch2(ctx, off_bytes + tot_bytes + 2 * x_bytes + 256));
+  int64_t *d_xoff = (int64_t *) ctx->d_scratch2;
+  float *d_tot = (float *) ((char *) ctx->d_scratch2 + off_bytes);
+  float *d_fx  = (float *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes);
+  float *d_bx  = (float *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes + x_bytes);
+  P7G_CUDA(cudaMemcpyAsync(d_xoff, xmx_offsets, sizeof(int64_t) * b.n, cudaMemcpyHostToDevice, ctx->stream));
+  if (ext) P7G_CUDA(cudaMemcpyAsync(d_fx, fwd_xmx, sizeof(float) * ext, cudaMemcpyHostToDevice, ctx->stream));
+  P7G_CHECK(launch_bwd(ctx, prof, db, b.d_idx, b.n, d_fx, d_xoff, b.d_sc, b.d_st, d_bx, d_tot));
+  if (bck_xmx && ext) P7G_CUDA(cudaMemcpyAsync(bck_xmx, d_bx, sizeof(float) * ext, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bck_totscale && b.n) P7G_CUDA(cudaMemcpyAsync(bck_totscale, d_tot, sizeof(float) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
+  return fetch_batch(ctx, b, sc, status);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Signature-level wrappers: one target per call (impl_sse.h:309-344)
+// ---------------------------------------------------------------------------------------------------
+struct OneSeq { p7gpu_seqdb *db = nullptr; ~OneSeq() { p7gpu_seqdb_destroy(db); } };
+
+static int one_seq_db(p7gpu_ctx *ctx, const uint8_t *dsq, int L, OneSeq *one)
+{
+  if (!dsq || L < 0) return P7GPU_EINVAL;
+  int64_t off = 1; int32_t len = L;
+  return p7gpu_seqdb_upload(ctx, dsq, (int64_t) L + 2, &off, &len, 1, &one->db);
+}
+
+int p7gpu_SSVFilter(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om, float *ret_sc)
+{
+  OneSeq one; int32_t st = 0; float sc = 0;
+  P7G_CHECK(one_seq_db(ctx, dsq, L, &one));
+  P7G_CHECK(p7gpu_ssvfilter_batch(ctx, om, one.db, nullptr, 1, &sc, &st));
+  if (st != P7GPU_ENORESULT || std::isinf(sc)) *ret_sc = sc;
+  return st;
+}
+int p7gpu_MSVFilter(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om, float *ret_sc)
+{
+  OneSeq one; int32_t st = 0;
+  P7G_CHECK(one_seq_db(ctx, dsq, L, &one));
+  P7G_CHECK(p7gpu_msvfilter_batch(ctx, om, one.db, nullptr, 1, ret_sc, &st));
+  return st;
+}
+int p7gpu_ViterbiFilter(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om, float *ret_sc)
+{
+  OneSeq one; int32_t st = 0;
+  P7G_CHECK(one_seq_db(ctx, dsq, L, &one));
+  P7G_CHECK(p7gpu_vitfilter_batch(ctx, om, one.db, nullptr, 1, ret_sc, &st));
+  return st;
+}
+int p7gpu_ForwardParser(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
+                        float *fwd_xmx, float *fwd_totscale, float *opt_sc)
+{
+  OneSeq one; int32_t st = 0; float sc = 0; int64_t xoff = 0;
+  P7G_CHECK(one_seq_db(ctx, dsq, L, &one));
+  P7G_CHECK(p7gpu_forward_batch(ctx, om, one.db, nullptr, 1, &sc, &st, fwd_xmx, fwd_xmx ? &xoff : nullptr, fwd_totscale));
+  if (opt_sc) *opt_sc = sc;
+  return st;
+}
+int p7gpu_BackwardParser(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
+                         const float *fwd_xmx, float *bck_xmx, float *bck_totscale, float *opt_sc)
+{
+  OneSeq one; int32_t st = 0; float sc = 0; int64_t xoff = 0;
+  P7G_CHECK(one_seq_db(ctx, dsq, L, &one));
+  P7G_CHECK(p7gpu_backward_batch(ctx, om, one.db, nullptr, 1, fwd_xmx, &xoff, &sc, &st, bck_xmx, bck_totscale));
+  if (opt_sc) *opt_sc = sc;
+  return st;
+}
+
+float p7gpu_nullsc(int L)
+{
+  float p1 = (float) L / (float) (L + 1);
+  return (float) ((double) (float) L * log((double) p1) + log(1. - (double) p1));
+}
+
+// esl_gumbel_surv of (usc - nullsc)/ln2 (p7_pipeline.c:691-692; easel/esl_gumbel.c:129-138)
+double p7gpu_msv_pvalue(float usc, float nullsc, float mmu, float mlambda)
+{
+  float seq_score = (usc - nullsc) / 0.69314718055994529;
+  double y = (double) mlambda * ((double) seq_score - (double) mmu);
+  double ey = -exp(-y);
+  if (fabs(ey) < 5e-9) return -ey;
+  return 1 - exp(ey);
+}
+
+}  // extern "C"

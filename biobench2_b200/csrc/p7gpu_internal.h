@@ -1,0 +1,132 @@
+// p7gpu_internal.h — internal structures of libp7gpu.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <mutex>
+#include "../../include/p7gpu.h"
+
+namespace p7g {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+#define P7G_CUDA(call)                                                                           \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      p7g::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+      return P7GPU_ESYS;                                                                         \
+    }                                                                                            \
+  } while (0)
+#define P7G_CHECK(call)                                                                          \
+  do { int s__ = (call); if (s__ != P7GPU_OK) return s__; } while (0)
+
+// ---- geometry of the diagonal ("slot") layout used by the SSV and MSV kernels ------------------
+// A warp holds 64*Q slots: lane l, register q, half h  <->  diagonal start column l*Q + q + h*32*Q.
+// At DP row i the slot sits on column (start + i) mod P, P = 64*Q >= M+1; columns >= M are pad columns
+// whose gain is PADGAIN, which resets the running diagonal to the floor before it re-enters at k=1.
+// Q is odd so that the 32 lanes of one LDS.32 (stride Q words) hit 32 distinct banks.
+constexpr int DIAG_CHUNK   = 16;      // DP rows per unrolled chunk = one 16-byte residue load
+constexpr int PADRES       = 29;      // table row used for masked (out-of-sequence) rows: all PADGAIN
+constexpr int NTABROWS     = 30;      // Kp + 1
+constexpr int SSV_PADGAIN  = -20000;  // int16; |v| stays < 2^15 (overflow argument)
+constexpr int MAX_Q        = 65;      // M <= 64*65-1 = 4159
+
+struct DiagGeom {
+  int M, Q, P, rowWords;              // rowWords = P + DIAG_CHUNK + Q  (wrap-free reads inside one chunk)
+  size_t tableBytes() const { return (size_t) NTABROWS * rowWords * 4; }
+};
+DiagGeom diag_geom(int M);
+int dp_cells_per_lane(int M);       // smallest supported C with 32*C >= M (dp_common.cuh)
+
+// ---- per-target-length constants: what p7_oprofile_ReconfigLength()/p7_bg_SetLength() derive ----
+// (impl_sse/p7_oprofile.c:1085-1127, p7_bg.c:190-199,358-363), built on the host with the host libm.
+struct LenConst {
+  float   pmove;      // xf[N|C|J][MOVE]; LOOP = 1.0f - pmove
+  float   nullsc;     // p7_bg_NullOne
+  int16_t xw_move;    // xw[N|C|J][MOVE]
+  uint8_t tjb_b;
+  uint8_t pad;
+};
+
+// scalar parameters handed to kernels by value
+struct MsvScalars { int tbm_b, tec_b, base_b, bias_b; float scale_b; };
+struct VitScalars { int xw_E_move, xw_E_loop, base_w, ddbound_w; float scale_w; };
+struct FwdScalars { float xf_E_move, xf_E_loop; };
+
+}  // namespace p7g
+
+struct p7gpu_ctx {
+  int          device = 0;
+  int          sm_count = 0;
+  int          smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool         own_stream = false;
+  int64_t      launches = 0;
+  // device scratch: work counters / compaction counters
+  unsigned int *d_counters = nullptr;   // [16]
+  // growable scratch buffers (device + pinned host)
+  void  *d_scratch = nullptr;  size_t d_scratch_bytes = 0;
+  void  *h_pinned  = nullptr;  size_t h_pinned_bytes  = 0;
+  void  *d_scratch2 = nullptr; size_t d_scratch2_bytes = 0;
+};
+
+struct p7gpu_profile {
+  p7gpu_ctx *ctx = nullptr;
+  int M = 0, Kp = 0;
+  float nj = 0.f;
+  float evparam[6];
+  p7g::MsvScalars msv;
+  p7g::VitScalars vit;
+  p7g::FwdScalars fwd;
+  // SSV / MSV diagonal tables (device): [NTABROWS][rowWords] words = (int16 gain lo, int16 gain hi)
+  p7g::DiagGeom geom;
+  uint32_t *d_ssv_tab = nullptr;
+  uint32_t *d_msv_tab = nullptr;
+  // Viterbi (int16) and Forward/Backward (f32) k-space tables (device)
+  int       dpC = 0;                   // cells per lane of the row-synchronous kernels (dp_common.cuh)
+  int16_t  *d_rw = nullptr;            // [NTABROWS][dpC][32]  lane-transposed: node k = lane*dpC + j + 1
+  int16_t  *d_tw = nullptr;            // [8][dpC][32]
+  float    *d_rf = nullptr;            // [NTABROWS][dpC][32]
+  float    *d_tf = nullptr;            // [8][dpC][32]
+  // per-L constants
+  mutable std::mutex  len_mutex;
+  mutable int         len_cap = 0;
+  mutable p7g::LenConst *d_len = nullptr;
+  mutable std::vector<p7g::LenConst> h_len;
+  float scale_b = 0, scale_w = 0;
+};
+
+struct p7gpu_seqdb {
+  p7gpu_ctx *ctx = nullptr;
+  const uint8_t *d_res = nullptr;      // padded to a 16-byte multiple + 16 slack bytes
+  const int64_t *d_off = nullptr;
+  const int32_t *d_len = nullptr;
+  int32_t       *d_order = nullptr;    // targets sorted by length, longest first (work order)
+  int64_t nseq = 0, nbytes = 0, nres = 0;
+  int32_t max_length = 0;
+  bool owns = false;
+};
+
+namespace p7g {
+int ensure_len_table(const p7gpu_profile *prof, int Lmax);
+int ensure_scratch(p7gpu_ctx *ctx, size_t bytes);
+int ensure_scratch2(p7gpu_ctx *ctx, size_t bytes);
+int ensure_pinned(p7gpu_ctx *ctx, size_t bytes);
+
+// kernel launchers (ssv_msv.cu, vit.cu, fwdbwd.cu).  idx==nullptr: all targets in db->d_order order,
+// outputs indexed by target; idx!=nullptr (device pointer): outputs indexed by list position.
+int launch_ssv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+               float *d_sc, int32_t *d_status, int64_t *d_noresult_list, unsigned int *d_noresult_count);
+int launch_msv_j(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_list,
+                 const unsigned int *d_count, int64_t max_n, bool list_holds_positions, const int64_t *d_idx,
+                 float *d_sc, int32_t *d_status);
+int launch_vit(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+               float *d_sc, int32_t *d_status);
+int launch_fwd(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+               float *d_sc, int32_t *d_status, float *d_xmx, const int64_t *d_xmx_off, float *d_totscale);
+int launch_bwd(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+               const float *d_fwd_xmx, const int64_t *d_xmx_off, float *d_sc, int32_t *d_status,
+               float *d_bck_xmx, float *d_totscale);
+}  // namespace p7g

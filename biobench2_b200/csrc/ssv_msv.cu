@@ -1,0 +1,307 @@
+// ssv_msv.cu — sm_100a kernels for the 8-bit MSV stage of p7_Pipeline():
+//   ssv_kernel  : p7_SSVFilter  (HMMER/src/impl_sse/ssvfilter.c:833-926), all targets
+//   msvj_kernel : the J-state recursion of p7_MSVFilter (impl_sse/msvfilter.c:108-207) for the targets
+//                 where SSV answers eslENORESULT (msvfilter.c:105-106)
+//
+// One warp per target sequence, model states across lanes.  The DP lives in registers as 64*Q running
+// diagonals ("slots", 2 x int16 per register, DPX VIADDMNMX.S16x2 / VIMNMX3.S16x2); because the SSV
+// recurrence v(i,k) = max(floor, v(i-1,k-1) + gain[x_i][k]) has no row-to-row scalar, a slot simply
+// follows its diagonal and wraps through >= 1 pad column (gain = PADGAIN) that resets it to the floor:
+// no shuffles, no permutes.  The per-profile gain table is staged once per CTA in shared memory as
+// (lo,hi) int16 pairs laid out so that every LDS.32 of a warp is bank-conflict free (lane stride Q odd).
+#include "p7gpu_internal.h"
+#include <math_constants.h>
+
+namespace p7g {
+
+constexpr int SSV_THREADS = 256;
+constexpr int MSVJ_THREADS = 128;
+
+struct SsvParams {
+  const uint32_t *tab;          // [NTABROWS][rowWords]
+  int rowWords, P, M;
+  const uint8_t *res; const int64_t *off; const int32_t *len; const int32_t *order; const int64_t *idx;
+  long long n;
+  const LenConst *lc;
+  MsvScalars s;
+  float *sc; int32_t *status;
+  long long *nores_list;        // pairs (target, output slot), may be null
+  unsigned int *nores_count;
+  unsigned long long *work_counter;
+};
+
+__device__ __forceinline__ uint32_t patch_word(uint32_t w, long long wpos, long long o, long long end)
+{
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    long long pos = wpos + b;
+    if (pos < o || pos >= end) w = (w & ~(0xffu << (8 * b))) | ((uint32_t) PADRES << (8 * b));
+  }
+  return w;
+}
+
+__device__ __forceinline__ int hmax16(uint32_t x)
+{
+  int lo = (int) (short) (x & 0xffff), hi = (int) (short) (x >> 16);
+  return lo > hi ? lo : hi;
+}
+
+// The decision tree of p7_SSVFilter after get_xE (ssvfilter.c:884-925), on one lane.
+__device__ __forceinline__ int ssv_epilogue(int maxu, int tjb, const MsvScalars &s, float *ret_sc)
+{
+  int xE = 128 + maxu; if (xE > 255) xE = 255;
+  if (xE >= 255 - s.bias_b) {
+    *ret_sc = CUDART_INF_F;
+    return (s.base_b - tjb - s.tbm_b < 128) ? P7GPU_ENORESULT : P7GPU_ERANGE;
+  }
+  unsigned short xE16 = (unsigned short) (xE + s.base_b - tjb - s.tbm_b);
+  xE16 = (unsigned short) (xE16 - 128);
+  if (xE16 >= 255 - s.bias_b) { *ret_sc = CUDART_INF_F; return P7GPU_ERANGE; }
+  unsigned short xJ = (unsigned short) (xE16 - s.tec_b);
+  if (xJ > s.base_b) { *ret_sc = 0.0f; return P7GPU_ENORESULT; }
+  float sc = ((float) ((int) xJ - tjb) - (float) s.base_b);
+  sc = __fdiv_rn(sc, s.scale_b);
+  sc = __fsub_rn(sc, 3.0f);
+  *ret_sc = sc;
+  return P7GPU_OK;
+}
+
+template <int Q, bool SMEM>
+__global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvParams p)
+{
+  extern __shared__ __align__(16) uint32_t s_tab[];
+  if (SMEM) {
+    const int nwords = NTABROWS * p.rowWords;
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_tab[i] = __ldg(p.tab + i);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int P = p.P, rowWords = p.rowWords;
+  const int thresh = 127 - p.s.bias_b;          // u >= thresh  <=>  xE >= 255 - bias
+
+  for (;;) {
+    unsigned long long j = 0;
+    if (lane == 0) j = atomicAdd(p.work_counter, 1ULL);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= (unsigned long long) p.n) break;
+    const long long s   = p.idx ? p.idx[j] : (p.order ? (long long) p.order[j] : (long long) j);
+    const long long out = p.idx ? (long long) j : s;
+    const int       L   = p.len[s];
+    const long long o   = p.off[s];
+    const int       tjb = p.lc[L].tjb_b;
+
+    int status; float sc = 0.0f;
+    if (tjb + p.s.tbm_b + p.s.tec_b + p.s.bias_b >= 127) {      // ssvfilter.c:884
+      status = P7GPU_ENORESULT;
+    } else {
+      uint32_t v[Q];
+#pragma unroll
+      for (int q = 0; q < Q; q++) v[q] = 0u;
+      uint32_t xE = 0u;
+      int c = lane * Q;
+      const long long end = o + L;
+      long long pos = o & ~15LL;
+      uint4 cur = __ldg(reinterpret_cast<const uint4 *>(p.res + pos));
+      int since_check = 0;
+      for (; pos < end; pos += DIAG_CHUNK) {
+        uint4 nxt = cur;
+        if (pos + DIAG_CHUNK < end) nxt = __ldg(reinterpret_cast<const uint4 *>(p.res + pos + DIAG_CHUNK));
+        uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+        if (pos < o || pos + DIAG_CHUNK > end) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) w[b] = patch_word(w[b], pos + 4 * b, o, end);
+        }
+#pragma unroll
+        for (int r = 0; r < DIAG_CHUNK; r++) {
+          const uint32_t x = __byte_perm(w[r >> 2], 0u, 0x4440u | (r & 3));
+          uint32_t g[Q];
+          if (SMEM) {
+            const uint32_t *rowp = s_tab + x * rowWords + c + r;
+#pragma unroll
+            for (int q = 0; q < Q; q++) g[q] = rowp[q];
+          } else {
+            const uint32_t *rowp = p.tab + x * rowWords + c + r;
+#pragma unroll
+            for (int q = 0; q < Q; q++) g[q] = __ldg(rowp + q);
+          }
+#pragma unroll
+          for (int q = 0; q < Q; q++) v[q] = __viaddmax_s16x2(v[q], g[q], 0u);
+#pragma unroll
+          for (int q = 0; q + 1 < Q; q += 2) xE = __vimax3_s16x2(xE, v[q], v[q + 1]);
+          if (Q & 1) xE = __vmaxs2(xE, v[Q - 1]);
+        }
+        c += DIAG_CHUNK; if (c >= P) c -= P;
+        cur = nxt;
+        // once any cell reaches 255-bias the outcome is fixed (overflow); leaving early also keeps
+        // every int16 lane far from wrap-around (<= thresh + 64*bias < 2^15).
+        if (++since_check == 4) {
+          since_check = 0;
+          if (__any_sync(0xffffffffu, hmax16(xE) >= thresh)) break;
+        }
+      }
+      const int maxu = __reduce_max_sync(0xffffffffu, hmax16(xE));
+      status = ssv_epilogue(maxu, tjb, p.s, &sc);
+    }
+    if (lane == 0) {
+      p.sc[out] = sc;
+      p.status[out] = status;
+      if (status == P7GPU_ENORESULT && p.nores_list) {
+        unsigned int t = atomicAdd(p.nores_count, 1u);
+        p.nores_list[2 * (long long) t]     = s;
+        p.nores_list[2 * (long long) t + 1] = out;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MsvjParams {
+  const uint32_t *tab; int rowWords, P, M;
+  const uint8_t *res; const int64_t *off; const int32_t *len;
+  const long long *list; const unsigned int *count; long long fixed_n;   // list of (target, out) pairs
+  const LenConst *lc; MsvScalars s;
+  float *sc; int32_t *status;
+  unsigned long long *work_counter;
+};
+
+template <int Q>
+__global__ void __launch_bounds__(MSVJ_THREADS) msvj_kernel(const MsvjParams p)
+{
+  const int lane = threadIdx.x & 31;
+  const int P = p.P, rowWords = p.rowWords;
+  const long long n = p.count ? (long long) *p.count : p.fixed_n;
+  const uint32_t bias2 = (uint32_t) p.s.bias_b * 0x00010001u;
+  const uint32_t c255  = 255u * 0x00010001u;
+  for (;;) {
+    unsigned long long j = 0;
+    if (lane == 0) j = atomicAdd(p.work_counter, 1ULL);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if ((long long) j >= n) break;
+    const long long s = p.list[2 * j], out = p.list[2 * j + 1];
+    const int L = p.len[s];
+    const long long o = p.off[s];
+    const int tjb = p.lc[L].tjb_b;
+    const int tjbm = (int) (unsigned char) ((int) (signed char) tjb + (int) (signed char) p.s.tbm_b);   // msvfilter.c:118
+    uint32_t v[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q] = 0u;
+    int xJ = 0;
+    int xB = p.s.base_b - tjbm; if (xB < 0) xB = 0;
+    int c = lane * Q;
+    int status = P7GPU_OK;
+    for (int i = 0; i < L; i++) {
+      const uint32_t x = __ldg(p.res + o + i);
+      const uint32_t *rowp = p.tab + x * rowWords + c;
+      const uint32_t xB2 = (uint32_t) xB * 0x00010001u;
+      uint32_t xEv = 0u;
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        uint32_t a = __vmaxs2(v[q], xB2);                      // max(M(i-1,k-1), xB)
+        a = __viaddmin_s16x2(a, bias2, c255);                  // adds_epu8(., bias)
+        v[q] = __viaddmax_s16x2(a, __ldg(rowp + q), 0u);       // subs_epu8(., rbv)
+        xEv = __vmaxs2(xEv, v[q]);
+      }
+      c += 1; if (c >= P) c -= P;
+      int xE = __reduce_max_sync(0xffffffffu, hmax16(xEv));
+      if (xE + p.s.bias_b >= 255) { status = P7GPU_ERANGE; break; }       // msvfilter.c:157-182
+      xE -= p.s.tec_b; if (xE < 0) xE = 0;
+      if (xE > xJ) xJ = xE;
+      xB = (p.s.base_b > xJ ? p.s.base_b : xJ) - tjbm; if (xB < 0) xB = 0;
+    }
+    if (lane == 0) {
+      float sc;
+      if (status == P7GPU_ERANGE) sc = CUDART_INF_F;
+      else {
+        sc = ((float) (xJ - tjb) - (float) p.s.base_b);
+        sc = __fdiv_rn(sc, p.s.scale_b);
+        sc = __fsub_rn(sc, 3.0f);
+      }
+      p.sc[out] = sc;
+      p.status[out] = status;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int Q, bool SMEM>
+static int launch_ssv_q(p7gpu_ctx *ctx, const SsvParams &p, size_t tabBytes)
+{
+  auto kern = ssv_kernel<Q, SMEM>;
+  size_t smem = SMEM ? tabBytes : 0;
+  if (SMEM) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  int occ = 0;
+  P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSV_THREADS, smem));
+  if (occ < 1) { set_error("ssv_kernel<%d>: zero occupancy (smem %zu)", Q, smem); return P7GPU_ESYS; }
+  long long warps_needed = p.n;
+  long long blocks = (long long) ctx->sm_count * occ;
+  long long need_blocks = (warps_needed + (SSV_THREADS / 32) - 1) / (SSV_THREADS / 32);
+  if (need_blocks < blocks) blocks = need_blocks;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned) blocks, SSV_THREADS, smem, ctx->stream>>>(p);
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return P7GPU_OK;
+}
+
+#define P7G_ODD_Q_CASES(X) \
+  X(1) X(3) X(5) X(7) X(9) X(11) X(13) X(15) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31) X(33) \
+  X(35) X(37) X(39) X(41) X(43) X(45) X(47) X(49) X(51) X(53) X(55) X(57) X(59) X(61) X(63) X(65)
+
+int launch_ssv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+               float *d_sc, int32_t *d_status, int64_t *d_noresult_list, unsigned int *d_noresult_count)
+{
+  if (n <= 0) return P7GPU_OK;
+  P7G_CHECK(ensure_len_table(prof, db->max_length));
+  SsvParams p;
+  p.tab = prof->d_ssv_tab; p.rowWords = prof->geom.rowWords; p.P = prof->geom.P; p.M = prof->M;
+  p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.order = d_idx ? nullptr : db->d_order; p.idx = d_idx;
+  p.n = n; p.lc = prof->d_len; p.s = prof->msv; p.sc = d_sc; p.status = d_status;
+  p.nores_list = (long long *) d_noresult_list; p.nores_count = d_noresult_count;
+  p.work_counter = (unsigned long long *) (ctx->d_counters + 0);
+  P7G_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned int), ctx->stream));   // work counter (2 words) + spare
+  const size_t tabBytes = prof->geom.tableBytes();
+  const bool smem_ok = tabBytes + 1024 <= (size_t) ctx->smem_optin;
+  switch (prof->geom.Q) {
+#define X(QV) case QV: return smem_ok ? launch_ssv_q<QV, true>(ctx, p, tabBytes) : launch_ssv_q<QV, false>(ctx, p, tabBytes);
+    P7G_ODD_Q_CASES(X)
+#undef X
+  default: set_error("SSV: unsupported Q=%d (M=%d too large; max M is %d)", prof->geom.Q, prof->M, 64 * MAX_Q - 1); return P7GPU_EINVAL;
+  }
+}
+
+template <int Q>
+static int launch_msvj_q(p7gpu_ctx *ctx, const MsvjParams &p, long long max_n)
+{
+  long long blocks = (max_n + (MSVJ_THREADS / 32) - 1) / (MSVJ_THREADS / 32);
+  long long cap = (long long) ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  msvj_kernel<Q><<<(unsigned) blocks, MSVJ_THREADS, 0, ctx->stream>>>(p);
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return P7GPU_OK;
+}
+
+// d_list holds (target, output slot) pairs.  If d_count != nullptr the number of pairs is read on the device.
+int launch_msv_j(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_list,
+                 const unsigned int *d_count, int64_t max_n, bool, const int64_t *,
+                 float *d_sc, int32_t *d_status)
+{
+  if (max_n <= 0) return P7GPU_OK;
+  P7G_CHECK(ensure_len_table(prof, db->max_length));
+  MsvjParams p;
+  p.tab = prof->d_msv_tab; p.rowWords = prof->geom.rowWords; p.P = prof->geom.P; p.M = prof->M;
+  p.res = db->d_res; p.off = db->d_off; p.len = db->d_len;
+  p.list = (const long long *) d_list; p.count = d_count; p.fixed_n = max_n;
+  p.lc = prof->d_len; p.s = prof->msv; p.sc = d_sc; p.status = d_status;
+  p.work_counter = (unsigned long long *) (ctx->d_counters + 4);
+  P7G_CUDA(cudaMemsetAsync(ctx->d_counters + 4, 0, 2 * sizeof(unsigned int), ctx->stream));
+  switch (prof->geom.Q) {
+#define X(QV) case QV: return launch_msvj_q<QV>(ctx, p, max_n);
+    P7G_ODD_Q_CASES(X)
+#undef X
+  default: set_error("MSV: unsupported Q=%d", prof->geom.Q); return P7GPU_EINVAL;
+  }
+}
+
+}  // namespace p7g

@@ -1,0 +1,164 @@
+// vit.cu — sm_100a kernel for p7_ViterbiFilter (HMMER/src/impl_sse/vitfilter.c:83-249).
+//
+// One warp per target, lane l owns nodes k = l*C+1 .. l*C+C (dp_common.cuh).  The 16-bit saturating
+// arithmetic of the reference is reproduced exactly in 32-bit lanes with DPX VIADDMNMX (max(a+b,c)):
+// every adds_epi16(a,t) with t <= 0 equals max(a+t, -32768), and the only add that can saturate upward
+// (the emission) makes xE >= 32767, which returns eslERANGE for the row before the value is used again.
+// The lazy-F test of vitfilter.c:198-199 is evaluated as written; when it fires, the D->D fixed point
+// of :203-226 is obtained with a max-plus prefix scan over the warp (exact: see DESIGN.md).
+#include "dp_common.cuh"
+#include <math_constants.h>
+
+namespace p7g {
+
+struct VitParams {
+  DpCommon c;
+  const int16_t *rw;    // [NTABROWS][C][32]
+  const int16_t *tw;    // [8][C][32]
+  VitScalars s;
+};
+
+constexpr int VNEG = -32768;
+constexpr int VNOCARRY = -(1 << 28);
+
+template <int C, bool SMEM>
+__global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
+{
+  extern __shared__ __align__(16) int16_t s_vit[];
+  const int16_t *tw = p.tw, *rw = p.rw;
+  if (SMEM) {
+    const int ntw = 8 * C * 32, nrw = NTABROWS * C * 32;
+    for (int i = threadIdx.x; i < ntw; i += blockDim.x) s_vit[i] = p.tw[i];
+    for (int i = threadIdx.x; i < nrw; i += blockDim.x) s_vit[ntw + i] = p.rw[i];
+    __syncthreads();
+    tw = s_vit; rw = s_vit + ntw;
+  }
+  const int lane = threadIdx.x & 31;
+  const int16_t *tBM = tw + 0 * C * 32 + lane, *tMM = tw + 1 * C * 32 + lane, *tIM = tw + 2 * C * 32 + lane,
+                *tDM = tw + 3 * C * 32 + lane, *tMD = tw + 4 * C * 32 + lane, *tMI = tw + 5 * C * 32 + lane,
+                *tII = tw + 6 * C * 32 + lane, *tDD = tw + 7 * C * 32 + lane;
+
+  long long s, out;
+  while (next_target(p.c, lane, &s, &out)) {
+    const int L = p.c.len[s];
+    const uint8_t *seq = p.c.res + p.c.off[s];
+    const int xw_move = p.c.lc[L].xw_move;
+    int mp[C], ip[C], dp[C];
+#pragma unroll
+    for (int j = 0; j < C; j++) mp[j] = ip[j] = dp[j] = VNEG;
+    int xN = p.s.base_w, xB = (short) (xN + xw_move), xJ = VNEG, xC = VNEG, xE = VNEG;
+    int status = P7GPU_OK;
+
+    for (int i = 0; i < L; i++) {
+      const int x = __ldg(seq + i);
+      const int16_t *rwx = rw + (size_t) x * C * 32 + lane;
+      int pm = __shfl_up_sync(0xffffffffu, mp[C - 1], 1);
+      int pi = __shfl_up_sync(0xffffffffu, ip[C - 1], 1);
+      int pd = __shfl_up_sync(0xffffffffu, dp[C - 1], 1);
+      if (lane == 0) pm = pi = pd = VNEG;
+      int xEl = VNEG, Dml = VNEG, dcv = VNEG;
+#pragma unroll
+      for (int j = 0; j < C; j++) {
+        int sv = __viaddmax_s32(xB, (int) tBM[j * 32], VNEG);          // vitfilter.c:146-150
+        sv = __viaddmax_s32(pm, (int) tMM[j * 32], sv);
+        sv = __viaddmax_s32(pi, (int) tIM[j * 32], sv);
+        sv = __viaddmax_s32(pd, (int) tDM[j * 32], sv);
+        sv = __viaddmax_s32(sv, (int) rwx[j * 32], VNEG);
+        xEl = max(xEl, sv);
+        pm = mp[j]; pi = ip[j]; pd = dp[j];                           // :155-157
+        mp[j] = sv;
+        dp[j] = dcv;                                                  // D(i,k) = M(i,k-1)+tMD so far (:160-161)
+        dcv = __viaddmax_s32(sv, (int) tMD[j * 32], VNEG);            // :166
+        Dml = max(Dml, dcv);
+        ip[j] = __viaddmax_s32(pi, (int) tII[j * 32], __viaddmax_s32(pm, (int) tMI[j * 32], VNEG));   // :170-171
+      }
+      {
+        int d0 = __shfl_up_sync(0xffffffffu, dcv, 1);
+        dp[0] = (lane == 0) ? VNEG : d0;
+      }
+      xE = __reduce_max_sync(0xffffffffu, xEl);
+      if (xE >= 32767) { status = P7GPU_ERANGE; break; }              // :177
+      // specials: int arithmetic truncated to int16_t on assignment (:178-181); N/C/J loops are 0
+      xC = (short) max(xC, xE + p.s.xw_E_move);
+      xJ = (short) max(xJ, xE + p.s.xw_E_loop);
+      xB = (short) max(xJ + xw_move, xN + xw_move);
+      const int Dmax = __reduce_max_sync(0xffffffffu, Dml);
+      if (Dmax + p.s.ddbound_w > xB) {                                // lazy F, :198-232
+        // lane-local map from the carry offered to cell 0 to the carry offered to the next lane:
+        // out = max(A, c + T)
+        int A = VNOCARRY, T = 0;
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+          const int t = (int) tDD[j * 32];
+          A = max(dp[j], A) + t;
+          T += t;
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int A2 = __shfl_up_sync(0xffffffffu, A, d), T2 = __shfl_up_sync(0xffffffffu, T, d);
+          if (lane >= d) { A = max(A, A2 + T); T = max(T + T2, VNOCARRY); }
+        }
+        int carry = __shfl_up_sync(0xffffffffu, A, 1);
+        if (lane == 0) carry = VNOCARRY;
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+          dp[j] = max(dp[j], carry);
+          carry = dp[j] + (int) tDD[j * 32];
+        }
+      }
+    }
+    if (lane == 0) {
+      float sc;
+      if (status == P7GPU_ERANGE) sc = CUDART_INF_F;
+      else if (xC > -32768) {                                         // :240-247
+        sc = (float) xC + (float) xw_move - (float) p.s.base_w;
+        sc = __fdiv_rn(sc, p.s.scale_w);
+        sc = __fsub_rn(sc, 3.0f);
+      } else sc = -CUDART_INF_F;
+      p.c.sc[out] = sc;
+      p.c.status[out] = status;
+    }
+  }
+}
+
+template <int C>
+static int launch_vit_c(p7gpu_ctx *ctx, const VitParams &p)
+{
+  const size_t smem = (size_t) (8 + NTABROWS) * C * 32 * sizeof(int16_t);
+  const bool use_smem = smem + 1024 <= (size_t) ctx->smem_optin;
+  auto kern = use_smem ? vit_kernel<C, true> : vit_kernel<C, false>;
+  const size_t dyn = use_smem ? smem : 0;
+  if (use_smem) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+  int occ = 0;
+  P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DP_THREADS, dyn));
+  if (occ < 1) { set_error("vit_kernel<%d>: zero occupancy", C); return P7GPU_ESYS; }
+  long long blocks = (long long) ctx->sm_count * occ;
+  long long need = (p.c.n + (DP_THREADS / 32) - 1) / (DP_THREADS / 32);
+  if (need < blocks) blocks = need;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned) blocks, DP_THREADS, dyn, ctx->stream>>>(p);
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return P7GPU_OK;
+}
+
+int launch_vit(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+               float *d_sc, int32_t *d_status)
+{
+  if (n <= 0) return P7GPU_OK;
+  P7G_CHECK(ensure_len_table(prof, db->max_length));
+  VitParams p;
+  p.c.res = db->d_res; p.c.off = db->d_off; p.c.len = db->d_len; p.c.order = d_idx ? nullptr : db->d_order; p.c.idx = d_idx;
+  p.c.n = n; p.c.lc = prof->d_len; p.c.sc = d_sc; p.c.status = d_status;
+  p.c.work_counter = (unsigned long long *) (ctx->d_counters + 6);
+  p.rw = prof->d_rw; p.tw = prof->d_tw; p.s = prof->vit;
+  P7G_CUDA(cudaMemsetAsync(ctx->d_counters + 6, 0, 2 * sizeof(unsigned int), ctx->stream));
+  switch (prof->dpC) {
+#define X(CV) case CV: return launch_vit_c<CV>(ctx, p);
+    P7G_DP_C_CASES(X)
+#undef X
+  default: set_error("vit: unsupported cells-per-lane %d", prof->dpC); return P7GPU_EINVAL;
+  }
+}
+
+}  // namespace p7g

@@ -1,0 +1,282 @@
+"""ctypes binding of libp7gpu.so (include/p7gpu.h): the only way this package computes anything.
+
+There is deliberately no CPU path: if the shared library is missing, or no sm_100 device is present,
+every compute call raises.  (The CPU oracle lives in oracle/ and is test infrastructure.)
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from .oprofile import OProfileView
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp7gpu.so")
+
+OK, EMEM, EINVAL, ESYS, ERANGE, ENORESULT = 0, 5, 11, 12, 16, 19
+
+EXPORTS = [
+    "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
+    "p7gpu_ctx_launch_count", "p7gpu_ctx_synchronize",
+    "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M",
+    "p7gpu_seqdb_upload", "p7gpu_seqdb_adopt_device", "p7gpu_seqdb_destroy", "p7gpu_seqdb_nseq", "p7gpu_seqdb_nres",
+    "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
+    "p7gpu_backward_batch", "p7gpu_msvfilter_device",
+    "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser",
+    "p7gpu_pipeline_run", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
+    "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
+    "p7gpu_nullsc", "p7gpu_msv_pvalue",
+]
+
+
+class P7GpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libp7gpu status %d: %s" % (code, msg))
+        self.code = code
+
+
+class PipelineOpts(C.Structure):
+    _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double),
+                ("do_biasfilter", C.c_int32), ("do_max", C.c_int32), ("want_specials", C.c_int32)]
+
+
+class PipelineCounters(C.Structure):
+    _fields_ = [("nseqs", C.c_uint64), ("nres", C.c_uint64), ("n_past_msv", C.c_uint64), ("n_past_bias", C.c_uint64),
+                ("n_past_vit", C.c_uint64), ("n_past_fwd", C.c_uint64)]
+
+
+class Survivor(C.Structure):
+    _fields_ = [("seqidx", C.c_int64), ("L", C.c_int32), ("msv_status", C.c_int32), ("vit_status", C.c_int32),
+                ("usc", C.c_float), ("vfsc", C.c_float), ("fwdsc", C.c_float), ("bcksc", C.c_float),
+                ("nullsc", C.c_float), ("filtersc", C.c_float), ("fwd_totscale", C.c_float), ("bck_totscale", C.c_float),
+                ("xmx_offset", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libp7gpu.so; fail loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libp7gpu.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "or `make -C biobench2_b200/csrc`; this package has no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+        L.p7gpu_last_error.restype = C.c_char_p
+        L.p7gpu_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.p7gpu_ctx_destroy.argtypes = [vp]
+        L.p7gpu_ctx_set_stream.argtypes = [vp, vp]
+        L.p7gpu_ctx_launch_count.restype = i64
+        L.p7gpu_ctx_launch_count.argtypes = [vp]
+        L.p7gpu_ctx_synchronize.argtypes = [vp]
+        L.p7gpu_profile_upload.argtypes = [vp, C.POINTER(OProfileView), C.POINTER(vp)]
+        L.p7gpu_profile_destroy.argtypes = [vp]
+        L.p7gpu_profile_M.argtypes = [vp]
+        L.p7gpu_seqdb_upload.argtypes = [vp, vp, i64, vp, vp, i64, C.POINTER(vp)]
+        L.p7gpu_seqdb_adopt_device.argtypes = [vp, vp, i64, vp, vp, i64, i32, C.POINTER(vp)]
+        L.p7gpu_seqdb_destroy.argtypes = [vp]
+        L.p7gpu_seqdb_nseq.restype = i64
+        L.p7gpu_seqdb_nseq.argtypes = [vp]
+        L.p7gpu_seqdb_nres.restype = i64
+        L.p7gpu_seqdb_nres.argtypes = [vp]
+        for nm in ("p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch"):
+            getattr(L, nm).argtypes = [vp, vp, vp, vp, i64, vp, vp]
+        L.p7gpu_forward_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+        L.p7gpu_backward_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+        L.p7gpu_msvfilter_device.argtypes = [vp, vp, vp, vp, vp]
+        for nm in ("p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter"):
+            getattr(L, nm).argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
+        L.p7gpu_ForwardParser.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.p7gpu_BackwardParser.argtypes = [vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.p7gpu_pipeline_run.argtypes = [vp, vp, vp, C.POINTER(PipelineOpts), C.POINTER(vp)]
+        L.p7gpu_result_counters.restype = C.POINTER(PipelineCounters)
+        L.p7gpu_result_counters.argtypes = [vp]
+        L.p7gpu_result_nsurvivors.restype = i64
+        L.p7gpu_result_nsurvivors.argtypes = [vp]
+        L.p7gpu_result_survivors.restype = C.POINTER(Survivor)
+        L.p7gpu_result_survivors.argtypes = [vp]
+        L.p7gpu_result_fwd_xmx.restype = C.POINTER(C.c_float)
+        L.p7gpu_result_fwd_xmx.argtypes = [vp]
+        L.p7gpu_result_bck_xmx.restype = C.POINTER(C.c_float)
+        L.p7gpu_result_bck_xmx.argtypes = [vp]
+        L.p7gpu_result_destroy.argtypes = [vp]
+        L.p7gpu_nullsc.restype = C.c_float
+        L.p7gpu_nullsc.argtypes = [C.c_int]
+        L.p7gpu_msv_pvalue.restype = C.c_double
+        L.p7gpu_msv_pvalue.argtypes = [C.c_float] * 4
+        _lib = L
+    return _lib
+
+
+def _check(st):
+    if st != OK:
+        raise P7GpuError(st, lib().p7gpu_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count():
+    return lib().p7gpu_device_count()
+
+
+class Context:
+    """One per worker / GPU (cf. WORKER_INFO, HMMER/src/hmmsearch.c:36-44)."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _check(lib().p7gpu_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().p7gpu_ctx_destroy(self.h)
+            self.h = None
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().p7gpu_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        _check(lib().p7gpu_ctx_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return lib().p7gpu_ctx_launch_count(self.h)
+
+
+class Profile:
+    """GPU-resident repacked profile (p7gpu_profile)."""
+
+    def __init__(self, ctx, oprofile):
+        """`oprofile`: biobench2_b200.oprofile.OProfile, or anything with .view() -> p7gpu_oprofile_view."""
+        self.ctx = ctx
+        self._src = oprofile
+        v = oprofile.view()
+        if not isinstance(v, OProfileView):      # a structurally identical ctypes struct from elsewhere
+            v = C.cast(C.pointer(v), C.POINTER(OProfileView)).contents
+        h = C.c_void_p()
+        _check(lib().p7gpu_profile_upload(ctx.h, C.byref(v), C.byref(h)))
+        self.h = h
+        self.M = v.M
+        self.evparam = [float(x) for x in v.evparam]
+
+    def close(self):
+        if self.h:
+            lib().p7gpu_profile_destroy(self.h)
+            self.h = None
+
+
+class SeqDB:
+    """GPU-resident packed target database (p7gpu_seqdb)."""
+
+    def __init__(self, ctx, handle, nseq, keep=None):
+        self.ctx, self.h, self.nseq, self._keep = ctx, handle, nseq, keep
+
+    @classmethod
+    def upload(cls, ctx, packed):
+        h = C.c_void_p()
+        _check(lib().p7gpu_seqdb_upload(ctx.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
+                                        _p(packed.lengths), packed.nseq, C.byref(h)))
+        return cls(ctx, h, packed.nseq)
+
+    @classmethod
+    def adopt_torch(cls, ctx, residues_t, offsets_t, lengths_t, max_length):
+        """Wrap torch CUDA tensors (uint8 / int64 / int32) without copying; residues need >= 32 slack bytes."""
+        h = C.c_void_p()
+        nbytes = int(residues_t.numel()) - 32
+        _check(lib().p7gpu_seqdb_adopt_device(ctx.h, C.c_void_p(residues_t.data_ptr()), nbytes,
+                                              C.c_void_p(offsets_t.data_ptr()), C.c_void_p(lengths_t.data_ptr()),
+                                              int(lengths_t.numel()), int(max_length), C.byref(h)))
+        return cls(ctx, h, int(lengths_t.numel()), keep=(residues_t, offsets_t, lengths_t))
+
+    @property
+    def nres(self):
+        return lib().p7gpu_seqdb_nres(self.h)
+
+    def close(self):
+        if self.h:
+            lib().p7gpu_seqdb_destroy(self.h)
+            self.h = None
+
+
+def _stage(fn, ctx, prof, db, idx):
+    n = len(idx) if idx is not None else db.nseq
+    idx_a = np.ascontiguousarray(idx, np.int64) if idx is not None else None
+    sc = np.zeros(n, np.float32); st = np.zeros(n, np.int32)
+    _check(fn(ctx.h, prof.h, db.h, _p(idx_a), n, _p(sc), _p(st)))
+    return sc, st
+
+
+def ssvfilter_batch(ctx, prof, db, idx=None): return _stage(lib().p7gpu_ssvfilter_batch, ctx, prof, db, idx)
+def msvfilter_batch(ctx, prof, db, idx=None): return _stage(lib().p7gpu_msvfilter_batch, ctx, prof, db, idx)
+def vitfilter_batch(ctx, prof, db, idx=None): return _stage(lib().p7gpu_vitfilter_batch, ctx, prof, db, idx)
+
+
+def xmx_offsets_for(lengths):
+    l = np.asarray(lengths, np.int64)
+    return np.concatenate([[0], np.cumsum((l + 1) * 6)[:-1]]).astype(np.int64), int(((l + 1) * 6).sum())
+
+
+def forward_batch(ctx, prof, db, lengths, idx=None, want_xmx=True):
+    """lengths: host array of the selected targets' lengths (sizes the specials)."""
+    n = len(idx) if idx is not None else db.nseq
+    idx_a = np.ascontiguousarray(idx, np.int64) if idx is not None else None
+    sc = np.zeros(n, np.float32); st = np.zeros(n, np.int32); tot = np.zeros(n, np.float32)
+    xoff, ext = xmx_offsets_for(lengths)
+    xmx = np.zeros(max(ext, 1), np.float32) if want_xmx else None
+    _check(lib().p7gpu_forward_batch(ctx.h, prof.h, db.h, _p(idx_a), n, _p(sc), _p(st), _p(xmx),
+                                     _p(xoff) if want_xmx else None, _p(tot)))
+    return sc, st, xmx, xoff, tot
+
+
+def backward_batch(ctx, prof, db, fwd_xmx, xoff, idx=None):
+    n = len(idx) if idx is not None else db.nseq
+    idx_a = np.ascontiguousarray(idx, np.int64) if idx is not None else None
+    sc = np.zeros(n, np.float32); st = np.zeros(n, np.int32); tot = np.zeros(n, np.float32)
+    bx = np.zeros_like(fwd_xmx)
+    _check(lib().p7gpu_backward_batch(ctx.h, prof.h, db.h, _p(idx_a), n, _p(fwd_xmx), _p(xoff), _p(sc), _p(st), _p(bx), _p(tot)))
+    return sc, st, bx, tot
+
+
+def msvfilter_device(ctx, prof, db, d_sc_ptr, d_status_ptr):
+    """MSV stage with results left in HBM (device pointers to nseq floats / int32)."""
+    _check(lib().p7gpu_msvfilter_device(ctx.h, prof.h, db.h, C.c_void_p(d_sc_ptr), C.c_void_p(d_status_ptr)))
+
+
+# ---- signature-level wrappers (one target per call), same meaning as impl_sse.h:309-344 ----
+def _one(fn, ctx, dsq, L, prof):
+    sc = C.c_float(0)
+    dsq = np.ascontiguousarray(dsq, np.uint8)
+    st = fn(ctx.h, _p(dsq), L, prof.h, C.byref(sc))
+    if st not in (OK, ERANGE, ENORESULT):
+        _check(st)
+    return st, np.float32(sc.value)
+
+
+def p7_SSVFilter(ctx, dsq, L, om): return _one(lib().p7gpu_SSVFilter, ctx, dsq, L, om)
+def p7_MSVFilter(ctx, dsq, L, om): return _one(lib().p7gpu_MSVFilter, ctx, dsq, L, om)
+def p7_ViterbiFilter(ctx, dsq, L, om): return _one(lib().p7gpu_ViterbiFilter, ctx, dsq, L, om)
+
+
+def p7_ForwardParser(ctx, dsq, L, om):
+    sc = C.c_float(0); tot = C.c_float(0)
+    xmx = np.zeros((L + 1, 6), np.float32)
+    dsq = np.ascontiguousarray(dsq, np.uint8)
+    st = lib().p7gpu_ForwardParser(ctx.h, _p(dsq), L, om.h, _p(xmx), C.byref(tot), C.byref(sc))
+    if st not in (OK, ERANGE):
+        _check(st)
+    return st, np.float32(sc.value), xmx, np.float32(tot.value)
+
+
+def p7_BackwardParser(ctx, dsq, L, om, fwd_xmx):
+    sc = C.c_float(0); tot = C.c_float(0)
+    bx = np.zeros((L + 1, 6), np.float32)
+    dsq = np.ascontiguousarray(dsq, np.uint8)
+    fwd_xmx = np.ascontiguousarray(fwd_xmx, np.float32)
+    st = lib().p7gpu_BackwardParser(ctx.h, _p(dsq), L, om.h, _p(fwd_xmx), _p(bx), C.byref(tot), C.byref(sc))
+    if st not in (OK, ERANGE):
+        _check(st)
+    return st, np.float32(sc.value), bx, np.float32(tot.value)

@@ -58,6 +58,7 @@ def lib():
         L.p7ref_name.restype = C.c_char_p
         L.p7ref_name.argtypes = [C.c_void_p]
         L.p7ref_get_view.argtypes = [C.c_void_p, C.POINTER(OProfileView)]
+        L.p7ref_emit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.p7ref_digitize.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.p7ref_background.argtypes = [C.c_void_p, C.c_void_p]
         L.p7ref_get_filter_hmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -142,6 +143,12 @@ class RefProfile:
         if st != 0:
             raise ValueError("esl_abc_Digitize status %d" % st)
         return dsq
+
+    def emit(self, seed, Lcfg=350, maxL=20000):
+        """Sample a homolog from the profile; returns residue codes (no sentinels) or None."""
+        buf = np.zeros(maxL + 2, np.uint8)
+        n = lib().p7ref_emit(self.h, seed, Lcfg, _p(buf), maxL)
+        return None if n < 0 else buf[1:n + 1].copy()
 
     def background(self):
         f = np.zeros(20, dtype=np.float32)

@@ -144,6 +144,21 @@ void p7ref_get_view(void *vh, p7gpu_oprofile_view *v)
   for (s = 0; s < 20; s++) v->compo[s]   = om->compo[s];
 }
 
+/* sample a homologous target from the profile (p7_ProfileEmit, emit.c), length configured to Lcfg.
+ * Returns the sequence length (<= maxL) or -1; dsq receives sentinel-framed residues. */
+int p7ref_emit(void *vh, int seed, int Lcfg, uint8_t *dsq, int maxL)
+{
+  P7REF *h = vh; ESL_RANDOMNESS *r = esl_randomness_CreateFast(seed);
+  ESL_SQ *sq = esl_sq_CreateDigital(h->abc); int n = -1;
+  p7_ReconfigLength(h->gm, Lcfg);
+  if (p7_ProfileEmit(r, h->hmm, h->gm, h->bg, sq, NULL) == eslOK && sq->n <= maxL) {
+    n = (int) sq->n; memcpy(dsq, sq->dsq, n + 2);
+  }
+  p7_ReconfigLength(h->gm, 100);
+  esl_sq_Destroy(sq); esl_randomness_Destroy(r);
+  return n;
+}
+
 /* digitize text with the reference alphabet (esl_abc_Digitize); dsq must hold L+2 bytes */
 int p7ref_digitize(void *vh, const char *seq, uint8_t *dsq)
 {

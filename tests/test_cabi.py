@@ -1,0 +1,78 @@
+"""Host-side checks that need no GPU: the C-ABI library loads, exports every symbol include/p7gpu.h declares,
+fails loudly without a device, and the product never routes through the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from biobench2_b200 import engine, seqdb
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "p7gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(p7gpu_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(engine.EXPORTS) == declared
+
+
+def test_no_cpu_fallback_without_device():
+    if engine.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(engine.P7GpuError) as e:
+        engine.Context(0)
+    assert e.value.code == engine.ESYS
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under biobench2_b200/ may import, link, dlopen or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "biobench2_b200")
+    bad = re.compile(r"import\s+oracle|from\s+oracle|#include\s*[\"<][^\n]*oracle|liboracle|libp7ref|oracle/_ref|p7o_|p7ref_")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                txt = open(os.path.join(dp, f)).read()
+                assert not bad.search(txt), os.path.join(dp, f)
+
+
+def test_host_scalar_helpers_match_oracle():
+    from oracle import port
+    lib = engine.lib()
+    for L in (1, 2, 17, 350, 5000, 43786, 100000):
+        assert np.float32(lib.p7gpu_nullsc(L)).view(np.uint32) == np.float32(port.nullsc(L)).view(np.uint32)
+    assert lib.p7gpu_msv_pvalue(-13.17, -6.86, -11.87, 0.698) == port.gumbel_surv(
+        float(np.float32((np.float32(-13.17) - np.float32(-6.86)) / 0.69314718055994529)), float(np.float32(-11.87)), float(np.float32(0.698)))
+
+
+def test_packed_db_layout_and_sharding():
+    db = seqdb.synth_db(500, mean=120, seed=1)
+    assert db.residues[0] == 255
+    for s in (0, 1, 250, 499):
+        d = db.dsq(s)
+        assert d[0] == 255 and d[-1] == 255 and len(d) == db.lengths[s] + 2 and (d[1:-1] < 20).all()
+    cover = []
+    for r in range(4):
+        lo, hi = db.shard(r, 4)
+        cover.extend(range(lo, hi))
+        res = int(db.lengths[lo:hi].astype(np.int64).sum())
+        assert abs(res - db.nres / 4) < 0.1 * db.nres
+    assert cover == list(range(db.nseq))
+    sub = db.subset([3, 5])
+    assert np.array_equal(sub.dsq(1), db.dsq(5))
+
+
+def test_digitize_matches_easel_alphabet():
+    assert list(seqdb.digitize("ACDEFGHIKLMNPQRSTVWY-BJZOUX*~")) == list(range(29))
+    with pytest.raises(ValueError):
+        seqdb.digitize("AC1")
