@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — hmmsearch MSV-filter throughput (GCUPS) of libp7gpu.so on B200, with its roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's own SSE code on the host cores
+
+Workload (BASELINE.json configs[1]): ONE synthetic calibrated profile, M=400, against 10,000,000 iid
+background-frequency protein targets (log-normal lengths, mean 350) PER GPU (weak scaling: the database is sharded
+by sequence, every rank filters its own shard, survivors are gathered to rank 0 with NCCL).  A "step" is one pass of
+the MSV filter (p7_MSVFilter = SSV + the J-state recursion for eslENORESULT targets, plus the P-value test of
+p7_pipeline.c:691-693) over the rank's whole shard.  One cell = one (target residue, model node) pair, the
+reference's own Mc/s unit (p7_pipeline.c:1791-1792).
+
+`value`  : device-resident GCUPS (database already in HBM), CUDA events, max over ranks.
+`e2e`    : the same pass through the host-buffer C-ABI calls (p7gpu_seqdb_upload + p7gpu_msvfilter_batch): the packed
+           database is copied host->device and the scores/statuses device->host inside the timed region.
+The inputs (3.5 GB of residues per rank) are larger than L2 (126 MB), so no L2 flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LN2 = 0.69314718055994529
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nseq", type=int, default=10_000_000, help="targets per GPU")
+    ap.add_argument("--mean-len", type=int, default=350)
+    ap.add_argument("--profile", default="synth_M400")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="also time Viterbi/Forward/Backward on survivor-sized subsets")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic database, generated on the device from a seeded stream (numpy cannot make 3.5 G residues in reasonable time)
+# ---------------------------------------------------------------------------------------------------------------
+def synth_lengths_np(n, mean, seed):
+    from biobench2_b200 import seqdb
+    return seqdb.synth_lengths(n, mean, np.random.default_rng(seed))
+
+
+def synth_db_device(torch, dev, nseq, mean, seed):
+    """Packed layout of include/p7gpu.h §4 built in HBM: (residues u8 [nbytes+32], offsets i64, lengths i32)."""
+    from biobench2_b200 import seqdb
+    lengths = synth_lengths_np(nseq, mean, seed)
+    l64 = lengths.astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(l64 + 1)[:-1]]) + 1
+    nbytes = int(l64.sum()) + nseq + 1
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    cdf = torch.tensor(np.cumsum(seqdb.AMINO_FREQ / seqdb.AMINO_FREQ.sum()), dtype=torch.float32, device=dev)
+    res = torch.empty(nbytes + 32, dtype=torch.uint8, device=dev)
+    chunk = 1 << 28
+    for lo in range(0, nbytes, chunk):
+        hi = min(nbytes, lo + chunk)
+        u = torch.rand(hi - lo, generator=g, device=dev)
+        res[lo:hi] = torch.searchsorted(cdf, u, right=True).clamp_(max=19).to(torch.uint8)
+        del u
+    res[nbytes:] = 255
+    d_off = torch.from_numpy(offsets).to(dev)
+    d_len = torch.from_numpy(lengths).to(dev)
+    res[d_off - 1] = 255
+    res[nbytes - 1] = 255
+    return res, d_off, d_len, lengths, offsets, nbytes
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region (NVML)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._stop_evt = index, [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference on the host cores (oracle/_ref = unmodified HMMER 3.1b2 SSE build; else the C port)
+# ---------------------------------------------------------------------------------------------------------------
+class CpuMsv:
+    """p7_MSVFilter over a packed sample with every host core, each thread owning an om clone (hmmsearch.c:505-516)."""
+
+    def __init__(self, profile_name, M):
+        from oracle import ref
+        self.cores = os.cpu_count() or 1
+        try:
+            self.cores = len(os.sched_getaffinity(0))
+        except Exception:
+            pass
+        self.M = M
+        if ref.available():
+            self.kind = "reference"
+            self.p = ref.RefProfile.sample(M, 42, True) if profile_name.startswith("synth_M") else None
+            if self.p is None:
+                raise RuntimeError("reference arm supports the synthetic profiles only")
+        else:
+            from oracle import port
+            from biobench2_b200.oprofile import OProfile
+            self.kind = "port"
+            op = OProfile.load(os.path.join(ROOT, "tests", "golden", "prof_%s.npz" % profile_name))
+            self.p = port.OracleProfile(op.view(), op)
+            self.cores = 1
+
+    def run(self, hdb):
+        """returns (seconds, cells)"""
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            self.p.stage_batch("msv", hdb.residues, hdb.offsets, hdb.lengths, threads=self.cores)
+        else:
+            self.p.stage_batch("msv", hdb)
+        dt = time.perf_counter() - t0
+        return dt, float(self.M) * float(hdb.nres)
+
+
+def cpu_sample(nseq, mean, seed=4242):
+    from biobench2_b200 import seqdb
+    return seqdb.synth_db(nseq, mean=mean, seed=seed)
+
+
+def sized_cpu_sample(cpu, mean, target_seconds):
+    """Pick a sample size whose filter pass takes about target_seconds on this host."""
+    probe = cpu_sample(20000, mean)
+    dt, cells = cpu.run(probe)
+    dt, cells = cpu.run(probe)
+    rate = cells / dt
+    n = int(max(20000, min(4_000_000, target_seconds * rate / (cpu.M * mean))))
+    return cpu_sample(n, mean), n
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    M = int(args.profile.split("M")[-1])
+    cpu = CpuMsv(args.profile, M)
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    hdb, n = sized_cpu_sample(cpu, args.mean_len, per_step)
+    for _ in range(args.warmup):
+        cpu.run(hdb)
+    tot_t = tot_c = 0.0
+    for _ in range(args.steps):
+        dt, cells = cpu.run(hdb)
+        tot_t += dt; tot_c += cells
+    gcups = tot_c / tot_t / 1e9
+    sample = "%d iid targets (mean L=%d, %d residues) per step, p7_MSVFilter, %d threads" % (n, args.mean_len, hdb.nres, cpu.cores)
+    line = {"impl": "reference", "metric": "hmmsearch MSV-filter GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "MSV/SSV filter only: synthetic profile M=%s vs %d iid protein targets per GPU (mean L=%d), "
+                        "BASELINE.json configs[1]" % (args.profile.split("M")[-1], args.nseq, args.mean_len),
+            "profile": args.profile, "targets_per_gpu": args.nseq, "mean_length": args.mean_len,
+            "sharding": "by sequence, %d rank(s)" % world, "l2": "inputs_larger_than_L2 (no flush needed)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from biobench2_b200 import engine
+    from biobench2_b200.oprofile import OProfile
+    from biobench2_b200.seqdb import PackedDB
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libp7gpu has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    op = OProfile.load(os.path.join(ROOT, "tests", "golden", "prof_%s.npz" % args.profile))
+    M = op.M
+    ctx = engine.Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    prof = engine.Profile(ctx, op)
+
+    with torch.cuda.stream(stream):
+        res, d_off, d_len, lengths, offsets, nbytes = synth_db_device(torch, dev, args.nseq, args.mean_len, 42 + rank)
+    stream.synchronize()
+    db = engine.SeqDB.adopt_torch(ctx, res, d_off, d_len, int(lengths.max()))
+    nres = int(lengths.astype(np.int64).sum())
+    cells = float(M) * float(nres)
+    d_sc = torch.empty(args.nseq, dtype=torch.float32, device=dev)
+    d_st = torch.empty(args.nseq, dtype=torch.int32, device=dev)
+
+    # per-L MSV pass threshold on the score (p7_pipeline.c:691-693): P = gumbel_surv((usc - nullsc)/ln2) <= F1
+    lib = engine.lib()
+    Ls = np.arange(int(lengths.max()) + 1)
+    nullsc = np.array([lib.p7gpu_nullsc(int(L)) for L in Ls], np.float32)
+    d_null = torch.from_numpy(nullsc).to(dev)
+    mmu, mlambda = prof.evparam[0], prof.evparam[1]
+    F1 = 0.02
+
+    def gather_survivors():
+        """P-value test on the device + NCCL gather of the survivors' (index, score) records to rank 0."""
+        seq_score = (d_sc - d_null[d_len.long()]) / LN2
+        y = mlambda * (seq_score.double() - mmu)
+        P = 1.0 - torch.exp(-torch.exp(-y))
+        keep = (P <= F1) | torch.isinf(d_sc)
+        idx = torch.nonzero(keep).squeeze(1)
+        rec = torch.stack([idx.double() + rank * args.nseq, d_sc[idx].double()], 1)
+        if world == 1:
+            return int(idx.numel())
+        cnt = torch.tensor([idx.numel()], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        mx = int(max(int(c.item()) for c in cnts))
+        pad = torch.zeros((mx, 2), dtype=torch.float64, device=dev); pad[: rec.shape[0]] = rec
+        out = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, out, dst=0)
+        return int(sum(int(c.item()) for c in cnts))
+
+    def step():
+        engine.msvfilter_device(ctx, prof, db, d_sc.data_ptr(), d_st.data_ptr())
+        return gather_survivors()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            nsurv = step()
+        barrier()
+        clocks = ClockSampler(physical_gpu_index(local_rank)); clocks.start()
+        ctx.set_timing(True); ctx.reset_timing()
+        l0 = ctx.launches
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            nsurv = step()
+        e1.record(stream)
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = ctx.launches - l0
+        ssv_ms, ssv_n = ctx.kernel_time(engine.KERNEL_SSV)
+        msvj_ms, msvj_n = ctx.kernel_time(engine.KERNEL_MSVJ)
+        ctx.set_timing(False)
+        clk = clocks.finish()
+    total_cells = sum_over_ranks(cells)
+    value = total_cells * args.steps / (ms_total * 1e-3) / 1e9
+    statuses = torch.bincount(d_st.clamp(min=0), minlength=20).cpu().numpy()
+
+    # ---- roofline of the dominant kernel (ssv_kernel), measured live with CUDA events on the launching stream ----
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ssv_avg_ms = ssv_ms / max(1, ssv_n)
+    alg_bytes = nres + args.nseq * (8 + 4 + 4 + 4 + 4)      # dsq bytes + offset, length, order in; score, status out
+    hbm_achieved = alg_bytes / (ssv_avg_ms * 1e-3) / 1e9
+    int_peak, fp32_peak, lds_peak = ctx.measure_peaks()
+    ssv_gcups = cells / (ssv_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                "traffic": None, "kernel": "ssv_kernel", "avg_launch_ms": ssv_avg_ms,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "note": "the path moves 1 byte per M cells, so HBM is NOT the binding roof; see roofline_alu (integer issue)"}
+    roofline_alu = {"bound": "int16x2-alu", "kernel": "ssv_kernel", "achieved": ssv_gcups * 2.0, "peak": int_peak,
+                    "unit": "G int16 ops/s", "frac": ssv_gcups * 2.0 / int_peak if int_peak else None,
+                    "ops_per_cell": 2, "kernel_gcups": ssv_gcups, "lds_peak_gbs": lds_peak,
+                    "lds_achieved_gbs": ssv_gcups * 2.0, "fp32_nofma_peak_gflops": fp32_peak,
+                    "peak_source": "measured live (p7gpu_measure_peaks: dependent-free VIADDMNMX.S16x2 chains)"}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if args.e2e_steps > 0:
+        h_res = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        h_res.copy_(res[:nbytes]); torch.cuda.synchronize()
+        hdb = PackedDB(h_res.numpy(), offsets, lengths)
+        h_sc = torch.empty(args.nseq, dtype=torch.float32, pin_memory=True).numpy()
+        h_st = torch.empty(args.nseq, dtype=torch.int32, pin_memory=True).numpy()
+
+        def e2e_step():
+            d = engine.SeqDB.upload(ctx, hdb)
+            engine.msvfilter_batch_into(ctx, prof, d, h_sc, h_st)
+            d.close()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": total_cells * args.e2e_steps / dt / 1e9, "unit": "GCUPS", "steps": args.e2e_steps,
+               "h2d_bytes_per_step": int(nbytes + args.nseq * 12), "d2h_bytes_per_step": int(args.nseq * 8),
+               "ms_per_step": dt / args.e2e_steps * 1e3,
+               "api": "p7gpu_seqdb_upload(host packed DB) + p7gpu_msvfilter_batch(host sc/status)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = CpuMsv(args.profile, M)
+        sample_db, n = sized_cpu_sample(cpu, args.mean_len, args.cpu_seconds)
+        dt, c = cpu.run(sample_db)
+        cpu_baseline = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": cpu.cores, "kind": cpu.kind,
+                        "sample": "%d iid targets (mean L=%d, %d residues), p7_MSVFilter on %d threads, %.1f s"
+                                  % (n, args.mean_len, sample_db.nres, cpu.cores, dt)}
+
+    if rank == 0:
+        line = {"metric": "hmmsearch MSV-filter GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "roofline_alu": roofline_alu,
+                "cpu_baseline": cpu_baseline,
+                "detail": {"cells_per_step_per_gpu": cells, "residues_per_gpu": nres, "M": M,
+                           "ssv_launches": int(ssv_n), "ssv_ms_total": ssv_ms, "msvj_launches": int(msvj_n), "msvj_ms_total": msvj_ms,
+                           "msv_survivors_all_ranks": nsurv,
+                           "status_counts": {"ok": int(statuses[0]), "erange": int(statuses[16]), "noresult": int(statuses[19])}}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -309,7 +309,7 @@ static int launch_fb_c(p7gpu_ctx *ctx, const FbParams &p)
   long long need = (p.c.n + (DP_THREADS / 32) - 1) / (DP_THREADS / 32);
   if (need < blocks) blocks = need;
   if (blocks < 1) blocks = 1;
-  kern<<<(unsigned) blocks, DP_THREADS, dyn, ctx->stream>>>(p);
+  { LaunchTimer t(ctx, BWD ? P7GPU_KERNEL_BWD : P7GPU_KERNEL_FWD); kern<<<(unsigned) blocks, DP_THREADS, dyn, ctx->stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;

@@ -57,7 +57,14 @@ struct FwdScalars { float xf_E_move, xf_E_loop; };
 
 }  // namespace p7g
 
+// per-launch CUDA-event timing (p7gpu_ctx_set_timing): bench.py's live roofline measurement
+struct TimedLaunch { int kind; cudaEvent_t start, stop; };
+
 struct p7gpu_ctx {
+  bool         timing = false;
+  std::vector<TimedLaunch> timed;
+  double       kernel_ms[P7GPU_NKERNELS] = {0};
+  int64_t      kernel_launches[P7GPU_NKERNELS] = {0};
   int          device = 0;
   int          sm_count = 0;
   int          smem_optin = 0;
@@ -110,6 +117,16 @@ struct p7gpu_seqdb {
 };
 
 namespace p7g {
+// brackets one kernel launch with events on the launching stream when ctx->timing is on
+struct LaunchTimer {
+  p7gpu_ctx *ctx; int kind; cudaEvent_t start = nullptr, stop = nullptr;
+  LaunchTimer(p7gpu_ctx *c, int k) : ctx(c), kind(k) {
+    if (ctx->timing) { cudaEventCreate(&start); cudaEventCreate(&stop); cudaEventRecord(start, ctx->stream); }
+  }
+  ~LaunchTimer() {
+    if (start) { cudaEventRecord(stop, ctx->stream); ctx->timed.push_back({kind, start, stop}); }
+  }
+};
 int ensure_len_table(const p7gpu_profile *prof, int Lmax);
 int ensure_scratch(p7gpu_ctx *ctx, size_t bytes);
 int ensure_scratch2(p7gpu_ctx *ctx, size_t bytes);

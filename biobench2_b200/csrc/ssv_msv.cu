@@ -237,7 +237,7 @@ static int launch_ssv_q(p7gpu_ctx *ctx, const SsvParams &p, size_t tabBytes)
   long long need_blocks = (warps_needed + (SSV_THREADS / 32) - 1) / (SSV_THREADS / 32);
   if (need_blocks < blocks) blocks = need_blocks;
   if (blocks < 1) blocks = 1;
-  kern<<<(unsigned) blocks, SSV_THREADS, smem, ctx->stream>>>(p);
+  { LaunchTimer t(ctx, P7GPU_KERNEL_SSV); kern<<<(unsigned) blocks, SSV_THREADS, smem, ctx->stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;
@@ -276,7 +276,7 @@ static int launch_msvj_q(p7gpu_ctx *ctx, const MsvjParams &p, long long max_n)
   long long cap = (long long) ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  msvj_kernel<Q><<<(unsigned) blocks, MSVJ_THREADS, 0, ctx->stream>>>(p);
+  { LaunchTimer t(ctx, P7GPU_KERNEL_MSVJ); msvj_kernel<Q><<<(unsigned) blocks, MSVJ_THREADS, 0, ctx->stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;

@@ -13,10 +13,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libp7gpu.so")
 
 OK, EMEM, EINVAL, ESYS, ERANGE, ENORESULT = 0, 5, 11, 12, 16, 19
+KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD = range(5)
 
 EXPORTS = [
     "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
     "p7gpu_ctx_launch_count", "p7gpu_ctx_synchronize",
+    "p7gpu_ctx_set_timing", "p7gpu_ctx_reset_timing", "p7gpu_ctx_kernel_time", "p7gpu_measure_peaks",
     "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M",
     "p7gpu_seqdb_upload", "p7gpu_seqdb_adopt_device", "p7gpu_seqdb_destroy", "p7gpu_seqdb_nseq", "p7gpu_seqdb_nres",
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
@@ -70,6 +72,10 @@ def lib():
         L.p7gpu_ctx_launch_count.restype = i64
         L.p7gpu_ctx_launch_count.argtypes = [vp]
         L.p7gpu_ctx_synchronize.argtypes = [vp]
+        L.p7gpu_ctx_set_timing.argtypes = [vp, C.c_int]
+        L.p7gpu_ctx_reset_timing.argtypes = [vp]
+        L.p7gpu_ctx_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
+        L.p7gpu_measure_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.p7gpu_profile_upload.argtypes = [vp, C.POINTER(OProfileView), C.POINTER(vp)]
         L.p7gpu_profile_destroy.argtypes = [vp]
         L.p7gpu_profile_M.argtypes = [vp]
@@ -146,6 +152,24 @@ class Context:
     def launches(self):
         return lib().p7gpu_ctx_launch_count(self.h)
 
+    def set_timing(self, on=True):
+        _check(lib().p7gpu_ctx_set_timing(self.h, int(on)))
+
+    def reset_timing(self):
+        _check(lib().p7gpu_ctx_reset_timing(self.h))
+
+    def kernel_time(self, kind):
+        """(total ms, launches) of one kernel kind since reset_timing(); kinds: KERNEL_SSV .. KERNEL_BWD."""
+        ms = C.c_double(0); n = C.c_int64(0)
+        _check(lib().p7gpu_ctx_kernel_time(self.h, kind, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def measure_peaks(self):
+        """Measured issue peaks: (packed int16x2 add-max Gop/s, non-fused fp32 GFLOP/s, LDS.32 GB/s)."""
+        a = C.c_double(0); b = C.c_double(0); c = C.c_double(0)
+        _check(lib().p7gpu_measure_peaks(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
 
 class Profile:
     """GPU-resident repacked profile (p7gpu_profile)."""
@@ -213,6 +237,12 @@ def _stage(fn, ctx, prof, db, idx):
 def ssvfilter_batch(ctx, prof, db, idx=None): return _stage(lib().p7gpu_ssvfilter_batch, ctx, prof, db, idx)
 def msvfilter_batch(ctx, prof, db, idx=None): return _stage(lib().p7gpu_msvfilter_batch, ctx, prof, db, idx)
 def vitfilter_batch(ctx, prof, db, idx=None): return _stage(lib().p7gpu_vitfilter_batch, ctx, prof, db, idx)
+
+
+def msvfilter_batch_into(ctx, prof, db, sc, st):
+    """p7gpu_msvfilter_batch over the whole database into caller-owned (e.g. pinned) host arrays."""
+    assert sc.dtype == np.float32 and st.dtype == np.int32 and sc.shape[0] >= db.nseq and st.shape[0] >= db.nseq
+    _check(lib().p7gpu_msvfilter_batch(ctx.h, prof.h, db.h, None, db.nseq, _p(sc), _p(st)))
 
 
 def xmx_offsets_for(lengths):

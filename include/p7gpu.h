@@ -84,6 +84,23 @@ int         p7gpu_ctx_set_stream(p7gpu_ctx *ctx, void *cuda_stream);
 int64_t     p7gpu_ctx_launch_count(const p7gpu_ctx *ctx);
 int         p7gpu_ctx_synchronize(p7gpu_ctx *ctx);
 
+/* Diagnostics for bench.py's roofline line (no reference counterpart; cf. the Mc/s drivers msvfilter.c:512-600).
+ * With timing on, every kernel launch is bracketed by CUDA events on the launching stream;
+ * p7gpu_ctx_kernel_time() synchronises, folds the finished events in and returns the totals since the last
+ * p7gpu_ctx_reset_timing() for one kernel kind. */
+#define P7GPU_KERNEL_SSV  0
+#define P7GPU_KERNEL_MSVJ 1
+#define P7GPU_KERNEL_VIT  2
+#define P7GPU_KERNEL_FWD  3
+#define P7GPU_KERNEL_BWD  4
+#define P7GPU_NKERNELS    5
+int         p7gpu_ctx_set_timing  (p7gpu_ctx *ctx, int on);
+int         p7gpu_ctx_reset_timing(p7gpu_ctx *ctx);
+int         p7gpu_ctx_kernel_time (p7gpu_ctx *ctx, int kind, double *ms_total, int64_t *nlaunches);
+/* measured issue peaks of this device for the roofline denominators: packed int16x2 add-max (the SSV/MSV/Viterbi
+ * arithmetic), non-fused fp32 mul+add (Forward/Backward) and shared-memory LDS.32 bandwidth. */
+int         p7gpu_measure_peaks(p7gpu_ctx *ctx, double *int16x2_gops, double *fp32_gflops, double *lds_gbs);
+
 /* ------------------------------------------------------------------------------------------------
  * 3. Profile: replaces the consumer side of p7_oprofile_Convert()/p7_oprofile_Clone()
  *    (impl_sse/p7_oprofile.c:1004-1041, :403-420).  Per-target p7_oprofile_ReconfigLength()
