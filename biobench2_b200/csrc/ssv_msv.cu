@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvParams p)
   }
   const int lane = threadIdx.x & 31;
   const int P = p.P, rowWords = p.rowWords;
+  const uint32_t rowBytes = 4u * (uint32_t) rowWords;
+  const uint32_t tab_base = (uint32_t) __cvta_generic_to_shared(s_tab);
   const int thresh = 127 - p.s.bias_b;          // u >= thresh  <=>  xE >= 255 - bias
 
   for (;;) {
@@ -111,25 +113,34 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvParams p)
 #pragma unroll
           for (int b = 0; b < 4; b++) w[b] = patch_word(w[b], pos + 4 * b, o, end);
         }
+        // byte address of this lane's first slot in table row 0 for this chunk; row x adds x*rowBytes (one IMAD),
+        // the in-chunk row r and the slot q are immediate offsets of the LDS
+        const uint32_t cbase = tab_base + 4u * (uint32_t) c;
+        uint32_t pend = 0u; bool have_pend = false;
 #pragma unroll
         for (int r = 0; r < DIAG_CHUNK; r++) {
           const uint32_t x = __byte_perm(w[r >> 2], 0u, 0x4440u | (r & 3));
           uint32_t g[Q];
           if (SMEM) {
-            const uint32_t *rowp = s_tab + x * rowWords + c + r;
+            const uint32_t a = x * rowBytes + cbase;
 #pragma unroll
-            for (int q = 0; q < Q; q++) g[q] = rowp[q];
+            for (int q = 0; q < Q; q++) asm("ld.shared.u32 %0, [%1];" : "=r"(g[q]) : "r"(a + 4u * (uint32_t) (r + q)));
           } else {
             const uint32_t *rowp = p.tab + x * rowWords + c + r;
 #pragma unroll
             for (int q = 0; q < Q; q++) g[q] = __ldg(rowp + q);
           }
+          // v >= 0 always, so max(v+g, g, 0) == max(v+g, 0): the .RELU form needs no zero operand register
 #pragma unroll
-          for (int q = 0; q < Q; q++) v[q] = __viaddmax_s16x2(v[q], g[q], 0u);
+          for (int q = 0; q < Q; q++) v[q] = __viaddmax_s16x2_relu(v[q], g[q], g[q]);
+          // running maximum, two cells per VIMNMX3; an odd leftover waits for the next row (flag folds at compile time)
 #pragma unroll
-          for (int q = 0; q + 1 < Q; q += 2) xE = __vimax3_s16x2(xE, v[q], v[q + 1]);
-          if (Q & 1) xE = __vmaxs2(xE, v[Q - 1]);
+          for (int q = 0; q < Q; q++) {
+            if (have_pend) { xE = __vimax3_s16x2(xE, pend, v[q]); have_pend = false; }
+            else           { pend = v[q]; have_pend = true; }
+          }
         }
+        if (have_pend) { xE = __vmaxs2(xE, pend); have_pend = false; }
         c += DIAG_CHUNK; if (c >= P) c -= P;
         cur = nxt;
         // once any cell reaches 255-bias the outcome is fixed (overflow); leaving early also keeps
@@ -198,7 +209,7 @@ __global__ void __launch_bounds__(MSVJ_THREADS) msvj_kernel(const MsvjParams p)
       for (int q = 0; q < Q; q++) {
         uint32_t a = __vmaxs2(v[q], xB2);                      // max(M(i-1,k-1), xB)
         a = __viaddmin_s16x2(a, bias2, c255);                  // adds_epu8(., bias)
-        v[q] = __viaddmax_s16x2(a, __ldg(rowp + q), 0u);       // subs_epu8(., rbv)
+        { const uint32_t g = __ldg(rowp + q); v[q] = __viaddmax_s16x2_relu(a, g, g); }   // subs_epu8(., rbv); a >= 0
         xEv = __vmaxs2(xEv, v[q]);
       }
       c += 1; if (c >= P) c -= P;
