@@ -12,8 +12,9 @@ p7_pipeline.c:691-693) over the rank's whole shard.  One cell = one (target resi
 reference's own Mc/s unit (p7_pipeline.c:1791-1792).
 
 `value`  : device-resident GCUPS (database already in HBM), CUDA events, max over ranks.
-`e2e`    : the same pass through the host-buffer C-ABI calls (p7gpu_seqdb_upload + p7gpu_msvfilter_batch): the packed
-           database is copied host->device and the scores/statuses device->host inside the timed region.
+`e2e`    : the same pass through the host-buffer C-ABI call p7gpu_pipeline_run_host(stop_after_msv=1): the packed
+           database is copied host->device (streamed under the kernels) and the survivor records device->host inside the
+           timed region.
 The inputs (3.5 GB of residues per rank) are larger than L2 (126 MB), so no L2 flush is needed between steps.
 """
 import argparse
@@ -283,25 +284,20 @@ def main():
     d_sc = torch.empty(args.nseq, dtype=torch.float32, device=dev)
     d_st = torch.empty(args.nseq, dtype=torch.int32, device=dev)
 
-    # per-L MSV pass threshold on the score (p7_pipeline.c:691-693): P = gumbel_surv((usc - nullsc)/ln2) <= F1
-    lib = engine.lib()
-    Ls = np.arange(int(lengths.max()) + 1)
-    nullsc = np.array([lib.p7gpu_nullsc(int(L)) for L in Ls], np.float32)
-    d_null = torch.from_numpy(nullsc).to(dev)
-    mmu, mlambda = prof.evparam[0], prof.evparam[1]
+    # survivors of the P-value test (p7_pipeline.c:691-693) are compacted by the filter kernels themselves
     F1 = 0.02
+    d_pass = torch.empty(args.nseq, dtype=torch.int32, device=dev)
+    d_pass_count = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def gather_survivors():
-        """P-value test on the device + NCCL gather of the survivors' (index, score) records to rank 0."""
-        seq_score = (d_sc - d_null[d_len.long()]) / LN2
-        y = mlambda * (seq_score.double() - mmu)
-        P = 1.0 - torch.exp(-torch.exp(-y))
-        keep = (P <= F1) | torch.isinf(d_sc)
-        idx = torch.nonzero(keep).squeeze(1)
-        rec = torch.stack([idx.double() + rank * args.nseq, d_sc[idx].double()], 1)
+        """The multi-GPU exchange: every rank's survivor records (global index, score) go to rank 0 with one NCCL gather
+        (counts first, then the padded payload), like the MPI workers' hit return (hmmsearch.c:1242-1243)."""
+        n = int(d_pass_count.item())
         if world == 1:
-            return int(idx.numel())
-        cnt = torch.tensor([idx.numel()], dtype=torch.int64, device=dev)
+            return n
+        idx = d_pass[:n].long()
+        rec = torch.stack([(idx + rank * args.nseq).double(), d_sc[idx].double()], 1)
+        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
         cnts = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(cnts, cnt)
         mx = int(max(int(c.item()) for c in cnts))
@@ -311,7 +307,7 @@ def main():
         return int(sum(int(c.item()) for c in cnts))
 
     def step():
-        engine.msvfilter_device(ctx, prof, db, d_sc.data_ptr(), d_st.data_ptr())
+        engine.msvfilter_device(ctx, prof, db, d_sc.data_ptr(), d_st.data_ptr(), F1, d_pass.data_ptr(), d_pass_count.data_ptr())
         return gather_survivors()
 
     with torch.cuda.stream(stream):
@@ -361,13 +357,12 @@ def main():
         h_res = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         h_res.copy_(res[:nbytes]); torch.cuda.synchronize()
         hdb = PackedDB(h_res.numpy(), offsets, lengths)
-        h_sc = torch.empty(args.nseq, dtype=torch.float32, pin_memory=True).numpy()
-        h_st = torch.empty(args.nseq, dtype=torch.int32, pin_memory=True).numpy()
+
+        e2e_out = {}
 
         def e2e_step():
-            d = engine.SeqDB.upload(ctx, hdb)
-            engine.msvfilter_batch_into(ctx, prof, d, h_sc, h_st)
-            d.close()
+            r = engine.pipeline_run_host(ctx, prof, hdb, F1=F1, stop_after_msv=True)
+            e2e_out["survivors"] = len(r.msv_pass); e2e_out["counters"] = [int(x) for x in r.counters]
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -376,9 +371,10 @@ def main():
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": total_cells * args.e2e_steps / dt / 1e9, "unit": "GCUPS", "steps": args.e2e_steps,
-               "h2d_bytes_per_step": int(nbytes + args.nseq * 12), "d2h_bytes_per_step": int(args.nseq * 8),
-               "ms_per_step": dt / args.e2e_steps * 1e3,
-               "api": "p7gpu_seqdb_upload(host packed DB) + p7gpu_msvfilter_batch(host sc/status)"}
+               "h2d_bytes_per_step": int(nbytes + args.nseq * 12), "d2h_bytes_per_step": int(e2e_out["survivors"] * 24 + 4),
+               "ms_per_step": dt / args.e2e_steps * 1e3, "survivors": e2e_out["survivors"], "counters": e2e_out["counters"],
+               "api": "p7gpu_pipeline_run_host(stop_after_msv): pinned host packed DB streamed in 48 MB chunks under the "
+                      "SSV/MSV kernels; the MSV survivor records (index, L, status, score) come back to the host"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,70 @@
+// bias.cu — sm_100a kernel for the bias filter score of p7_Pipeline() (p7_pipeline.c:697-703):
+// p7_bg_FilterScore (HMMER/src/p7_bg.c:472-484) = esl_hmm_Forward on the 2-state filter HMM
+// (HMMER/easel/esl_hmm.c:351-409) plus the length term.  It runs on the ~2% of targets that pass the MSV filter.
+//
+// One thread per target: the recursion is a 2x2 matrix-vector product per residue with a per-row renormalisation
+// and a double-precision log() of the row maximum (float sc[i] = log(max), accumulated in float) — O(L) work with
+// no parallelism inside a target worth a warp.  Float operations are issued in the reference's order with explicit
+// round-to-nearest intrinsics (no FMA contraction); the L-dependent logf() terms come from the host-built per-L table.
+#include "p7gpu_internal.h"
+
+namespace p7g {
+
+struct BiasParams {
+  const uint8_t *res; const int64_t *off; const int32_t *len; const int64_t *idx; long long first; long long n;
+  const LenConst *lc;
+  BiasHmm h;
+  float *filtersc;
+};
+
+__global__ void __launch_bounds__(128) bias_kernel(const BiasParams p)
+{
+  const long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.n) return;
+  const long long s = p.idx ? p.idx[j] : p.first + j;
+  const int L = p.len[s];
+  const uint8_t *x = p.res + p.off[s];                 // x[i-1] = residue i
+  const float p1 = __fdiv_rn((float) L, (float) (L + 1));
+  const float t00 = p1, t01 = __fsub_rn(1.0f, p1);      // p7_bg_SetLength, p7_bg.c:193-196
+  const float t10 = p.h.t[1][0], t11 = p.h.t[1][1], t02 = p.h.t[0][2], t12 = p.h.t[1][2];
+  const float len_term_a = __fmul_rn((float) L, p.lc[L].logf_p1), len_term_b = p.lc[L].logf_1mp1;
+  float logsc = 0.0f;
+  if (L == 0) {                                        // esl_hmm.c:362-368 (not reached by the pipeline, :682)
+    p.filtersc[j] = __fadd_rn(__fadd_rn((float) log((double) p.h.pi[2]), len_term_a), len_term_b);
+    return;
+  }
+  float dp0 = __fmul_rn(p.h.eo[x[0]][0], p.h.pi[0]);
+  float dp1 = __fmul_rn(p.h.eo[x[0]][1], p.h.pi[1]);
+  float mx = 0.0f; if (dp0 > mx) mx = dp0; if (dp1 > mx) mx = dp1;
+  dp0 = __fdiv_rn(dp0, mx); dp1 = __fdiv_rn(dp1, mx);
+  logsc = __fadd_rn(logsc, (float) log((double) mx));
+  for (int i = 2; i <= L; i++) {
+    const int r = x[i - 1];
+    float n0 = __fadd_rn(0.0f, __fmul_rn(dp0, t00)); n0 = __fadd_rn(n0, __fmul_rn(dp1, t10)); n0 = __fmul_rn(n0, p.h.eo[r][0]);
+    float n1 = __fadd_rn(0.0f, __fmul_rn(dp0, t01)); n1 = __fadd_rn(n1, __fmul_rn(dp1, t11)); n1 = __fmul_rn(n1, p.h.eo[r][1]);
+    mx = 0.0f; if (n0 > mx) mx = n0; if (n1 > mx) mx = n1;
+    dp0 = __fdiv_rn(n0, mx); dp1 = __fdiv_rn(n1, mx);
+    logsc = __fadd_rn(logsc, (float) log((double) mx));
+  }
+  float last = __fadd_rn(0.0f, __fmul_rn(dp0, t02)); last = __fadd_rn(last, __fmul_rn(dp1, t12));
+  logsc = __fadd_rn(logsc, (float) log((double) last));
+  p.filtersc[j] = __fadd_rn(__fadd_rn(logsc, len_term_a), len_term_b);          // p7_bg.c:481
+}
+
+int launch_bias(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+                float *d_filtersc)
+{
+  if (n <= 0) return P7GPU_OK;
+  if (!prof->have_bias) { set_error("bias filter: the profile has no filter HMM (p7gpu_profile_set_biasfilter)"); return P7GPU_EINVAL; }
+  P7G_CHECK(ensure_len_table(prof, db.max_length));
+  const Lane &ln = ctx->lanes[lane];
+  BiasParams p;
+  p.res = db.res; p.off = db.off; p.len = db.len; p.idx = d_idx; p.first = db.first; p.n = n;
+  p.lc = prof->d_len; p.h = prof->bias; p.filtersc = d_filtersc;
+  { LaunchTimer t(ctx, P7GPU_KERNEL_BIAS, ln.stream); bias_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ln.stream>>>(p); }
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return P7GPU_OK;
+}
+
+}  // namespace p7g

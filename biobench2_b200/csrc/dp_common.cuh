@@ -13,6 +13,7 @@ constexpr int DP_THREADS = 128;
 
 struct DpCommon {
   const uint8_t *res; const int64_t *off; const int32_t *len; const int32_t *order; const int64_t *idx;
+  long long first;
   long long n;
   const LenConst *lc;
   float *sc; int32_t *status;
@@ -26,7 +27,7 @@ __device__ __forceinline__ bool next_target(const DpCommon &p, int lane, long lo
   if (lane == 0) j = atomicAdd(p.work_counter, 1ULL);
   j = __shfl_sync(0xffffffffu, j, 0);
   if (j >= (unsigned long long) p.n) return false;
-  *s   = p.idx ? p.idx[j] : (p.order ? (long long) p.order[j] : (long long) j);
+  *s   = p.idx ? p.idx[j] : (p.order ? (long long) p.order[j] : p.first + (long long) j);
   *out = p.idx ? (long long) j : *s;
   return true;
 }

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
 
 // ------------------------------------------------------------------------------------------------
 template <int C, bool BWD>
-static int launch_fb_c(p7gpu_ctx *ctx, const FbParams &p)
+static int launch_fb_c(p7gpu_ctx *ctx, cudaStream_t stream, const FbParams &p)
 {
   const size_t smem = (size_t) (8 + NTABROWS) * C * 32 * sizeof(float);
   const bool use_smem = smem + 1024 <= (size_t) ctx->smem_optin;
@@ -309,49 +309,51 @@ static int launch_fb_c(p7gpu_ctx *ctx, const FbParams &p)
   long long need = (p.c.n + (DP_THREADS / 32) - 1) / (DP_THREADS / 32);
   if (need < blocks) blocks = need;
   if (blocks < 1) blocks = 1;
-  { LaunchTimer t(ctx, BWD ? P7GPU_KERNEL_BWD : P7GPU_KERNEL_FWD); kern<<<(unsigned) blocks, DP_THREADS, dyn, ctx->stream>>>(p); }
+  { LaunchTimer t(ctx, BWD ? P7GPU_KERNEL_BWD : P7GPU_KERNEL_FWD, stream); kern<<<(unsigned) blocks, DP_THREADS, dyn, stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;
 }
 
-static int fill_common(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+static int fill_common(const Lane &ln, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                        float *d_sc, int32_t *d_status, int counter_slot, FbParams *p)
 {
-  P7G_CHECK(ensure_len_table(prof, db->max_length));
-  p->c.res = db->d_res; p->c.off = db->d_off; p->c.len = db->d_len; p->c.order = d_idx ? nullptr : db->d_order; p->c.idx = d_idx;
+  P7G_CHECK(ensure_len_table(prof, db.max_length));
+  p->c.res = db.res; p->c.off = db.off; p->c.len = db.len; p->c.order = d_idx ? nullptr : db.order; p->c.idx = d_idx; p->c.first = db.first;
   p->c.n = n; p->c.lc = prof->d_len; p->c.sc = d_sc; p->c.status = d_status;
-  p->c.work_counter = (unsigned long long *) (ctx->d_counters + counter_slot);
+  p->c.work_counter = (unsigned long long *) (ln.counters + counter_slot);
   p->rf = prof->d_rf; p->tf = prof->d_tf; p->s = prof->fwd;
-  P7G_CUDA(cudaMemsetAsync(ctx->d_counters + counter_slot, 0, 2 * sizeof(unsigned int), ctx->stream));
+  P7G_CUDA(cudaMemsetAsync(ln.counters + counter_slot, 0, 2 * sizeof(unsigned int), ln.stream));
   return P7GPU_OK;
 }
 
-int launch_fwd(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                float *d_sc, int32_t *d_status, float *d_xmx, const int64_t *d_xmx_off, float *d_totscale)
 {
   if (n <= 0) return P7GPU_OK;
+  const Lane &ln = ctx->lanes[lane];
   FbParams p;
-  P7G_CHECK(fill_common(ctx, prof, db, d_idx, n, d_sc, d_status, 8, &p));
+  P7G_CHECK(fill_common(ln, prof, db, d_idx, n, d_sc, d_status, CTR_FWD_WORK, &p));
   p.xmx = d_xmx; p.fwd_xmx = nullptr; p.xmx_off = d_xmx_off; p.totscale = d_totscale;
   switch (prof->dpC) {
-#define X(CV) case CV: return launch_fb_c<CV, false>(ctx, p);
+#define X(CV) case CV: return launch_fb_c<CV, false>(ctx, ln.stream, p);
     P7G_DP_C_CASES(X)
 #undef X
   default: set_error("fwd: unsupported cells-per-lane %d", prof->dpC); return P7GPU_EINVAL;
   }
 }
 
-int launch_bwd(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+int launch_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                const float *d_fwd_xmx, const int64_t *d_xmx_off, float *d_sc, int32_t *d_status,
                float *d_bck_xmx, float *d_totscale)
 {
   if (n <= 0) return P7GPU_OK;
+  const Lane &ln = ctx->lanes[lane];
   FbParams p;
-  P7G_CHECK(fill_common(ctx, prof, db, d_idx, n, d_sc, d_status, 10, &p));
+  P7G_CHECK(fill_common(ln, prof, db, d_idx, n, d_sc, d_status, CTR_BWD_WORK, &p));
   p.xmx = d_bck_xmx; p.fwd_xmx = d_fwd_xmx; p.xmx_off = d_xmx_off; p.totscale = d_totscale;
   switch (prof->dpC) {
-#define X(CV) case CV: return launch_fb_c<CV, true>(ctx, p);
+#define X(CV) case CV: return launch_fb_c<CV, true>(ctx, ln.stream, p);
     P7G_DP_C_CASES(X)
 #undef X
   default: set_error("bwd: unsupported cells-per-lane %d", prof->dpC); return P7GPU_EINVAL;

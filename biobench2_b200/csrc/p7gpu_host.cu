@@ -67,30 +67,84 @@ static int16_t wordify(float scale_w, float sc)
   else if (sc <= -32768.0) return -32768;
   else return (int16_t) sc;
 }
-static LenConst len_const(const p7gpu_profile *prof, int L)
+float host_nullsc(int L)                                   // p7_bg_NullOne, p7_bg.c:358-363 (double math, float result)
+{
+  float p1 = (float) L / (float) (L + 1);
+  return (float) ((double) (float) L * log((double) p1) + log(1. - (double) p1));
+}
+double host_gumbel_surv(double x, double mu, double lambda)   // easel/esl_gumbel.c:129-138
+{
+  double y = lambda * (x - mu), ey = -exp(-y);
+  if (fabs(ey) < 5e-9) return -ey;
+  return 1 - exp(ey);
+}
+double host_exp_surv(double x, double mu, double lambda)      // easel/esl_exponential.c:127-132
+{
+  if (x < mu) return 1.0;
+  return exp(-lambda * (x - mu));
+}
+// seq_score = (sc - nullsc) / eslCONST_LOG2 is a float in the reference (p7_pipeline.c:691,699,720,728)
+double host_filter_pvalue_gumbel(float sc, float nullsc, float mu, float lambda)
+{
+  float seq_score = (sc - nullsc) / 0.69314718055994529;
+  return host_gumbel_surv((double) seq_score, (double) mu, (double) lambda);
+}
+double host_filter_pvalue_exp(float sc, float filtersc, float tau, float lambda)
+{
+  float seq_score = (sc - filtersc) / 0.69314718055994529;
+  return host_exp_surv((double) seq_score, (double) tau, (double) lambda);
+}
+
+// MSV score as a function of the final xJ byte (ssvfilter.c:921-923 == msvfilter.c:205-207)
+static float msv_score_of_xj(const p7gpu_profile *prof, int xJ, int tjb)
+{
+  float sc = ((float) (xJ - tjb) - (float) prof->msv.base_b);
+  sc /= prof->msv.scale_b;
+  sc -= 3.0f;
+  return sc;
+}
+
+static LenConst len_const(const p7gpu_profile *prof, int L, double F1)
 {
   LenConst c;
   c.tjb_b   = byteify_cost(prof->scale_b, logf(3.0f / (float) (L + 3)));
   c.pmove   = (2.0f + prof->nj) / ((float) L + 2.0f + prof->nj);
   c.xw_move = wordify(prof->scale_w, logf(c.pmove));
   float p1  = (float) L / (float) (L + 1);
-  c.nullsc  = (float) ((double) (float) L * log((double) p1) + log(1. - (double) p1));
-  c.pad = 0;
+  c.nullsc  = host_nullsc(L);
+  c.pad = 0; c.pad2 = 0;
+  c.logf_p1 = logf(p1);
+  c.logf_1mp1 = logf(1. - p1);
+  // smallest xJ whose P-value passes: P(xJ) is non-increasing in xJ, so bisect, then verify the boundary pair with
+  // the reference expression itself (p7_pipeline.c:691-693: fail iff P > F1)
+  if (L == 0) c.msv_xj_min = 256;                                       // p7_pipeline.c:682: empty targets never enter
+  else {
+    auto passes = [&](int xJ) { return !(host_filter_pvalue_gumbel(msv_score_of_xj(prof, xJ, c.tjb_b), c.nullsc, prof->evparam[0], prof->evparam[1]) > F1); };
+    int lo = 0, hi = 256;                                               // invariant: everything >= hi passes (256 = none)
+    while (lo < hi) { int mid = (lo + hi) / 2; if (passes(mid)) hi = mid; else lo = mid + 1; }
+    while (hi > 0 && passes(hi - 1)) hi--;                              // (never iterates unless libm is non-monotone)
+    c.msv_xj_min = (uint16_t) hi;
+  }
   return c;
 }
 
-int ensure_len_table(const p7gpu_profile *prof, int Lmax)
+int ensure_len_table(const p7gpu_profile *prof, int Lmax, double F1)
 {
   std::lock_guard<std::mutex> lock(prof->len_mutex);
+  if (F1 < 0) F1 = prof->len_F1 >= 0 ? prof->len_F1 : DEFAULT_F1;
+  if (F1 != prof->len_F1) {                                             // thresholds changed: rebuild everything
+    if (prof->d_len) { P7G_CUDA(cudaDeviceSynchronize()); cudaFree(prof->d_len); prof->d_len = nullptr; }
+    prof->len_cap = 0; prof->h_len.clear(); prof->len_F1 = F1;
+  }
   if (Lmax < prof->len_cap) return P7GPU_OK;
   int cap = std::max(Lmax + 1, std::max(4096, prof->len_cap * 2));
   prof->h_len.resize(cap);
-  for (int L = prof->len_cap; L < cap; L++) prof->h_len[L] = len_const(prof, L);
+  for (int L = prof->len_cap; L < cap; L++) prof->h_len[L] = len_const(prof, L, F1);
   LenConst *d_new = nullptr;
   P7G_CUDA(cudaMalloc(&d_new, sizeof(LenConst) * cap));
   P7G_CUDA(cudaMemcpyAsync(d_new, prof->h_len.data(), sizeof(LenConst) * cap, cudaMemcpyHostToDevice, prof->ctx->stream));
   P7G_CUDA(cudaStreamSynchronize(prof->ctx->stream));
-  if (prof->d_len) cudaFree(prof->d_len);
+  if (prof->d_len) { P7G_CUDA(cudaDeviceSynchronize()); cudaFree(prof->d_len); }
   prof->d_len = d_new;
   prof->len_cap = cap;
   return P7GPU_OK;
@@ -141,10 +195,19 @@ int p7gpu_ctx_create(int device, p7gpu_ctx **ret_ctx)
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = (int) prop.sharedMemPerBlockOptin;
-  P7G_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (int l = 0; l < NLANES; l++) {
+    P7G_CUDA(cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking));
+    P7G_CUDA(cudaMalloc(&ctx->lanes[l].counters, LANE_COUNTER_WORDS * sizeof(unsigned int)));
+    P7G_CUDA(cudaMemset(ctx->lanes[l].counters, 0, LANE_COUNTER_WORDS * sizeof(unsigned int)));
+  }
+  P7G_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  {  // keep stream-ordered allocations (pipeline scratch) cached in the pool instead of returning them at every sync
+    cudaMemPool_t pool; uint64_t thr = UINT64_MAX;
+    P7G_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    P7G_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+  ctx->stream = ctx->lanes[0].stream;
   ctx->own_stream = true;
-  P7G_CUDA(cudaMalloc(&ctx->d_counters, 16 * sizeof(unsigned int)));
-  P7G_CUDA(cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned int)));
   *ret_ctx = ctx;
   return P7GPU_OK;
 }
@@ -153,12 +216,16 @@ void p7gpu_ctx_destroy(p7gpu_ctx *ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  cudaDeviceSynchronize();
+  for (int l = 0; l < NLANES; l++) {
+    if (ctx->lanes[l].counters) cudaFree(ctx->lanes[l].counters);
+    if (ctx->lanes[l].stream && (l > 0 || ctx->own_stream)) cudaStreamDestroy(ctx->lanes[l].stream);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto &t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -168,6 +235,7 @@ int p7gpu_ctx_set_stream(p7gpu_ctx *ctx, void *cuda_stream)
   P7G_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = (cudaStream_t) cuda_stream;
+  ctx->lanes[0].stream = ctx->stream;
   ctx->own_stream = false;
   return P7GPU_OK;
 }
@@ -289,7 +357,8 @@ __global__ void iota_kernel(int32_t *v, int64_t n)
   if (i < n) v[i] = (int32_t) i;
 }
 
-static int build_order(p7gpu_ctx *ctx, p7gpu_seqdb *db)
+}  // extern "C"
+int p7g::build_order(p7gpu_ctx *ctx, p7gpu_seqdb *db)
 {
   const int64_t n = db->nseq;
   if (n == 0) return P7GPU_OK;
@@ -307,6 +376,7 @@ static int build_order(p7gpu_ctx *ctx, p7gpu_seqdb *db)
   cudaFree(d_tmp); cudaFree(d_keys_out); cudaFree(d_iota);
   return P7GPU_OK;
 }
+extern "C" {
 
 int p7gpu_seqdb_upload(p7gpu_ctx *ctx, const uint8_t *residues, int64_t nbytes, const int64_t *offsets,
                        const int32_t *lengths, int64_t nseq, p7gpu_seqdb **ret_db)
@@ -414,7 +484,7 @@ int p7gpu_ssvfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu
   P7G_CUDA(cudaSetDevice(ctx->device));
   BatchBufs b;
   P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
-  P7G_CHECK(launch_ssv(ctx, prof, db, b.d_idx, b.n, b.d_sc, b.d_st, nullptr, nullptr));
+  P7G_CHECK(launch_ssv(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc, b.d_st, nullptr, nullptr, nullptr, nullptr));
   return fetch_batch(ctx, b, sc, status);
 }
 
@@ -425,20 +495,48 @@ int p7gpu_msvfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu
   P7G_CUDA(cudaSetDevice(ctx->device));
   BatchBufs b;
   P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
-  P7G_CHECK(launch_ssv(ctx, prof, db, b.d_idx, b.n, b.d_sc, b.d_st, b.d_list, ctx->d_counters + 2));
-  P7G_CHECK(launch_msv_j(ctx, prof, db, b.d_list, ctx->d_counters + 2, b.n, false, nullptr, b.d_sc, b.d_st));
+  unsigned int *d_nores = ctx->lanes[0].counters + CTR_NORES_COUNT;
+  P7G_CHECK(launch_ssv(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc, b.d_st, b.d_list, d_nores, nullptr, nullptr));
+  P7G_CHECK(launch_msv_j(ctx, 0, prof, db->view(), b.d_list, d_nores, b.n, b.d_sc, b.d_st, nullptr, nullptr));
   return fetch_batch(ctx, b, sc, status);
 }
 
-int p7gpu_msvfilter_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, void *d_sc, void *d_status)
+int p7gpu_msvfilter_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, double F1,
+                           void *d_sc, void *d_status, void *d_pass_list, void *d_pass_count)
 {
-  if (!ctx || !prof || !db || !d_sc || !d_status) return P7GPU_EINVAL;
+  if (!ctx || !prof || !db || !d_sc || !d_status || ((d_pass_list == nullptr) != (d_pass_count == nullptr))) return P7GPU_EINVAL;
   P7G_CUDA(cudaSetDevice(ctx->device));
   const int64_t n = db->nseq;
+  P7G_CHECK(ensure_len_table(prof, db->max_length, F1));
   P7G_CHECK(ensure_scratch2(ctx, (size_t) std::max<int64_t>(n, 1) * 16));
-  P7G_CHECK(launch_ssv(ctx, prof, db, nullptr, n, (float *) d_sc, (int32_t *) d_status, (int64_t *) ctx->d_scratch2, ctx->d_counters + 2));
-  P7G_CHECK(launch_msv_j(ctx, prof, db, (int64_t *) ctx->d_scratch2, ctx->d_counters + 2, n, false, nullptr, (float *) d_sc, (int32_t *) d_status));
+  unsigned int *d_nores = ctx->lanes[0].counters + CTR_NORES_COUNT;
+  if (d_pass_count) P7G_CUDA(cudaMemsetAsync(d_pass_count, 0, sizeof(unsigned int), ctx->stream));
+  P7G_CHECK(launch_ssv(ctx, 0, prof, db->view(), nullptr, n, (float *) d_sc, (int32_t *) d_status, (int64_t *) ctx->d_scratch2, d_nores,
+                       (int32_t *) d_pass_list, (unsigned int *) d_pass_count));
+  P7G_CHECK(launch_msv_j(ctx, 0, prof, db->view(), (int64_t *) ctx->d_scratch2, d_nores, n, (float *) d_sc, (int32_t *) d_status,
+                         (int32_t *) d_pass_list, (unsigned int *) d_pass_count));
   return P7GPU_OK;
+}
+
+int p7gpu_profile_set_biasfilter(p7gpu_profile *prof, const float *t6, const float *pi3, const float *eo)
+{
+  if (!prof || !t6 || !pi3 || !eo) return P7GPU_EINVAL;
+  memcpy(prof->bias.t, t6, sizeof(float) * 6);
+  memcpy(prof->bias.pi, pi3, sizeof(float) * 3);
+  memcpy(prof->bias.eo, eo, sizeof(float) * P7GPU_KP * 2);
+  prof->have_bias = true;
+  return P7GPU_OK;
+}
+
+int p7gpu_biasfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                           const int64_t *idx, int64_t n, float *filtersc)
+{
+  if (!ctx || !prof || !db) return P7GPU_EINVAL;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  BatchBufs b;
+  P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
+  P7G_CHECK(launch_bias(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc));
+  return fetch_batch(ctx, b, filtersc, nullptr);
 }
 
 int p7gpu_vitfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
@@ -449,7 +547,7 @@ int p7gpu_vitfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu
   P7G_CUDA(cudaSetDevice(ctx->device));
   BatchBufs b;
   P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
-  P7G_CHECK(launch_vit(ctx, prof, db, b.d_idx, b.n, b.d_sc, b.d_st));
+  P7G_CHECK(launch_vit(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc, b.d_st));
   return fetch_batch(ctx, b, sc, status);
 }
 
@@ -494,7 +592,7 @@ int p7gpu_forward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_s
     d_xmx = (float *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes);
     P7G_CUDA(cudaMemcpyAsync(d_xoff, xmx_offsets, sizeof(int64_t) * b.n, cudaMemcpyHostToDevice, ctx->stream));
   }
-  P7G_CHECK(launch_fwd(ctx, prof, db, b.d_idx, b.n, b.d_sc, b.d_st, d_xmx, xmx ? d_xoff : nullptr, d_tot));
+  P7G_CHECK(launch_fwd(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc, b.d_st, d_xmx, xmx ? d_xoff : nullptr, d_tot));
   if (xmx && ext) P7G_CUDA(cudaMemcpyAsync(xmx, d_xmx, sizeof(float) * ext, cudaMemcpyDeviceToHost, ctx->stream));
   if (totscale && b.n) P7G_CUDA(cudaMemcpyAsync(totscale, d_tot, sizeof(float) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
   return fetch_batch(ctx, b, sc, status);
@@ -522,7 +620,7 @@ int p7gpu_backward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_
   float *d_bx  = (float *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes + x_bytes);
   P7G_CUDA(cudaMemcpyAsync(d_xoff, xmx_offsets, sizeof(int64_t) * b.n, cudaMemcpyHostToDevice, ctx->stream));
   if (ext) P7G_CUDA(cudaMemcpyAsync(d_fx, fwd_xmx, sizeof(float) * ext, cudaMemcpyHostToDevice, ctx->stream));
-  P7G_CHECK(launch_bwd(ctx, prof, db, b.d_idx, b.n, d_fx, d_xoff, b.d_sc, b.d_st, d_bx, d_tot));
+  P7G_CHECK(launch_bwd(ctx, 0, prof, db->view(), b.d_idx, b.n, d_fx, d_xoff, b.d_sc, b.d_st, d_bx, d_tot));
   if (bck_xmx && ext) P7G_CUDA(cudaMemcpyAsync(bck_xmx, d_bx, sizeof(float) * ext, cudaMemcpyDeviceToHost, ctx->stream));
   if (bck_totscale && b.n) P7G_CUDA(cudaMemcpyAsync(bck_totscale, d_tot, sizeof(float) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
   return fetch_batch(ctx, b, sc, status);
@@ -581,20 +679,12 @@ int p7gpu_BackwardParser(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_
   return st;
 }
 
-float p7gpu_nullsc(int L)
-{
-  float p1 = (float) L / (float) (L + 1);
-  return (float) ((double) (float) L * log((double) p1) + log(1. - (double) p1));
-}
+float p7gpu_nullsc(int L) { return host_nullsc(L); }
 
 // esl_gumbel_surv of (usc - nullsc)/ln2 (p7_pipeline.c:691-692; easel/esl_gumbel.c:129-138)
 double p7gpu_msv_pvalue(float usc, float nullsc, float mmu, float mlambda)
 {
-  float seq_score = (usc - nullsc) / 0.69314718055994529;
-  double y = (double) mlambda * ((double) seq_score - (double) mmu);
-  double ey = -exp(-y);
-  if (fabs(ey) < 5e-9) return -ey;
-  return 1 - exp(ey);
+  return host_filter_pvalue_gumbel(usc, nullsc, mmu, mlambda);
 }
 
 }  // extern "C"

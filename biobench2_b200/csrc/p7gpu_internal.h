@@ -41,19 +41,44 @@ DiagGeom diag_geom(int M);
 int dp_cells_per_lane(int M);       // smallest supported C with 32*C >= M (dp_common.cuh)
 
 // ---- per-target-length constants: what p7_oprofile_ReconfigLength()/p7_bg_SetLength() derive ----
-// (impl_sse/p7_oprofile.c:1085-1127, p7_bg.c:190-199,358-363), built on the host with the host libm.
+// (impl_sse/p7_oprofile.c:1085-1127, p7_bg.c:190-199,358-363), built on the host with the host libm,
+// plus the MSV pass threshold of p7_pipeline.c:691-693 folded into "smallest passing xJ byte" per L.
 struct LenConst {
-  float   pmove;      // xf[N|C|J][MOVE]; LOOP = 1.0f - pmove
-  float   nullsc;     // p7_bg_NullOne
-  int16_t xw_move;    // xw[N|C|J][MOVE]
-  uint8_t tjb_b;
-  uint8_t pad;
+  float    pmove;      // xf[N|C|J][MOVE]; LOOP = 1.0f - pmove
+  float    nullsc;     // p7_bg_NullOne
+  int16_t  xw_move;    // xw[N|C|J][MOVE]
+  uint8_t  tjb_b;
+  uint8_t  pad;
+  uint16_t msv_xj_min; // smallest xJ (0..255) whose P-value passes F1 for this L; 256 = none; L=0 never passes
+  uint16_t pad2;
+  float    logf_p1;    // logf(p1), p1 = L/(L+1)          } the length term of p7_bg_FilterScore (p7_bg.c:481)
+  float    logf_1mp1;  // logf(1. - p1)                   }
 };
 
 // scalar parameters handed to kernels by value
 struct MsvScalars { int tbm_b, tec_b, base_b, bias_b; float scale_b; };
 struct VitScalars { int xw_E_move, xw_E_loop, base_w, ddbound_w; float scale_w; };
 struct FwdScalars { float xf_E_move, xf_E_loop; };
+struct BiasHmm    { float t[2][3]; float pi[3]; float eo[P7GPU_KP][2]; };   // bg->fhmm after p7_bg_SetFilter
+
+// A lane = one stream + its own device work counters, so that launches on different lanes may overlap.
+constexpr int NLANES = 4;            // lane 0 is the ctx's main stream
+constexpr int LANE_COUNTER_WORDS = 32;
+struct Lane { cudaStream_t stream = nullptr; unsigned int *counters = nullptr; };
+
+// counter slots inside a lane (unsigned int words; 64-bit work counters take two)
+enum { CTR_SSV_WORK = 0, CTR_NORES_COUNT = 2, CTR_MSVJ_WORK = 4, CTR_VIT_WORK = 6, CTR_FWD_WORK = 8, CTR_BWD_WORK = 10,
+       CTR_PASS_COUNT = 12, CTR_BIAS_WORK = 14 };
+
+// what a kernel needs to know about the target set
+struct DbView {
+  const uint8_t *res = nullptr;      // residue base such that res[off[s]+i] is residue i of target s
+  const int64_t *off = nullptr;
+  const int32_t *len = nullptr;
+  const int32_t *order = nullptr;    // work order (longest first) or null
+  int64_t first = 0;                 // when neither idx nor order: target = first + work index
+  int32_t max_length = 0;
+};
 
 }  // namespace p7g
 
@@ -68,11 +93,11 @@ struct p7gpu_ctx {
   int          device = 0;
   int          sm_count = 0;
   int          smem_optin = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // == lanes[0].stream
   bool         own_stream = false;
+  p7g::Lane    lanes[p7g::NLANES];
+  cudaStream_t copy_stream = nullptr;   // H2D staging for the streamed database path
   int64_t      launches = 0;
-  // device scratch: work counters / compaction counters
-  unsigned int *d_counters = nullptr;   // [16]
   // growable scratch buffers (device + pinned host)
   void  *d_scratch = nullptr;  size_t d_scratch_bytes = 0;
   void  *h_pinned  = nullptr;  size_t h_pinned_bytes  = 0;
@@ -97,9 +122,13 @@ struct p7gpu_profile {
   int16_t  *d_tw = nullptr;            // [8][dpC][32]
   float    *d_rf = nullptr;            // [NTABROWS][dpC][32]
   float    *d_tf = nullptr;            // [8][dpC][32]
-  // per-L constants
+  // bias-filter HMM (p7_bg_SetFilter), optional
+  bool        have_bias = false;
+  p7g::BiasHmm bias;
+  // per-L constants (valid for the F1 they were built with)
   mutable std::mutex  len_mutex;
   mutable int         len_cap = 0;
+  mutable double      len_F1 = -1.0;
   mutable p7g::LenConst *d_len = nullptr;
   mutable std::vector<p7g::LenConst> h_len;
   float scale_b = 0, scale_w = 0;
@@ -110,40 +139,55 @@ struct p7gpu_seqdb {
   const uint8_t *d_res = nullptr;      // padded to a 16-byte multiple + 16 slack bytes
   const int64_t *d_off = nullptr;
   const int32_t *d_len = nullptr;
-  int32_t       *d_order = nullptr;    // targets sorted by length, longest first (work order)
+  int32_t       *d_order = nullptr;    // targets sorted by length, longest first (work order); may be null
   int64_t nseq = 0, nbytes = 0, nres = 0;
   int32_t max_length = 0;
   bool owns = false;
+  p7g::DbView view() const { p7g::DbView v; v.res = d_res; v.off = d_off; v.len = d_len; v.order = d_order; v.first = 0; v.max_length = max_length; return v; }
 };
 
 namespace p7g {
 // brackets one kernel launch with events on the launching stream when ctx->timing is on
 struct LaunchTimer {
-  p7gpu_ctx *ctx; int kind; cudaEvent_t start = nullptr, stop = nullptr;
-  LaunchTimer(p7gpu_ctx *c, int k) : ctx(c), kind(k) {
-    if (ctx->timing) { cudaEventCreate(&start); cudaEventCreate(&stop); cudaEventRecord(start, ctx->stream); }
+  p7gpu_ctx *ctx; int kind; cudaStream_t stream; cudaEvent_t start = nullptr, stop = nullptr;
+  LaunchTimer(p7gpu_ctx *c, int k, cudaStream_t s) : ctx(c), kind(k), stream(s) {
+    if (ctx->timing) { cudaEventCreate(&start); cudaEventCreate(&stop); cudaEventRecord(start, stream); }
   }
   ~LaunchTimer() {
-    if (start) { cudaEventRecord(stop, ctx->stream); ctx->timed.push_back({kind, start, stop}); }
+    if (start) { cudaEventRecord(stop, stream); ctx->timed.push_back({kind, start, stop}); }
   }
 };
-int ensure_len_table(const p7gpu_profile *prof, int Lmax);
+
+constexpr double DEFAULT_F1 = 0.02;
+int ensure_len_table(const p7gpu_profile *prof, int Lmax, double F1 = -1.0);   // F1 < 0: keep the current table's F1
 int ensure_scratch(p7gpu_ctx *ctx, size_t bytes);
 int ensure_scratch2(p7gpu_ctx *ctx, size_t bytes);
 int ensure_pinned(p7gpu_ctx *ctx, size_t bytes);
+int build_order(p7gpu_ctx *ctx, p7gpu_seqdb *db);
 
-// kernel launchers (ssv_msv.cu, vit.cu, fwdbwd.cu).  idx==nullptr: all targets in db->d_order order,
-// outputs indexed by target; idx!=nullptr (device pointer): outputs indexed by list position.
-int launch_ssv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
-               float *d_sc, int32_t *d_status, int64_t *d_noresult_list, unsigned int *d_noresult_count);
-int launch_msv_j(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_list,
-                 const unsigned int *d_count, int64_t max_n, bool list_holds_positions, const int64_t *d_idx,
-                 float *d_sc, int32_t *d_status);
-int launch_vit(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+// the reference's scalar score -> P-value arithmetic, host libm (p7_pipeline.c:691-730)
+float  host_nullsc(int L);
+double host_gumbel_surv(double x, double mu, double lambda);
+double host_exp_surv(double x, double mu, double lambda);
+double host_filter_pvalue_gumbel(float sc, float nullsc_or_filtersc, float mu, float lambda);
+double host_filter_pvalue_exp(float sc, float filtersc, float tau, float lambda);
+
+// kernel launchers (ssv_msv.cu, vit.cu, fwdbwd.cu, bias.cu).  Work item j of n maps to target
+//   idx ? idx[j] : (db.order ? db.order[j] : db.first + j);  outputs are indexed by j when idx != null, else by target.
+// pass_list/pass_count (optional): targets whose MSV score passes F1 (LenConst::msv_xj_min) are appended.
+int launch_ssv(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+               float *d_sc, int32_t *d_status, int64_t *d_noresult_list, unsigned int *d_noresult_count,
+               int32_t *d_pass_list, unsigned int *d_pass_count);
+int launch_msv_j(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_list,
+                 const unsigned int *d_count, int64_t max_n, float *d_sc, int32_t *d_status,
+                 int32_t *d_pass_list, unsigned int *d_pass_count);
+int launch_vit(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                float *d_sc, int32_t *d_status);
-int launch_fwd(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                float *d_sc, int32_t *d_status, float *d_xmx, const int64_t *d_xmx_off, float *d_totscale);
-int launch_bwd(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+int launch_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                const float *d_fwd_xmx, const int64_t *d_xmx_off, float *d_sc, int32_t *d_status,
                float *d_bck_xmx, float *d_totscale);
+int launch_bias(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+                float *d_filtersc);
 }  // namespace p7g

@@ -1,24 +1,484 @@
-// pipeline.cu — the batched p7_Pipeline() driver (include/p7gpu.h §7).
+// pipeline.cu — the batched p7_Pipeline() driver (include/p7gpu.h §7) and the streamed-database MSV pass.
+//
+// Stage-major restatement of p7_Pipeline() (HMMER/src/p7_pipeline.c:665-735) for a whole database:
+//   A. MSV filter on every target (SSV kernel + J-state kernel); the P-value test of :691-693 is decided inside the
+//      kernels from a host-built per-length table (smallest passing xJ byte), survivors are compacted on the device.
+//   B. bias filter score for the MSV survivors (kernel), P-value test on the host with the host libm (:697-703);
+//   C. Viterbi filter for those whose P still exceeds F2 (:716-722);   D. Forward parser (:727-730);
+//   E. Backward parser for the Forward survivors (:734-735), whose specials go back to the host.
+// Every score->P conversion after the MSV stage runs on the host, in the reference's own float/double expressions,
+// on the <= 2% of targets that get that far: pass/fail decisions therefore never depend on device libm.
 #include "p7gpu_internal.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
 
 struct p7gpu_pipeline_result {
   p7gpu_pipeline_counters counters;
   std::vector<p7gpu_survivor> survivors;
   std::vector<float> fwd_xmx, bck_xmx;
+  std::vector<p7gpu_msv_survivor> msv_pass;       // only when opts->stop_after_msv
 };
+
+namespace p7g {
+
+// stream-ordered device buffer
+struct DevBuf {
+  void *p = nullptr; cudaStream_t s = nullptr;
+  int alloc(size_t bytes, cudaStream_t stream) {
+    s = stream;
+    P7G_CUDA(cudaMallocAsync(&p, std::max<size_t>(bytes, 256), stream));
+    return P7GPU_OK;
+  }
+  ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+  template <class T> T *as() const { return (T *) p; }
+};
+
+__global__ void gather_pass_kernel(const int32_t *pass, unsigned n, const float *usc, const int32_t *st, const int32_t *len,
+                                   int64_t *idx64, float *o_usc, int32_t *o_st, int32_t *o_len)
+{
+  unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int32_t s = pass[j];
+  idx64[j] = s; o_usc[j] = usc[s]; o_st[j] = st[s]; o_len[j] = len[s];
+}
+
+// sorted survivors of the MSV stage on the host
+struct MsvPass { std::vector<int64_t> idx; std::vector<float> usc; std::vector<int32_t> st, len; DevBuf d_idx64; };
+
+static int fetch_msv_pass(p7gpu_ctx *ctx, const p7gpu_seqdb *db, const float *d_usc, const int32_t *d_st,
+                          int32_t *d_pass, unsigned npass, MsvPass *out)
+{
+  cudaStream_t st = ctx->stream;
+  out->idx.resize(npass); out->usc.resize(npass); out->st.resize(npass); out->len.resize(npass);
+  P7G_CHECK(out->d_idx64.alloc(sizeof(int64_t) * npass, st));
+  if (npass == 0) return P7GPU_OK;
+  DevBuf sorted, tmp, g_usc, g_st, g_len;
+  P7G_CHECK(sorted.alloc(sizeof(int32_t) * npass, st));
+  size_t tmp_bytes = 0;
+  P7G_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_pass, sorted.as<int32_t>(), (int) npass, 0, 32, st));
+  P7G_CHECK(tmp.alloc(tmp_bytes, st));
+  P7G_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, d_pass, sorted.as<int32_t>(), (int) npass, 0, 32, st));
+  P7G_CHECK(g_usc.alloc(4 * (size_t) npass, st)); P7G_CHECK(g_st.alloc(4 * (size_t) npass, st)); P7G_CHECK(g_len.alloc(4 * (size_t) npass, st));
+  gather_pass_kernel<<<(npass + 255) / 256, 256, 0, st>>>(sorted.as<int32_t>(), npass, d_usc, d_st, db->d_len,
+                                                           out->d_idx64.as<int64_t>(), g_usc.as<float>(), g_st.as<int32_t>(), g_len.as<int32_t>());
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches += 3;
+  P7G_CUDA(cudaMemcpyAsync(out->idx.data(), out->d_idx64.p, 8 * (size_t) npass, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaMemcpyAsync(out->usc.data(), g_usc.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaMemcpyAsync(out->st.data(), g_st.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaMemcpyAsync(out->len.data(), g_len.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaStreamSynchronize(st));
+  return P7GPU_OK;
+}
+
+// upload a host idx list, run `fn`, fetch float scores (+ statuses)
+static int upload_idx(p7gpu_ctx *ctx, const std::vector<int64_t> &idx, DevBuf *d_idx)
+{
+  P7G_CHECK(d_idx->alloc(8 * idx.size(), ctx->stream));
+  if (!idx.empty()) P7G_CUDA(cudaMemcpyAsync(d_idx->p, idx.data(), 8 * idx.size(), cudaMemcpyHostToDevice, ctx->stream));
+  return P7GPU_OK;
+}
+
+struct Cand {              // a target still alive after the bias stage
+  int64_t idx; int32_t L, msv_st, vit_st; float usc, nullsc, filtersc, vfsc, fwdsc, bcksc, ftot, btot; double P;
+};
+
+// Stages B..E on a resident database, given the MSV stage's outputs.
+static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const p7gpu_pipeline_opts *o,
+                              const float *d_usc, const int32_t *d_st, int32_t *d_pass, unsigned npass, p7gpu_pipeline_result *res)
+{
+  cudaStream_t st = ctx->stream;
+  const DbView dbv = db->view();
+  const double F1 = o->do_max ? 1.0 : o->F1, F2 = o->do_max ? 1.0 : o->F2, F3 = o->do_max ? 1.0 : o->F3;
+  const bool do_bias = o->do_biasfilter && !o->do_max;
+  const float *ev = prof->evparam;
+  res->counters.nseqs = (uint64_t) db->nseq; res->counters.nres = (uint64_t) db->nres;
+  res->counters.n_past_msv = npass;
+
+  MsvPass mp;
+  P7G_CHECK(fetch_msv_pass(ctx, db, d_usc, d_st, d_pass, npass, &mp));
+  if (o->stop_after_msv) {
+    res->msv_pass.resize(npass);
+    for (unsigned j = 0; j < npass; j++) res->msv_pass[j] = {mp.idx[j], mp.len[j], mp.st[j], mp.usc[j]};
+    return P7GPU_OK;
+  }
+
+  // ---- B. bias filter (p7_pipeline.c:697-705) ----
+  std::vector<float> filtersc(npass);
+  if (do_bias && npass) {
+    DevBuf d_f; P7G_CHECK(d_f.alloc(4 * (size_t) npass, st));
+    P7G_CHECK(launch_bias(ctx, 0, prof, dbv, mp.d_idx64.as<int64_t>(), npass, d_f.as<float>()));
+    P7G_CUDA(cudaMemcpyAsync(filtersc.data(), d_f.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
+    P7G_CUDA(cudaStreamSynchronize(st));
+  }
+  std::vector<Cand> cand; cand.reserve(npass);
+  for (unsigned j = 0; j < npass; j++) {
+    Cand c; memset(&c, 0, sizeof(c));
+    c.idx = mp.idx[j]; c.L = mp.len[j]; c.msv_st = mp.st[j]; c.usc = mp.usc[j]; c.nullsc = host_nullsc(c.L);
+    c.vit_st = -1; c.vfsc = NAN; c.fwdsc = NAN; c.bcksc = NAN;
+    if (do_bias) {
+      c.filtersc = filtersc[j];
+      c.P = host_filter_pvalue_gumbel(c.usc, c.filtersc, ev[0], ev[1]);
+      if (c.P > F1) continue;
+    } else {
+      c.filtersc = c.nullsc;
+      c.P = host_filter_pvalue_gumbel(c.usc, c.nullsc, ev[0], ev[1]);
+    }
+    cand.push_back(c);
+  }
+  res->counters.n_past_bias = cand.size();
+
+  // ---- C. Viterbi filter for the candidates whose P still exceeds F2 (:716-723) ----
+  {
+    std::vector<int64_t> vidx; std::vector<size_t> where;
+    for (size_t j = 0; j < cand.size(); j++) if (cand[j].P > F2) { vidx.push_back(cand[j].idx); where.push_back(j); }
+    if (!vidx.empty()) {
+      DevBuf d_idx, d_sc, d_stt;
+      P7G_CHECK(upload_idx(ctx, vidx, &d_idx));
+      P7G_CHECK(d_sc.alloc(4 * vidx.size(), st)); P7G_CHECK(d_stt.alloc(4 * vidx.size(), st));
+      P7G_CHECK(launch_vit(ctx, 0, prof, dbv, d_idx.as<int64_t>(), (int64_t) vidx.size(), d_sc.as<float>(), d_stt.as<int32_t>()));
+      std::vector<float> vsc(vidx.size()); std::vector<int32_t> vst(vidx.size());
+      P7G_CUDA(cudaMemcpyAsync(vsc.data(), d_sc.p, 4 * vidx.size(), cudaMemcpyDeviceToHost, st));
+      P7G_CUDA(cudaMemcpyAsync(vst.data(), d_stt.p, 4 * vidx.size(), cudaMemcpyDeviceToHost, st));
+      P7G_CUDA(cudaStreamSynchronize(st));
+      for (size_t k = 0; k < vidx.size(); k++) {
+        Cand &c = cand[where[k]];
+        c.vfsc = vsc[k]; c.vit_st = vst[k];
+        c.P = host_filter_pvalue_gumbel(c.vfsc, c.filtersc, ev[2], ev[3]);
+      }
+      size_t w = 0;
+      for (size_t j = 0; j < cand.size(); j++) { if (cand[j].vit_st >= 0 && cand[j].P > F2) continue; cand[w++] = cand[j]; }
+      cand.resize(w);
+    }
+  }
+  res->counters.n_past_vit = cand.size();
+
+  // ---- D + E. Forward parser, F3 test, Backward parser for the survivors (:727-735), in slices bounded by the
+  //      size of the specials ((L+1)*6 floats per target and direction) ----
+  const size_t slice_floats = (size_t) 1 << 29;                 // 2 GiB of forward specials per slice
+  size_t host_floats = 0;
+  for (size_t lo = 0; lo < cand.size();) {
+    size_t hi = lo, ext = 0;
+    std::vector<int64_t> idx, xoff;
+    while (hi < cand.size() && (hi == lo || ext + (size_t) (cand[hi].L + 1) * 6 <= slice_floats)) {
+      idx.push_back(cand[hi].idx); xoff.push_back((int64_t) ext); ext += (size_t) (cand[hi].L + 1) * 6; hi++;
+    }
+    const size_t n = hi - lo;
+    DevBuf d_idx, d_xoff, d_sc, d_stt, d_tot, d_fx;
+    P7G_CHECK(upload_idx(ctx, idx, &d_idx)); P7G_CHECK(upload_idx(ctx, xoff, &d_xoff));
+    P7G_CHECK(d_sc.alloc(4 * n, st)); P7G_CHECK(d_stt.alloc(4 * n, st)); P7G_CHECK(d_tot.alloc(4 * n, st));
+    P7G_CHECK(d_fx.alloc(4 * ext, st));
+    P7G_CHECK(launch_fwd(ctx, 0, prof, dbv, d_idx.as<int64_t>(), (int64_t) n, d_sc.as<float>(), d_stt.as<int32_t>(),
+                         d_fx.as<float>(), d_xoff.as<int64_t>(), d_tot.as<float>()));
+    std::vector<float> fsc(n), ftot(n);
+    P7G_CUDA(cudaMemcpyAsync(fsc.data(), d_sc.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    P7G_CUDA(cudaMemcpyAsync(ftot.data(), d_tot.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    P7G_CUDA(cudaStreamSynchronize(st));
+    std::vector<int64_t> bidx, boff; std::vector<size_t> bwhere;
+    for (size_t k = 0; k < n; k++) {
+      Cand &c = cand[lo + k];
+      c.fwdsc = fsc[k]; c.ftot = ftot[k];
+      c.P = host_filter_pvalue_exp(c.fwdsc, c.filtersc, ev[4], ev[5]);
+      if (c.P > F3) continue;
+      bidx.push_back(c.idx); boff.push_back(xoff[k]); bwhere.push_back(lo + k);
+    }
+    res->counters.n_past_fwd += bidx.size();
+    if (!bidx.empty()) {
+      const size_t nb = bidx.size();
+      DevBuf d_bidx, d_boff, d_bsc, d_bst, d_btot, d_bx;
+      P7G_CHECK(upload_idx(ctx, bidx, &d_bidx)); P7G_CHECK(upload_idx(ctx, boff, &d_boff));
+      P7G_CHECK(d_bsc.alloc(4 * nb, st)); P7G_CHECK(d_bst.alloc(4 * nb, st)); P7G_CHECK(d_btot.alloc(4 * nb, st));
+      P7G_CHECK(d_bx.alloc(o->want_specials ? 4 * ext : 256, st));
+      P7G_CHECK(launch_bwd(ctx, 0, prof, dbv, d_bidx.as<int64_t>(), (int64_t) nb, d_fx.as<float>(), d_boff.as<int64_t>(),
+                           d_bsc.as<float>(), d_bst.as<int32_t>(), o->want_specials ? d_bx.as<float>() : nullptr, d_btot.as<float>()));
+      std::vector<float> bsc(nb), btot(nb);
+      P7G_CUDA(cudaMemcpyAsync(bsc.data(), d_bsc.p, 4 * nb, cudaMemcpyDeviceToHost, st));
+      P7G_CUDA(cudaMemcpyAsync(btot.data(), d_btot.p, 4 * nb, cudaMemcpyDeviceToHost, st));
+      if (o->want_specials) {
+        size_t need = 0;
+        for (size_t k = 0; k < nb; k++) need += (size_t) (cand[bwhere[k]].L + 1) * 6;
+        if ((host_floats + need) * 8 > ((size_t) 48 << 30)) {
+          set_error("pipeline: Forward/Backward specials of the survivors exceed 48 GiB of host memory; run with want_specials=0 "
+                    "(the on-device region trigger that would avoid this is SURVEY.md 8f-2, not built yet)");
+          return P7GPU_EMEM;
+        }
+        res->fwd_xmx.resize(host_floats + need); res->bck_xmx.resize(host_floats + need);
+        if (nb == n) {                                           // everything survived (e.g. --max): one bulk copy each
+          P7G_CUDA(cudaMemcpyAsync(res->fwd_xmx.data() + host_floats, d_fx.p, 4 * need, cudaMemcpyDeviceToHost, st));
+          P7G_CUDA(cudaMemcpyAsync(res->bck_xmx.data() + host_floats, d_bx.p, 4 * need, cudaMemcpyDeviceToHost, st));
+        } else {
+          size_t pos = host_floats;
+          for (size_t k = 0; k < nb; k++) {
+            const size_t len = (size_t) (cand[bwhere[k]].L + 1) * 6;
+            P7G_CUDA(cudaMemcpyAsync(res->fwd_xmx.data() + pos, d_fx.as<float>() + boff[k], 4 * len, cudaMemcpyDeviceToHost, st));
+            P7G_CUDA(cudaMemcpyAsync(res->bck_xmx.data() + pos, d_bx.as<float>() + boff[k], 4 * len, cudaMemcpyDeviceToHost, st));
+            pos += len;
+          }
+        }
+      }
+      P7G_CUDA(cudaStreamSynchronize(st));
+      for (size_t k = 0; k < nb; k++) {
+        const Cand &c = cand[bwhere[k]];
+        p7gpu_survivor s;
+        s.seqidx = c.idx; s.L = c.L; s.msv_status = c.msv_st; s.vit_status = c.vit_st;
+        s.usc = c.usc; s.vfsc = c.vfsc; s.fwdsc = c.fwdsc; s.bcksc = bsc[k]; s.nullsc = c.nullsc; s.filtersc = c.filtersc;
+        s.fwd_totscale = c.ftot; s.bck_totscale = btot[k];
+        s.xmx_offset = o->want_specials ? (int64_t) host_floats : -1;
+        if (o->want_specials) host_floats += (size_t) (c.L + 1) * 6;
+        res->survivors.push_back(s);
+      }
+    }
+    lo = hi;
+  }
+  return P7GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Streamed MSV pass over a HOST database: the packed residues are copied in chunks on a copy stream while the SSV/MSV
+// kernels of earlier chunks run on alternating lanes.  The database stays resident in HBM (returned in *ret_db).
+// ------------------------------------------------------------------------------------------------------------------
+static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
+                      const int64_t *offsets, const int32_t *lengths, int64_t nseq, double F1,
+                      float *h_sc, int32_t *h_status, float *d_sc, int32_t *d_st, int32_t *d_pass, unsigned int *d_pass_count,
+                      p7gpu_seqdb **ret_db)
+{
+  if (nseq > 0x7fffffffLL) { set_error("stream: more than 2^31-1 targets per device"); return P7GPU_EINVAL; }
+  p7gpu_seqdb *db = new p7gpu_seqdb();
+  db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->owns = true;
+  const size_t padded = ((size_t) nbytes + 15) / 16 * 16 + 32;
+  uint8_t *d_res = nullptr; int64_t *d_off = nullptr; int32_t *d_len = nullptr;
+  auto fail = [&](int code) { p7gpu_seqdb_destroy(db); return code; };
+#define S_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(P7GPU_ESYS); } } while (0)
+  S_CUDA(cudaMalloc(&d_res, padded));               db->d_res = d_res;
+  S_CUDA(cudaMalloc(&d_off, 8 * (size_t) std::max<int64_t>(nseq, 1))); db->d_off = d_off;
+  S_CUDA(cudaMalloc(&d_len, 4 * (size_t) std::max<int64_t>(nseq, 1))); db->d_len = d_len;
+  cudaStream_t cs = ctx->copy_stream;
+  // everything queued here comes after what the caller already queued on the main stream
+  cudaEvent_t ev_main; S_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+  S_CUDA(cudaEventRecord(ev_main, ctx->stream));
+  S_CUDA(cudaStreamWaitEvent(cs, ev_main, 0));
+  for (int l = 1; l <= 2; l++) S_CUDA(cudaStreamWaitEvent(ctx->lanes[l].stream, ev_main, 0));
+  S_CUDA(cudaMemsetAsync(d_res + (padded - 64), 0xff, 64, cs));
+  S_CUDA(cudaMemsetAsync(d_pass_count, 0, sizeof(unsigned int), cs));
+
+  const int64_t chunk_bytes = (int64_t) 48 << 20;
+  std::vector<cudaEvent_t> events;
+  int64_t nores_cap = 0;
+  // per-lane eslENORESULT pair lists, sized for the largest chunk (bounded by chunk_bytes / 1 byte per target)
+  {
+    int64_t s = 0;
+    while (s < nseq) {
+      int64_t e = s, lim = offsets[s] + chunk_bytes;
+      // bisect for the first target starting beyond lim
+      int64_t lo = s + 1, hi = nseq;
+      while (lo < hi) { int64_t mid = (lo + hi) / 2; if (offsets[mid] <= lim) lo = mid + 1; else hi = mid; }
+      e = lo;
+      nores_cap = std::max(nores_cap, e - s);
+      s = e;
+    }
+  }
+  int64_t *d_nores[3] = {nullptr, nullptr, nullptr};
+  for (int l = 1; l <= 2; l++) S_CUDA(cudaMalloc(&d_nores[l], 16 * (size_t) std::max<int64_t>(nores_cap, 1)));
+  auto cleanup = [&]() { for (auto e : events) cudaEventDestroy(e); cudaEventDestroy(ev_main); cudaFree(d_nores[1]); cudaFree(d_nores[2]); };
+#undef S_CUDA
+#define S_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); cudaDeviceSynchronize(); cleanup(); return fail(P7GPU_ESYS); } } while (0)
+#define S_CHECK(call) do { int s__ = (call); if (s__ != P7GPU_OK) { cudaDeviceSynchronize(); cleanup(); return fail(s__); } } while (0)
+
+  int64_t s_lo = 0, nres = 0; int32_t Lmax = 0; int chunk = 0;
+  while (s_lo < nseq) {
+    const int64_t lim = offsets[s_lo] + chunk_bytes;
+    int64_t lo = s_lo + 1, hi = nseq;
+    while (lo < hi) { int64_t mid = (lo + hi) / 2; if (offsets[mid] <= lim) lo = mid + 1; else hi = mid; }
+    const int64_t s_hi = lo;
+    // validate this chunk's targets (same checks as p7gpu_seqdb_upload) while earlier chunks run
+    int32_t cLmax = 0;
+    for (int64_t s = s_lo; s < s_hi; s++) {
+      const int64_t o = offsets[s]; const int32_t L = lengths[s];
+      if (L < 0 || o < 1 || o + L >= nbytes || (s > s_lo && o < offsets[s - 1] + lengths[s - 1] + 1)) {
+        set_error("stream: target %lld (offset %lld, length %d) does not fit the packed array of %lld bytes / overlaps its predecessor",
+                  (long long) s, (long long) o, L, (long long) nbytes);
+        cudaDeviceSynchronize(); cleanup(); return fail(P7GPU_EINVAL);
+      }
+      cLmax = std::max(cLmax, L); nres += L;
+    }
+    Lmax = std::max(Lmax, cLmax);
+    S_CHECK(ensure_len_table(prof, Lmax, F1));
+    const int64_t b_lo = (offsets[s_lo] - 1) & ~15LL;
+    const int64_t b_hi = std::min<int64_t>(nbytes, (offsets[s_hi - 1] + lengths[s_hi - 1] + 1 + 15) & ~15LL);
+    S_CUDA(cudaMemcpyAsync(d_res + b_lo, residues + b_lo, (size_t) (b_hi - b_lo), cudaMemcpyHostToDevice, cs));
+    S_CUDA(cudaMemcpyAsync(d_off + s_lo, offsets + s_lo, 8 * (size_t) (s_hi - s_lo), cudaMemcpyHostToDevice, cs));
+    S_CUDA(cudaMemcpyAsync(d_len + s_lo, lengths + s_lo, 4 * (size_t) (s_hi - s_lo), cudaMemcpyHostToDevice, cs));
+    cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
+    S_CUDA(cudaEventRecord(ev, cs));
+    const int lane = 1 + (chunk & 1);
+    const Lane &ln = ctx->lanes[lane];
+    S_CUDA(cudaStreamWaitEvent(ln.stream, ev, 0));
+    DbView v; v.res = d_res; v.off = d_off; v.len = d_len; v.order = nullptr; v.first = s_lo; v.max_length = Lmax;
+    unsigned int *d_nores_count = ln.counters + CTR_NORES_COUNT;
+    S_CHECK(launch_ssv(ctx, lane, prof, v, nullptr, s_hi - s_lo, d_sc, d_st, d_nores[lane], d_nores_count, d_pass, d_pass_count));
+    S_CHECK(launch_msv_j(ctx, lane, prof, v, d_nores[lane], d_nores_count, s_hi - s_lo, d_sc, d_st, d_pass, d_pass_count));
+    if (h_sc)     S_CUDA(cudaMemcpyAsync(h_sc + s_lo, d_sc + s_lo, 4 * (size_t) (s_hi - s_lo), cudaMemcpyDeviceToHost, ln.stream));
+    if (h_status) S_CUDA(cudaMemcpyAsync(h_status + s_lo, d_st + s_lo, 4 * (size_t) (s_hi - s_lo), cudaMemcpyDeviceToHost, ln.stream));
+    s_lo = s_hi; chunk++;
+  }
+  // the main stream continues after both lanes
+  for (int l = 1; l <= 2; l++) {
+    cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
+    S_CUDA(cudaEventRecord(ev, ctx->lanes[l].stream));
+    S_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
+  }
+  {
+    cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
+    S_CUDA(cudaEventRecord(ev, cs));
+    S_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
+  }
+  S_CUDA(cudaStreamSynchronize(ctx->stream));
+  cleanup();
+#undef S_CUDA
+#undef S_CHECK
+  db->nres = nres; db->max_length = Lmax;
+  *ret_db = db;
+  return P7GPU_OK;
+}
+
+static int read_count(p7gpu_ctx *ctx, const unsigned int *d_count, unsigned *out)
+{
+  P7G_CUDA(cudaMemcpyAsync(out, d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  P7G_CUDA(cudaStreamSynchronize(ctx->stream));
+  return P7GPU_OK;
+}
+
+static int check_opts(const p7gpu_profile *prof, const p7gpu_pipeline_opts *o)
+{
+  if (o->stop_after_msv) return P7GPU_OK;
+  if (!prof->d_rw || !prof->d_rf) { set_error("pipeline: the profile was uploaded without its Viterbi/Forward parts"); return P7GPU_EINVAL; }
+  if (o->do_biasfilter && !o->do_max && !prof->have_bias) { set_error("pipeline: do_biasfilter needs p7gpu_profile_set_biasfilter()"); return P7GPU_EINVAL; }
+  return P7GPU_OK;
+}
+
+}  // namespace p7g
+using namespace p7g;
 
 extern "C" {
 
-int p7gpu_pipeline_run(p7gpu_ctx *, const p7gpu_profile *, const p7gpu_seqdb *, const p7gpu_pipeline_opts *, p7gpu_pipeline_result **)
+int p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const p7gpu_pipeline_opts *opts,
+                       p7gpu_pipeline_result **ret_res)
 {
-  p7g::set_error("p7gpu_pipeline_run: not implemented yet");
-  return P7GPU_EINVAL;
+  if (!ctx || !prof || !db || !opts || !ret_res) return P7GPU_EINVAL;
+  *ret_res = nullptr;
+  P7G_CHECK(check_opts(prof, opts));
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = db->nseq;
+  const double F1 = opts->do_max ? 1.0 : opts->F1;
+  P7G_CHECK(ensure_len_table(prof, db->max_length, F1));
+  p7gpu_pipeline_result *res = new p7gpu_pipeline_result();
+  memset(&res->counters, 0, sizeof(res->counters));
+  int status = P7GPU_OK;
+  {
+    DevBuf d_sc, d_st, d_pass, d_nores;
+    cudaStream_t st = ctx->stream;
+    unsigned npass = 0;
+    unsigned int *d_pass_count = ctx->lanes[0].counters + CTR_PASS_COUNT;
+    unsigned int *d_nores_count = ctx->lanes[0].counters + CTR_NORES_COUNT;
+    auto body = [&]() -> int {
+      const size_t nn = (size_t) std::max<int64_t>(n, 1);
+      P7G_CHECK(d_sc.alloc(4 * nn, st)); P7G_CHECK(d_st.alloc(4 * nn, st)); P7G_CHECK(d_pass.alloc(4 * nn, st)); P7G_CHECK(d_nores.alloc(16 * nn, st));
+      P7G_CUDA(cudaMemsetAsync(d_pass_count, 0, sizeof(unsigned int), st));
+      P7G_CHECK(launch_ssv(ctx, 0, prof, db->view(), nullptr, n, d_sc.as<float>(), d_st.as<int32_t>(), d_nores.as<int64_t>(), d_nores_count,
+                           d_pass.as<int32_t>(), d_pass_count));
+      P7G_CHECK(launch_msv_j(ctx, 0, prof, db->view(), d_nores.as<int64_t>(), d_nores_count, n, d_sc.as<float>(), d_st.as<int32_t>(),
+                             d_pass.as<int32_t>(), d_pass_count));
+      P7G_CHECK(read_count(ctx, d_pass_count, &npass));
+      return pipeline_after_msv(ctx, prof, db, opts, d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), npass, res);
+    };
+    status = body();
+  }
+  if (status != P7GPU_OK) { cudaStreamSynchronize(ctx->stream); delete res; return status; }
+  *ret_res = res;
+  return P7GPU_OK;
 }
+
+int p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
+                            const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                            const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res)
+{
+  if (!ctx || !prof || !opts || !ret_res || nseq < 0 || (nseq > 0 && (!residues || !offsets || !lengths))) return P7GPU_EINVAL;
+  *ret_res = nullptr;
+  P7G_CHECK(check_opts(prof, opts));
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  p7gpu_pipeline_result *res = new p7gpu_pipeline_result();
+  memset(&res->counters, 0, sizeof(res->counters));
+  if (nseq == 0) { *ret_res = res; return P7GPU_OK; }
+  const double F1 = opts->do_max ? 1.0 : opts->F1;
+  int status = P7GPU_OK;
+  p7gpu_seqdb *db = nullptr;
+  {
+    DevBuf d_sc, d_st, d_pass;
+    cudaStream_t st = ctx->stream;
+    unsigned npass = 0;
+    unsigned int *d_pass_count = ctx->lanes[0].counters + CTR_PASS_COUNT;
+    auto body = [&]() -> int {
+      P7G_CHECK(d_sc.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_st.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_pass.alloc(4 * (size_t) nseq, st));
+      P7G_CHECK(stream_msv(ctx, prof, residues, nbytes, offsets, lengths, nseq, F1, nullptr, nullptr,
+                           d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), d_pass_count, &db));
+      P7G_CHECK(read_count(ctx, d_pass_count, &npass));
+      return pipeline_after_msv(ctx, prof, db, opts, d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), npass, res);
+    };
+    status = body();
+    cudaStreamSynchronize(st);
+  }
+  p7gpu_seqdb_destroy(db);
+  if (status != P7GPU_OK) { delete res; return status; }
+  *ret_res = res;
+  return P7GPU_OK;
+}
+
+int p7gpu_msvfilter_stream(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
+                           const int64_t *offsets, const int32_t *lengths, int64_t nseq, double F1,
+                           float *sc, int32_t *status, int32_t *pass_list, int64_t *npass_out, p7gpu_seqdb **opt_ret_db)
+{
+  if (!ctx || !prof || nseq < 0 || (nseq > 0 && (!residues || !offsets || !lengths))) return P7GPU_EINVAL;
+  if (opt_ret_db) *opt_ret_db = nullptr;
+  if (npass_out) *npass_out = 0;
+  if (nseq == 0) return P7GPU_OK;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  p7gpu_seqdb *db = nullptr;
+  int rc = P7GPU_OK;
+  {
+    DevBuf d_sc, d_st, d_pass;
+    cudaStream_t st = ctx->stream;
+    unsigned int *d_pass_count = ctx->lanes[0].counters + CTR_PASS_COUNT;
+    auto body = [&]() -> int {
+      P7G_CHECK(d_sc.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_st.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_pass.alloc(4 * (size_t) nseq, st));
+      P7G_CHECK(stream_msv(ctx, prof, residues, nbytes, offsets, lengths, nseq, F1, sc, status,
+                           d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), d_pass_count, &db));
+      unsigned npass = 0;
+      P7G_CHECK(read_count(ctx, d_pass_count, &npass));
+      if (npass_out) *npass_out = npass;
+      if (pass_list && npass) {
+        P7G_CUDA(cudaMemcpyAsync(pass_list, d_pass.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
+        P7G_CUDA(cudaStreamSynchronize(st));
+        std::sort(pass_list, pass_list + npass);
+      }
+      return P7GPU_OK;
+    };
+    rc = body();
+    cudaStreamSynchronize(st);
+  }
+  if (rc != P7GPU_OK || !opt_ret_db) p7gpu_seqdb_destroy(db);
+  else *opt_ret_db = db;
+  return rc;
+}
+
 const p7gpu_pipeline_counters *p7gpu_result_counters(const p7gpu_pipeline_result *res) { return res ? &res->counters : nullptr; }
 int64_t p7gpu_result_nsurvivors(const p7gpu_pipeline_result *res) { return res ? (int64_t) res->survivors.size() : 0; }
 const p7gpu_survivor *p7gpu_result_survivors(const p7gpu_pipeline_result *res) { return res ? res->survivors.data() : nullptr; }
 const float *p7gpu_result_fwd_xmx(const p7gpu_pipeline_result *res) { return res ? res->fwd_xmx.data() : nullptr; }
 const float *p7gpu_result_bck_xmx(const p7gpu_pipeline_result *res) { return res ? res->bck_xmx.data() : nullptr; }
+int64_t p7gpu_result_nmsvpass(const p7gpu_pipeline_result *res) { return res ? (int64_t) res->msv_pass.size() : 0; }
+const p7gpu_msv_survivor *p7gpu_result_msvpass(const p7gpu_pipeline_result *res) { return res ? res->msv_pass.data() : nullptr; }
 void p7gpu_result_destroy(p7gpu_pipeline_result *res) { delete res; }
 
 }

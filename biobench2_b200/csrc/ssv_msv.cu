@@ -21,12 +21,15 @@ struct SsvParams {
   const uint32_t *tab;          // [NTABROWS][rowWords]
   int rowWords, P, M;
   const uint8_t *res; const int64_t *off; const int32_t *len; const int32_t *order; const int64_t *idx;
+  long long first;
   long long n;
   const LenConst *lc;
   MsvScalars s;
   float *sc; int32_t *status;
   long long *nores_list;        // pairs (target, output slot), may be null
   unsigned int *nores_count;
+  int32_t *pass_list;           // targets passing the MSV P-value test (p7_pipeline.c:691-693), may be null
+  unsigned int *pass_count;
   unsigned long long *work_counter;
 };
 
@@ -47,8 +50,9 @@ __device__ __forceinline__ int hmax16(uint32_t x)
 }
 
 // The decision tree of p7_SSVFilter after get_xE (ssvfilter.c:884-925), on one lane.
-__device__ __forceinline__ int ssv_epilogue(int maxu, int tjb, const MsvScalars &s, float *ret_sc)
+__device__ __forceinline__ int ssv_epilogue(int maxu, int tjb, const MsvScalars &s, float *ret_sc, int *ret_xJ)
 {
+  *ret_xJ = 0;
   int xE = 128 + maxu; if (xE > 255) xE = 255;
   if (xE >= 255 - s.bias_b) {
     *ret_sc = CUDART_INF_F;
@@ -59,6 +63,7 @@ __device__ __forceinline__ int ssv_epilogue(int maxu, int tjb, const MsvScalars 
   if (xE16 >= 255 - s.bias_b) { *ret_sc = CUDART_INF_F; return P7GPU_ERANGE; }
   unsigned short xJ = (unsigned short) (xE16 - s.tec_b);
   if (xJ > s.base_b) { *ret_sc = 0.0f; return P7GPU_ENORESULT; }
+  *ret_xJ = (int) xJ;
   float sc = ((float) ((int) xJ - tjb) - (float) s.base_b);
   sc = __fdiv_rn(sc, s.scale_b);
   sc = __fsub_rn(sc, 3.0f);
@@ -86,13 +91,14 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvParams p)
     if (lane == 0) j = atomicAdd(p.work_counter, 1ULL);
     j = __shfl_sync(0xffffffffu, j, 0);
     if (j >= (unsigned long long) p.n) break;
-    const long long s   = p.idx ? p.idx[j] : (p.order ? (long long) p.order[j] : (long long) j);
+    const long long s   = p.idx ? p.idx[j] : (p.order ? (long long) p.order[j] : p.first + (long long) j);
     const long long out = p.idx ? (long long) j : s;
     const int       L   = p.len[s];
     const long long o   = p.off[s];
-    const int       tjb = p.lc[L].tjb_b;
+    const LenConst  lc  = p.lc[L];
+    const int       tjb = lc.tjb_b;
 
-    int status; float sc = 0.0f;
+    int status; float sc = 0.0f; int xJ = 0;
     if (tjb + p.s.tbm_b + p.s.tec_b + p.s.bias_b >= 127) {      // ssvfilter.c:884
       status = P7GPU_ENORESULT;
     } else {
@@ -151,11 +157,13 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvParams p)
         }
       }
       const int maxu = __reduce_max_sync(0xffffffffu, hmax16(xE));
-      status = ssv_epilogue(maxu, tjb, p.s, &sc);
+      status = ssv_epilogue(maxu, tjb, p.s, &sc, &xJ);
     }
     if (lane == 0) {
       p.sc[out] = sc;
       p.status[out] = status;
+      if (p.pass_list && L > 0 && (status == P7GPU_ERANGE || (status == P7GPU_OK && xJ >= (int) lc.msv_xj_min)))
+        p.pass_list[atomicAdd(p.pass_count, 1u)] = (int32_t) s;
       if (status == P7GPU_ENORESULT && p.nores_list) {
         unsigned int t = atomicAdd(p.nores_count, 1u);
         p.nores_list[2 * (long long) t]     = s;
@@ -172,6 +180,7 @@ struct MsvjParams {
   const long long *list; const unsigned int *count; long long fixed_n;   // list of (target, out) pairs
   const LenConst *lc; MsvScalars s;
   float *sc; int32_t *status;
+  int32_t *pass_list; unsigned int *pass_count;
   unsigned long long *work_counter;
 };
 
@@ -191,7 +200,8 @@ __global__ void __launch_bounds__(MSVJ_THREADS) msvj_kernel(const MsvjParams p)
     const long long s = p.list[2 * j], out = p.list[2 * j + 1];
     const int L = p.len[s];
     const long long o = p.off[s];
-    const int tjb = p.lc[L].tjb_b;
+    const LenConst lc = p.lc[L];
+    const int tjb = lc.tjb_b;
     const int tjbm = (int) (unsigned char) ((int) (signed char) tjb + (int) (signed char) p.s.tbm_b);   // msvfilter.c:118
     uint32_t v[Q];
 #pragma unroll
@@ -229,26 +239,33 @@ __global__ void __launch_bounds__(MSVJ_THREADS) msvj_kernel(const MsvjParams p)
       }
       p.sc[out] = sc;
       p.status[out] = status;
+      if (p.pass_list && L > 0 && (status == P7GPU_ERANGE || xJ >= (int) lc.msv_xj_min))
+        p.pass_list[atomicAdd(p.pass_count, 1u)] = (int32_t) s;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 template <int Q, bool SMEM>
-static int launch_ssv_q(p7gpu_ctx *ctx, const SsvParams &p, size_t tabBytes)
+static int launch_ssv_q(p7gpu_ctx *ctx, cudaStream_t stream, const SsvParams &p, size_t tabBytes)
 {
   auto kern = ssv_kernel<Q, SMEM>;
   size_t smem = SMEM ? tabBytes : 0;
-  if (SMEM) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  int occ = 0;
-  P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSV_THREADS, smem));
-  if (occ < 1) { set_error("ssv_kernel<%d>: zero occupancy (smem %zu)", Q, smem); return P7GPU_ESYS; }
+  static int occ_dev[64];                         // per template instance (one geometry), per device; 0 = unknown
+  int &occ_cache = occ_dev[ctx->device & 63];
+  if (occ_cache <= 0) {
+    if (SMEM) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int occ = 0;
+    P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSV_THREADS, smem));
+    if (occ < 1) { set_error("ssv_kernel<%d>: zero occupancy (smem %zu)", Q, smem); return P7GPU_ESYS; }
+    occ_cache = occ;
+  }
   long long warps_needed = p.n;
-  long long blocks = (long long) ctx->sm_count * occ;
+  long long blocks = (long long) ctx->sm_count * occ_cache;
   long long need_blocks = (warps_needed + (SSV_THREADS / 32) - 1) / (SSV_THREADS / 32);
   if (need_blocks < blocks) blocks = need_blocks;
   if (blocks < 1) blocks = 1;
-  { LaunchTimer t(ctx, P7GPU_KERNEL_SSV); kern<<<(unsigned) blocks, SSV_THREADS, smem, ctx->stream>>>(p); }
+  { LaunchTimer t(ctx, P7GPU_KERNEL_SSV, stream); kern<<<(unsigned) blocks, SSV_THREADS, smem, stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;
@@ -258,22 +275,26 @@ static int launch_ssv_q(p7gpu_ctx *ctx, const SsvParams &p, size_t tabBytes)
   X(1) X(3) X(5) X(7) X(9) X(11) X(13) X(15) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31) X(33) \
   X(35) X(37) X(39) X(41) X(43) X(45) X(47) X(49) X(51) X(53) X(55) X(57) X(59) X(61) X(63) X(65)
 
-int launch_ssv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
-               float *d_sc, int32_t *d_status, int64_t *d_noresult_list, unsigned int *d_noresult_count)
+int launch_ssv(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+               float *d_sc, int32_t *d_status, int64_t *d_noresult_list, unsigned int *d_noresult_count,
+               int32_t *d_pass_list, unsigned int *d_pass_count)
 {
   if (n <= 0) return P7GPU_OK;
-  P7G_CHECK(ensure_len_table(prof, db->max_length));
+  P7G_CHECK(ensure_len_table(prof, db.max_length));
+  const Lane &ln = ctx->lanes[lane];
   SsvParams p;
   p.tab = prof->d_ssv_tab; p.rowWords = prof->geom.rowWords; p.P = prof->geom.P; p.M = prof->M;
-  p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.order = d_idx ? nullptr : db->d_order; p.idx = d_idx;
+  p.res = db.res; p.off = db.off; p.len = db.len; p.order = d_idx ? nullptr : db.order; p.idx = d_idx; p.first = db.first;
   p.n = n; p.lc = prof->d_len; p.s = prof->msv; p.sc = d_sc; p.status = d_status;
   p.nores_list = (long long *) d_noresult_list; p.nores_count = d_noresult_count;
-  p.work_counter = (unsigned long long *) (ctx->d_counters + 0);
-  P7G_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned int), ctx->stream));   // work counter (2 words) + spare
+  p.pass_list = d_pass_list; p.pass_count = d_pass_count;
+  p.work_counter = (unsigned long long *) (ln.counters + CTR_SSV_WORK);
+  // work counter (2 words) + the lane's eslENORESULT count (CTR_NORES_COUNT = CTR_SSV_WORK + 2)
+  P7G_CUDA(cudaMemsetAsync(ln.counters + CTR_SSV_WORK, 0, 4 * sizeof(unsigned int), ln.stream));
   const size_t tabBytes = prof->geom.tableBytes();
   const bool smem_ok = tabBytes + 1024 <= (size_t) ctx->smem_optin;
   switch (prof->geom.Q) {
-#define X(QV) case QV: return smem_ok ? launch_ssv_q<QV, true>(ctx, p, tabBytes) : launch_ssv_q<QV, false>(ctx, p, tabBytes);
+#define X(QV) case QV: return smem_ok ? launch_ssv_q<QV, true>(ctx, ln.stream, p, tabBytes) : launch_ssv_q<QV, false>(ctx, ln.stream, p, tabBytes);
     P7G_ODD_Q_CASES(X)
 #undef X
   default: set_error("SSV: unsupported Q=%d (M=%d too large; max M is %d)", prof->geom.Q, prof->M, 64 * MAX_Q - 1); return P7GPU_EINVAL;
@@ -281,34 +302,36 @@ int launch_ssv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
 }
 
 template <int Q>
-static int launch_msvj_q(p7gpu_ctx *ctx, const MsvjParams &p, long long max_n)
+static int launch_msvj_q(p7gpu_ctx *ctx, cudaStream_t stream, const MsvjParams &p, long long max_n)
 {
   long long blocks = (max_n + (MSVJ_THREADS / 32) - 1) / (MSVJ_THREADS / 32);
   long long cap = (long long) ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  { LaunchTimer t(ctx, P7GPU_KERNEL_MSVJ); msvj_kernel<Q><<<(unsigned) blocks, MSVJ_THREADS, 0, ctx->stream>>>(p); }
+  { LaunchTimer t(ctx, P7GPU_KERNEL_MSVJ, stream); msvj_kernel<Q><<<(unsigned) blocks, MSVJ_THREADS, 0, stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;
 }
 
 // d_list holds (target, output slot) pairs.  If d_count != nullptr the number of pairs is read on the device.
-int launch_msv_j(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_list,
-                 const unsigned int *d_count, int64_t max_n, bool, const int64_t *,
-                 float *d_sc, int32_t *d_status)
+int launch_msv_j(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_list,
+                 const unsigned int *d_count, int64_t max_n, float *d_sc, int32_t *d_status,
+                 int32_t *d_pass_list, unsigned int *d_pass_count)
 {
   if (max_n <= 0) return P7GPU_OK;
-  P7G_CHECK(ensure_len_table(prof, db->max_length));
+  P7G_CHECK(ensure_len_table(prof, db.max_length));
+  const Lane &ln = ctx->lanes[lane];
   MsvjParams p;
   p.tab = prof->d_msv_tab; p.rowWords = prof->geom.rowWords; p.P = prof->geom.P; p.M = prof->M;
-  p.res = db->d_res; p.off = db->d_off; p.len = db->d_len;
+  p.res = db.res; p.off = db.off; p.len = db.len;
   p.list = (const long long *) d_list; p.count = d_count; p.fixed_n = max_n;
   p.lc = prof->d_len; p.s = prof->msv; p.sc = d_sc; p.status = d_status;
-  p.work_counter = (unsigned long long *) (ctx->d_counters + 4);
-  P7G_CUDA(cudaMemsetAsync(ctx->d_counters + 4, 0, 2 * sizeof(unsigned int), ctx->stream));
+  p.pass_list = d_pass_list; p.pass_count = d_pass_count;
+  p.work_counter = (unsigned long long *) (ln.counters + CTR_MSVJ_WORK);
+  P7G_CUDA(cudaMemsetAsync(ln.counters + CTR_MSVJ_WORK, 0, 2 * sizeof(unsigned int), ln.stream));
   switch (prof->geom.Q) {
-#define X(QV) case QV: return launch_msvj_q<QV>(ctx, p, max_n);
+#define X(QV) case QV: return launch_msvj_q<QV>(ctx, ln.stream, p, max_n);
     P7G_ODD_Q_CASES(X)
 #undef X
   default: set_error("MSV: unsupported Q=%d", prof->geom.Q); return P7GPU_EINVAL;

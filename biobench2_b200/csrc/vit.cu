@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
 }
 
 template <int C>
-static int launch_vit_c(p7gpu_ctx *ctx, const VitParams &p)
+static int launch_vit_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitParams &p)
 {
   const size_t smem = (size_t) (8 + NTABROWS) * C * 32 * sizeof(int16_t);
   const bool use_smem = smem + 1024 <= (size_t) ctx->smem_optin;
@@ -136,25 +136,26 @@ static int launch_vit_c(p7gpu_ctx *ctx, const VitParams &p)
   long long need = (p.c.n + (DP_THREADS / 32) - 1) / (DP_THREADS / 32);
   if (need < blocks) blocks = need;
   if (blocks < 1) blocks = 1;
-  { LaunchTimer t(ctx, P7GPU_KERNEL_VIT); kern<<<(unsigned) blocks, DP_THREADS, dyn, ctx->stream>>>(p); }
+  { LaunchTimer t(ctx, P7GPU_KERNEL_VIT, stream); kern<<<(unsigned) blocks, DP_THREADS, dyn, stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;
 }
 
-int launch_vit(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const int64_t *d_idx, int64_t n,
+int launch_vit(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                float *d_sc, int32_t *d_status)
 {
   if (n <= 0) return P7GPU_OK;
-  P7G_CHECK(ensure_len_table(prof, db->max_length));
+  P7G_CHECK(ensure_len_table(prof, db.max_length));
+  const Lane &ln = ctx->lanes[lane];
   VitParams p;
-  p.c.res = db->d_res; p.c.off = db->d_off; p.c.len = db->d_len; p.c.order = d_idx ? nullptr : db->d_order; p.c.idx = d_idx;
+  p.c.res = db.res; p.c.off = db.off; p.c.len = db.len; p.c.order = d_idx ? nullptr : db.order; p.c.idx = d_idx; p.c.first = db.first;
   p.c.n = n; p.c.lc = prof->d_len; p.c.sc = d_sc; p.c.status = d_status;
-  p.c.work_counter = (unsigned long long *) (ctx->d_counters + 6);
+  p.c.work_counter = (unsigned long long *) (ln.counters + CTR_VIT_WORK);
   p.rw = prof->d_rw; p.tw = prof->d_tw; p.s = prof->vit;
-  P7G_CUDA(cudaMemsetAsync(ctx->d_counters + 6, 0, 2 * sizeof(unsigned int), ctx->stream));
+  P7G_CUDA(cudaMemsetAsync(ln.counters + CTR_VIT_WORK, 0, 2 * sizeof(unsigned int), ln.stream));
   switch (prof->dpC) {
-#define X(CV) case CV: return launch_vit_c<CV>(ctx, p);
+#define X(CV) case CV: return launch_vit_c<CV>(ctx, ln.stream, p);
     P7G_DP_C_CASES(X)
 #undef X
   default: set_error("vit: unsupported cells-per-lane %d", prof->dpC); return P7GPU_EINVAL;

@@ -19,12 +19,12 @@ EXPORTS = [
     "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
     "p7gpu_ctx_launch_count", "p7gpu_ctx_synchronize",
     "p7gpu_ctx_set_timing", "p7gpu_ctx_reset_timing", "p7gpu_ctx_kernel_time", "p7gpu_measure_peaks",
-    "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M",
+    "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M", "p7gpu_profile_set_biasfilter",
     "p7gpu_seqdb_upload", "p7gpu_seqdb_adopt_device", "p7gpu_seqdb_destroy", "p7gpu_seqdb_nseq", "p7gpu_seqdb_nres",
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
-    "p7gpu_backward_batch", "p7gpu_msvfilter_device",
+    "p7gpu_backward_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
     "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser",
-    "p7gpu_pipeline_run", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
+    "p7gpu_pipeline_run", "p7gpu_pipeline_run_host", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
 ]
@@ -38,7 +38,12 @@ class P7GpuError(RuntimeError):
 
 class PipelineOpts(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double),
-                ("do_biasfilter", C.c_int32), ("do_max", C.c_int32), ("want_specials", C.c_int32)]
+                ("do_biasfilter", C.c_int32), ("do_max", C.c_int32), ("want_specials", C.c_int32),
+                ("stop_after_msv", C.c_int32)]
+
+
+class MsvSurvivor(C.Structure):
+    _fields_ = [("seqidx", C.c_int64), ("L", C.c_int32), ("msv_status", C.c_int32), ("usc", C.c_float)]
 
 
 class PipelineCounters(C.Structure):
@@ -90,7 +95,15 @@ def lib():
             getattr(L, nm).argtypes = [vp, vp, vp, vp, i64, vp, vp]
         L.p7gpu_forward_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         L.p7gpu_backward_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
-        L.p7gpu_msvfilter_device.argtypes = [vp, vp, vp, vp, vp]
+        L.p7gpu_msvfilter_device.argtypes = [vp, vp, vp, C.c_double, vp, vp, vp, vp]
+        L.p7gpu_profile_set_biasfilter.argtypes = [vp, vp, vp, vp]
+        L.p7gpu_biasfilter_batch.argtypes = [vp, vp, vp, vp, i64, vp]
+        L.p7gpu_msvfilter_stream.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.c_double, vp, vp, vp, C.POINTER(i64), C.POINTER(vp)]
+        L.p7gpu_pipeline_run_host.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.POINTER(PipelineOpts), C.POINTER(vp)]
+        L.p7gpu_result_nmsvpass.restype = i64
+        L.p7gpu_result_nmsvpass.argtypes = [vp]
+        L.p7gpu_result_msvpass.restype = C.POINTER(MsvSurvivor)
+        L.p7gpu_result_msvpass.argtypes = [vp]
         for nm in ("p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter"):
             getattr(L, nm).argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
         L.p7gpu_ForwardParser.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -186,6 +199,15 @@ class Profile:
         self.h = h
         self.M = v.M
         self.evparam = [float(x) for x in v.evparam]
+        bg = getattr(oprofile, "bg_filter", None)
+        if bg is not None:
+            self.set_biasfilter(*bg[:3])
+
+    def set_biasfilter(self, t, pi, eo):
+        """bg->fhmm tables after p7_bg_SetFilter (HMMER/src/p7_bg.c:430-453): t[2][3], pi[3], eo[Kp][2]."""
+        t = np.ascontiguousarray(t, np.float32); pi = np.ascontiguousarray(pi, np.float32); eo = np.ascontiguousarray(eo, np.float32)
+        assert t.size == 6 and pi.size == 3 and eo.size == 58
+        _check(lib().p7gpu_profile_set_biasfilter(self.h, _p(t), _p(pi), _p(eo)))
 
     def close(self):
         if self.h:
@@ -271,9 +293,86 @@ def backward_batch(ctx, prof, db, fwd_xmx, xoff, idx=None):
     return sc, st, bx, tot
 
 
-def msvfilter_device(ctx, prof, db, d_sc_ptr, d_status_ptr):
-    """MSV stage with results left in HBM (device pointers to nseq floats / int32)."""
-    _check(lib().p7gpu_msvfilter_device(ctx.h, prof.h, db.h, C.c_void_p(d_sc_ptr), C.c_void_p(d_status_ptr)))
+def msvfilter_device(ctx, prof, db, d_sc_ptr, d_status_ptr, F1=0.02, d_pass_list_ptr=None, d_pass_count_ptr=None):
+    """MSV stage with results left in HBM (device pointers: nseq floats / int32; optional pass list int32[nseq] + uint32 count)."""
+    _check(lib().p7gpu_msvfilter_device(ctx.h, prof.h, db.h, F1, C.c_void_p(d_sc_ptr), C.c_void_p(d_status_ptr),
+                                        C.c_void_p(d_pass_list_ptr) if d_pass_list_ptr else None,
+                                        C.c_void_p(d_pass_count_ptr) if d_pass_count_ptr else None))
+
+
+def biasfilter_batch(ctx, prof, db, idx=None):
+    n = len(idx) if idx is not None else db.nseq
+    idx_a = np.ascontiguousarray(idx, np.int64) if idx is not None else None
+    out = np.zeros(n, np.float32)
+    _check(lib().p7gpu_biasfilter_batch(ctx.h, prof.h, db.h, _p(idx_a), n, _p(out)))
+    return out
+
+
+def msvfilter_stream(ctx, prof, packed, F1=0.02, sc=None, st=None, want_pass=True, keep_db=False):
+    """Streamed MSV pass over a HOST PackedDB (p7gpu_msvfilter_stream).  Returns (sc, status, pass_list, SeqDB|None)."""
+    n = packed.nseq
+    sc = np.zeros(n, np.float32) if sc is None else sc
+    st = np.zeros(n, np.int32) if st is None else st
+    pl = np.zeros(max(n, 1), np.int32) if want_pass else None
+    npass = C.c_int64(0); h = C.c_void_p()
+    _check(lib().p7gpu_msvfilter_stream(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
+                                        _p(packed.lengths), n, F1, _p(sc), _p(st), _p(pl), C.byref(npass),
+                                        C.byref(h) if keep_db else None))
+    db = SeqDB(ctx, h, n) if keep_db and h else None
+    return sc, st, (pl[:npass.value] if want_pass else None), db
+
+
+class PipelineResult:
+    """Host copy of a p7gpu_pipeline_result."""
+
+    def __init__(self, h):
+        L = lib()
+        c = L.p7gpu_result_counters(h).contents
+        self.counters = np.array([c.nseqs, c.nres, c.n_past_msv, c.n_past_bias, c.n_past_vit, c.n_past_fwd], np.uint64)
+        n = L.p7gpu_result_nsurvivors(h)
+        sv = L.p7gpu_result_survivors(h)
+        names = [f[0] for f in Survivor._fields_]
+        self.survivors = [{k: getattr(sv[i], k) for k in names} for i in range(n)]
+        ext = 0
+        for s in self.survivors:
+            if s["xmx_offset"] >= 0:
+                ext = max(ext, s["xmx_offset"] + (s["L"] + 1) * 6)
+        if ext:
+            self.fwd_xmx = np.ctypeslib.as_array(L.p7gpu_result_fwd_xmx(h), shape=(ext,)).copy()
+            self.bck_xmx = np.ctypeslib.as_array(L.p7gpu_result_bck_xmx(h), shape=(ext,)).copy()
+        else:
+            self.fwd_xmx = self.bck_xmx = np.zeros(0, np.float32)
+        m = L.p7gpu_result_nmsvpass(h)
+        if m:
+            raw = np.ctypeslib.as_array(C.cast(L.p7gpu_result_msvpass(h), C.POINTER(C.c_uint8)), shape=(m * C.sizeof(MsvSurvivor),))
+            rec = raw.view(np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")]))
+            self.msv_pass = rec.copy()
+        else:
+            self.msv_pass = np.zeros(0, np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")]))
+        L.p7gpu_result_destroy(h)
+
+
+def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv):
+    return PipelineOpts(F1, F2, F3, int(do_biasfilter), int(do_max), int(want_specials), int(stop_after_msv))
+
+
+def pipeline_run(ctx, prof, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
+                 stop_after_msv=False):
+    """The batched p7_Pipeline() over a resident database (defaults: p7_pipeline.c:214-216)."""
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv)
+    h = C.c_void_p()
+    _check(lib().p7gpu_pipeline_run(ctx.h, prof.h, db.h, C.byref(o), C.byref(h)))
+    return PipelineResult(h)
+
+
+def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
+                      stop_after_msv=False):
+    """Same for a HOST PackedDB: the upload is streamed under the MSV stage."""
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv)
+    h = C.c_void_p()
+    _check(lib().p7gpu_pipeline_run_host(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
+                                         _p(packed.lengths), packed.nseq, C.byref(o), C.byref(h)))
+    return PipelineResult(h)
 
 
 # ---- signature-level wrappers (one target per call), same meaning as impl_sse.h:309-344 ----

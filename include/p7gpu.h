@@ -93,7 +93,8 @@ int         p7gpu_ctx_synchronize(p7gpu_ctx *ctx);
 #define P7GPU_KERNEL_VIT  2
 #define P7GPU_KERNEL_FWD  3
 #define P7GPU_KERNEL_BWD  4
-#define P7GPU_NKERNELS    5
+#define P7GPU_KERNEL_BIAS 5
+#define P7GPU_NKERNELS    6
 int         p7gpu_ctx_set_timing  (p7gpu_ctx *ctx, int on);
 int         p7gpu_ctx_reset_timing(p7gpu_ctx *ctx);
 int         p7gpu_ctx_kernel_time (p7gpu_ctx *ctx, int kind, double *ms_total, int64_t *nlaunches);
@@ -109,6 +110,9 @@ int         p7gpu_measure_peaks(p7gpu_ctx *ctx, double *int16x2_gops, double *fp
 int  p7gpu_profile_upload (p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_profile **ret_prof);
 void p7gpu_profile_destroy(p7gpu_profile *prof);
 int  p7gpu_profile_M      (const p7gpu_profile *prof);
+/* the bias-filter HMM as p7_bg_SetFilter() built it (p7_bg.c:430-453): bg->fhmm->t[2][3] (row-major), pi[3], eo[Kp][2].
+ * t[0][0], t[0][1] are overwritten per target exactly like p7_bg_SetLength (p7_bg.c:193-196). */
+int  p7gpu_profile_set_biasfilter(p7gpu_profile *prof, const float *t6, const float *pi3, const float *eo);
 
 /* ------------------------------------------------------------------------------------------------
  * 4. Target database: replaces ESL_SQ_BLOCK hand-off (easel/esl_sqio.c:1041; hmmsearch.c:1317-1361).
@@ -152,10 +156,24 @@ int p7gpu_backward_batch (p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu
                           const int64_t *idx, int64_t n, const float *fwd_xmx, const int64_t *xmx_offsets,
                           float *sc, int32_t *status, float *bck_xmx, float *bck_totscale);
 
-/* device-resident variant of the MSV stage for throughput measurement: results stay in HBM
- * (d_sc: n floats, d_status: n int32, both device pointers owned by the caller).                 */
-int p7gpu_msvfilter_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
-                           void *d_sc, void *d_status);
+/* p7_bg_FilterScore (p7_bg.c:472-484): the bias-filter null score of the selected targets */
+int p7gpu_biasfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                           const int64_t *idx, int64_t n, float *filtersc);
+
+/* device-resident variant of the MSV stage: results stay in HBM (d_sc: nseq floats, d_status: nseq int32, device
+ * pointers owned by the caller).  If d_pass_list/d_pass_count are given (nseq int32 / one uint32, device), the targets
+ * whose P-value passes F1 (p7_pipeline.c:691-693, decided exactly from a host-built per-length table) are appended
+ * there in no particular order.  Asynchronous on the ctx's stream. */
+int p7gpu_msvfilter_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, double F1,
+                           void *d_sc, void *d_status, void *d_pass_list, void *d_pass_count);
+
+/* The ESL_SQ_BLOCK stream (hmmsearch.c:1317-1361 reader thread -> :1372-1424 workers) as one call: a HOST packed
+ * database is copied to the device in chunks while the MSV filter of earlier chunks runs.  Host outputs (any may be
+ * NULL): sc/status per target, pass_list (ascending target indices passing F1; room for nseq) and *npass.
+ * If opt_ret_db != NULL the uploaded database stays resident and is returned for the later stages. */
+int p7gpu_msvfilter_stream(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
+                           const int64_t *offsets, const int32_t *lengths, int64_t nseq, double F1,
+                           float *sc, int32_t *status, int32_t *pass_list, int64_t *npass, p7gpu_seqdb **opt_ret_db);
 
 /* ------------------------------------------------------------------------------------------------
  * 6. Signature-level wrappers: one target per call, same argument meaning as impl_sse.h:309-344
@@ -183,6 +201,7 @@ typedef struct p7gpu_pipeline_opts {   /* the fields of P7_PIPELINE the path rea
   int32_t do_biasfilter;               /* pli->do_biasfilter                                          */
   int32_t do_max;                      /* --max: F1=F2=F3=1, bias off (p7_pipeline.c:222-229)         */
   int32_t want_specials;               /* 1: return fwd/bck xmx for Forward survivors                  */
+  int32_t stop_after_msv;              /* 1: MSV stage only (BASELINE config 2): counters + the MSV survivors */
 } p7gpu_pipeline_opts;
 
 typedef struct p7gpu_pipeline_counters { /* P7_PIPELINE accounting (hmmer.h:1224-1231), merged like p7_pipeline_Merge */
@@ -199,10 +218,20 @@ typedef struct p7gpu_survivor {        /* one per target that passed the Forward
   int64_t xmx_offset;                  /* float offset of this target's (L+1)*6 block in fwd_xmx/bck_xmx, or -1 */
 } p7gpu_survivor;
 
+typedef struct p7gpu_msv_survivor {    /* stop_after_msv: one per target with P(MSV) <= F1 (p7_pipeline.c:693-694) */
+  int64_t seqidx; int32_t L; int32_t msv_status; float usc;
+} p7gpu_msv_survivor;
+
 typedef struct p7gpu_pipeline_result p7gpu_pipeline_result;
 
 int  p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
                         const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+/* same for a HOST packed database: the upload is streamed under the MSV stage (p7gpu_msvfilter_stream) */
+int  p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
+                             const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                             const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+int64_t                        p7gpu_result_nmsvpass  (const p7gpu_pipeline_result *res);
+const p7gpu_msv_survivor      *p7gpu_result_msvpass   (const p7gpu_pipeline_result *res);
 const p7gpu_pipeline_counters *p7gpu_result_counters (const p7gpu_pipeline_result *res);
 int64_t                        p7gpu_result_nsurvivors(const p7gpu_pipeline_result *res);
 const p7gpu_survivor          *p7gpu_result_survivors (const p7gpu_pipeline_result *res);

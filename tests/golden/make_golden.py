@@ -123,6 +123,7 @@ def main():
                        ("Pkinase", REFROOT + "/tutorial/Pkinase.hmm")):
         p = ref.RefProfile.open(path)
         dump_profile(p, name)
+        p.write_hmm(os.path.join(OUT, "%s.hmm" % name))     # re-serialised by p7_hmmfile_WriteASCII: lets GPU-box tests rebuild the profile
         if name == "globins4":
             seqs = seqs_of(seqdb.read_fasta(REFROOT + "/tutorial/globins45.fa")) + seqs_of(seqdb.synth_db(80, seed=5))
             db = seqdb.pack(seqs)

@@ -1,0 +1,147 @@
+"""The batched p7_Pipeline() (p7gpu_pipeline_run / _run_host, p7gpu_msvfilter_stream) against the reference.
+
+Parity surface: the six pipeline counters (they only match if every pass/fail decision matches),
+the survivor set with its scores, and — after the reference's own unchanged host post-processing of our
+Forward/Backward specials — the final hit list.  Needs a B200.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bits, golden_set, GOLDEN_SETS, GOLDEN
+from biobench2_b200 import engine, seqdb
+from oracle import port, ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = engine.Context(0)
+    yield c
+    c.close()
+
+
+def test_bias_filter_score_bit_exact_vs_golden(ctx):
+    for name in GOLDEN_SETS:
+        g = golden_set(name)
+        prof = engine.Profile(ctx, g.oprofile)
+        db = engine.SeqDB.upload(ctx, g.db)
+        got = engine.biasfilter_batch(ctx, prof, db)
+        keep = g.db.lengths > 0
+        bad = np.nonzero(bits(got[keep]) != bits(g.vec["filtersc"][keep]))[0]
+        assert bad.size == 0, (name, bad[:5], got[keep][bad[:5]], g.vec["filtersc"][keep][bad[:5]])
+        db.close(); prof.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_pipeline_counters_and_survivors_vs_golden(ctx, name):
+    g = golden_set(name)
+    prof = engine.Profile(ctx, g.oprofile)
+    db = engine.SeqDB.upload(ctx, g.db)
+    r = engine.pipeline_run(ctx, prof, db)
+    assert list(r.counters) == list(g.vec["pli_counters"]), (list(r.counters), list(g.vec["pli_counters"]))
+    r2 = engine.pipeline_run_host(ctx, prof, g.db)
+    assert list(r2.counters) == list(g.vec["pli_counters"])
+    assert [s["seqidx"] for s in r2.survivors] == [s["seqidx"] for s in r.survivors]
+    rm = engine.pipeline_run(ctx, prof, db, do_max=True, want_specials=False)
+    assert list(rm.counters) == list(g.vec["pli_counters_max"])
+    # survivors against the CPU oracle's chain (scores: integer stages bit-exact, Forward within 1e-4)
+    o = port.OracleProfile(g.oprofile.view(), g.oprofile)
+    t, pi, eo, _ = g.oprofile.bg_filter
+    oc = o.pipeline(g.db, (t, pi, eo))
+    want = np.nonzero(oc["stage"] == 4)[0]
+    assert [s["seqidx"] for s in r.survivors] == list(want)
+    for s in r.survivors:
+        i = s["seqidx"]
+        assert bits(s["usc"]) == bits(oc["usc"][i]) and bits(s["filtersc"]) == bits(oc["filtersc"][i])
+        if not np.isnan(oc["vfsc"][i]):
+            assert bits(s["vfsc"]) == bits(oc["vfsc"][i])
+        else:
+            assert np.isnan(s["vfsc"]) and s["vit_status"] == -1      # Viterbi skipped (p7_pipeline.c:716)
+        np.testing.assert_allclose(s["fwdsc"], oc["fwdsc"][i], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(s["bcksc"], s["fwdsc"], rtol=1e-4, atol=1e-4)
+    o.close(); db.close(); prof.close()
+
+
+def test_msv_only_mode_and_pass_list(ctx):
+    """stop_after_msv (BASELINE config 2): survivors = targets with P(MSV) <= F1, decided exactly as p7_pipeline.c:691-693."""
+    g = golden_set("synth_M400")
+    hdb = seqdb.synth_db(30000, mean=300, seed=21, degenerate_frac=0.002)
+    prof = engine.Profile(ctx, g.oprofile)
+    db = engine.SeqDB.upload(ctx, hdb)
+    o = port.OracleProfile(g.oprofile.view(), g.oprofile)
+    osc, ost = o.stage_batch("msv", hdb)
+    for F1 in (0.02, 0.3, 1e-4):
+        want = []
+        for s in range(hdb.nseq):
+            L = int(hdb.lengths[s])
+            seq_score = float(np.float32((np.float32(osc[s]) - port.nullsc(L)) / 0.69314718055994529))
+            P = port.gumbel_surv(seq_score, float(np.float32(g.oprofile.evparam[0])), float(np.float32(g.oprofile.evparam[1])))
+            if L > 0 and not (P > F1):
+                want.append(s)
+        r = engine.pipeline_run(ctx, prof, db, F1=F1, stop_after_msv=True)
+        assert list(r.msv_pass["seqidx"]) == want, F1
+        assert r.counters[2] == len(want) and r.counters[0] == hdb.nseq and r.counters[1] == hdb.nres
+        assert np.array_equal(bits(r.msv_pass["usc"]), bits(osc[want]))
+    o.close(); db.close(); prof.close()
+
+
+def test_streamed_host_database_equals_resident(ctx):
+    """p7gpu_msvfilter_stream: several 48 MB chunks, copies overlapped with compute, same scores/statuses/pass list."""
+    g = golden_set("synth_M100")
+    hdb = seqdb.synth_db(420000, mean=350, seed=5)          # ~147 MB of residues -> 4 chunks
+    prof = engine.Profile(ctx, g.oprofile)
+    db = engine.SeqDB.upload(ctx, hdb)
+    sc0, st0 = engine.msvfilter_batch(ctx, prof, db)
+    sc1, st1, pl, kept = engine.msvfilter_stream(ctx, prof, hdb, F1=0.02, keep_db=True)
+    assert np.array_equal(bits(sc0), bits(sc1)) and np.array_equal(st0, st1)
+    r = engine.pipeline_run(ctx, prof, db, stop_after_msv=True)
+    assert np.array_equal(pl, r.msv_pass["seqidx"].astype(np.int32))
+    assert abs(len(pl) / hdb.nseq - 0.02) < 0.02               # F1 = 0.02 on a random database
+    # the database returned by the stream is a normal resident database
+    idx = np.arange(0, hdb.nseq, 5000, dtype=np.int64)
+    a = engine.vitfilter_batch(ctx, prof, db, idx); b = engine.vitfilter_batch(ctx, prof, kept, idx)
+    assert np.array_equal(bits(a[0]), bits(b[0]))
+    kept.close(); db.close(); prof.close()
+
+
+def test_stream_rejects_malformed_database(ctx):
+    g = golden_set("synth_M100")
+    hdb = seqdb.synth_db(100, mean=100, seed=1)
+    bad = seqdb.PackedDB(hdb.residues, hdb.offsets.copy(), hdb.lengths.copy())
+    bad.lengths[50] = 10 ** 6
+    prof = engine.Profile(ctx, g.oprofile)
+    with pytest.raises(engine.P7GpuError) as e:
+        engine.msvfilter_stream(ctx, prof, bad)
+    assert e.value.code == engine.EINVAL
+    prof.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libp7ref.so not built")
+@pytest.mark.parametrize("name,source", [("globins4", "file"), ("fn3", "file"), ("Pkinase", "file")])
+def test_final_hit_list_vs_reference(ctx, name, source):
+    """GPU survivors + specials -> the reference's own domain definition / hit creation (p7_pipeline.c:737-898) ->
+    the same hit list the reference's whole pipeline reports (seqidx order, ndom, flags; scores to 1e-3 bits)."""
+    g = golden_set(name)
+    rp = ref.RefProfile.open(os.path.join(GOLDEN, "%s.hmm" % name))
+    prof = engine.Profile(ctx, g.oprofile)
+    r = engine.pipeline_run_host(ctx, prof, g.db)
+    counters, ref_hits = rp.pipeline(g.db.residues, g.db.offsets, g.db.lengths)
+    assert list(r.counters) == list(counters)
+    sv = r.survivors
+    hits = rp.finish_from_specials(g.db.residues, g.db.offsets, g.db.lengths,
+                                   [s["seqidx"] for s in sv], [s["fwdsc"] for s in sv], r.fwd_xmx, r.bck_xmx,
+                                   [s["xmx_offset"] for s in sv], [s["fwd_totscale"] for s in sv], [s["bck_totscale"] for s in sv],
+                                   int(r.counters[0]), int(r.counters[1]))
+    assert len(ref_hits) >= 4
+    assert [h.seqidx for h in hits] == [h.seqidx for h in ref_hits]
+    assert [h.ndom for h in hits] == [h.ndom for h in ref_hits]
+    assert [h.flags for h in hits] == [h.flags for h in ref_hits]
+    assert [(h.best_dom_ienv, h.best_dom_jenv) for h in hits] == [(h.best_dom_ienv, h.best_dom_jenv) for h in ref_hits]
+    np.testing.assert_allclose([h.score for h in hits], [h.score for h in ref_hits], atol=1e-3)
+    np.testing.assert_allclose([h.lnP for h in hits], [h.lnP for h in ref_hits], rtol=1e-4, atol=1e-3)
+    exact = sum(1 for a, b in zip(hits, ref_hits) if np.float32(a.score).view(np.uint32) == np.float32(b.score).view(np.uint32))
+    print("%s: %d hits, %d with bit-identical bit scores" % (name, len(hits), exact))
+    rp.close(); prof.close()
