@@ -145,3 +145,25 @@ def test_final_hit_list_vs_reference(ctx, name, source):
     exact = sum(1 for a, b in zip(hits, ref_hits) if np.float32(a.score).view(np.uint32) == np.float32(b.score).view(np.uint32))
     print("%s: %d hits, %d with bit-identical bit scores" % (name, len(hits), exact))
     rp.close(); prof.close()
+
+
+def test_partition_independence_of_sharded_search(ctx):
+    """Any sharding gives the same counters and survivors (SURVEY.md §8b 'partition-independence'): run the shards of a
+    3-way split one after the other on this GPU and merge them like rank 0 would."""
+    from biobench2_b200 import search
+    g = golden_set("globins4")
+    prof = engine.Profile(ctx, g.oprofile)
+    whole = engine.pipeline_run_host(ctx, prof, g.db, want_specials=False)
+    ctr = np.zeros(6, np.uint64); recs = []
+    for r in range(3):
+        shard, first = search.shard_db(g.db, r, 3)
+        res = engine.pipeline_run_host(ctx, prof, shard, want_specials=False)
+        ctr += res.counters
+        recs.append(search.survivors_to_records(res, first))
+    rec = np.concatenate(recs)
+    assert list(ctr) == list(whole.counters)
+    assert list(rec["seqidx"]) == [s["seqidx"] for s in whole.survivors]
+    assert np.array_equal(bits(rec["fwdsc"]), bits(np.array([s["fwdsc"] for s in whole.survivors], np.float32)))
+    c1, r1 = search.sharded_pipeline(ctx, prof, g.db)                       # world size 1: no process group needed
+    assert list(c1) == list(whole.counters) and np.array_equal(r1["seqidx"], rec["seqidx"])
+    prof.close()
