@@ -356,7 +356,9 @@ def main():
     if args.e2e_steps > 0:
         h_res = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         h_res.copy_(res[:nbytes]); torch.cuda.synchronize()
-        hdb = PackedDB(h_res.numpy(), offsets, lengths)
+        h_off = torch.empty(args.nseq, dtype=torch.int64, pin_memory=True); h_off.copy_(torch.from_numpy(offsets))
+        h_len = torch.empty(args.nseq, dtype=torch.int32, pin_memory=True); h_len.copy_(torch.from_numpy(lengths))
+        hdb = PackedDB(h_res.numpy(), h_off.numpy(), h_len.numpy())
 
         e2e_out = {}
 
@@ -373,7 +375,7 @@ def main():
         e2e = {"value": total_cells * args.e2e_steps / dt / 1e9, "unit": "GCUPS", "steps": args.e2e_steps,
                "h2d_bytes_per_step": int(nbytes + args.nseq * 12), "d2h_bytes_per_step": int(e2e_out["survivors"] * 24 + 4),
                "ms_per_step": dt / args.e2e_steps * 1e3, "survivors": e2e_out["survivors"], "counters": e2e_out["counters"],
-               "api": "p7gpu_pipeline_run_host(stop_after_msv): pinned host packed DB streamed in 48 MB chunks under the "
+               "api": "p7gpu_pipeline_run_host(stop_after_msv): pinned host packed DB streamed in 8-96 MB chunks (each sorted longest-first on the device) under the "
                       "SSV/MSV kernels; the MSV survivor records (index, L, status, score) come back to the host"}
 
     cpu_baseline = None

@@ -435,8 +435,16 @@ void p7gpu_seqdb_destroy(p7gpu_seqdb *db)
   if (!db) return;
   cudaSetDevice(db->ctx->device);
   cudaStreamSynchronize(db->ctx->stream);
-  if (db->owns) { cudaFree((void *) db->d_res); cudaFree((void *) db->d_off); cudaFree((void *) db->d_len); }
-  cudaFree(db->d_order);
+  if (db->pooled) {
+    cudaStream_t s = db->ctx->stream;
+    if (db->d_res) cudaFreeAsync((void *) db->d_res, s);
+    if (db->d_off) cudaFreeAsync((void *) db->d_off, s);
+    if (db->d_len) cudaFreeAsync((void *) db->d_len, s);
+    if (db->d_order) cudaFreeAsync(db->d_order, s);
+  } else {
+    if (db->owns) { cudaFree((void *) db->d_res); cudaFree((void *) db->d_off); cudaFree((void *) db->d_len); }
+    cudaFree(db->d_order);
+  }
   delete db;
 }
 int64_t p7gpu_seqdb_nseq(const p7gpu_seqdb *db) { return db ? db->nseq : 0; }

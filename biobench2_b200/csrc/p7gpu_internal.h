@@ -143,6 +143,7 @@ struct p7gpu_seqdb {
   int64_t nseq = 0, nbytes = 0, nres = 0;
   int32_t max_length = 0;
   bool owns = false;
+  bool pooled = false;                 // buffers came from cudaMallocAsync on ctx->stream (streamed path)
   p7g::DbView view() const { p7g::DbView v; v.res = d_res; v.off = d_off; v.len = d_len; v.order = d_order; v.first = 0; v.max_length = max_length; return v; }
 };
 

@@ -11,7 +11,10 @@
 #include "p7gpu_internal.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 struct p7gpu_pipeline_result {
@@ -22,6 +25,19 @@ struct p7gpu_pipeline_result {
 };
 
 namespace p7g {
+
+// P7GPU_TRACE=1: wall-clock checkpoints of the batched entry points on stderr
+struct Trace {
+  bool on; std::chrono::steady_clock::time_point t0, last;
+  Trace() : on(getenv("P7GPU_TRACE") != nullptr) { t0 = last = std::chrono::steady_clock::now(); }
+  void mark(const char *what) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[p7gpu] %-28s +%8.3f ms  (total %8.3f ms)\n", what,
+            std::chrono::duration<double, std::milli>(now - last).count(), std::chrono::duration<double, std::milli>(now - t0).count());
+    last = now;
+  }
+};
 
 // stream-ordered device buffer
 struct DevBuf {
@@ -239,105 +255,135 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
 // Streamed MSV pass over a HOST database: the packed residues are copied in chunks on a copy stream while the SSV/MSV
 // kernels of earlier chunks run on alternating lanes.  The database stays resident in HBM (returned in *ret_db).
 // ------------------------------------------------------------------------------------------------------------------
+__global__ void iota_from_kernel(int32_t *v, int32_t first, int32_t n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = first + i;
+}
+
 static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
                       const int64_t *offsets, const int32_t *lengths, int64_t nseq, double F1,
                       float *h_sc, int32_t *h_status, float *d_sc, int32_t *d_st, int32_t *d_pass, unsigned int *d_pass_count,
                       p7gpu_seqdb **ret_db)
 {
   if (nseq > 0x7fffffffLL) { set_error("stream: more than 2^31-1 targets per device"); return P7GPU_EINVAL; }
-  p7gpu_seqdb *db = new p7gpu_seqdb();
-  db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->owns = true;
-  const size_t padded = ((size_t) nbytes + 15) / 16 * 16 + 32;
-  uint8_t *d_res = nullptr; int64_t *d_off = nullptr; int32_t *d_len = nullptr;
-  auto fail = [&](int code) { p7gpu_seqdb_destroy(db); return code; };
-#define S_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(P7GPU_ESYS); } } while (0)
-  S_CUDA(cudaMalloc(&d_res, padded));               db->d_res = d_res;
-  S_CUDA(cudaMalloc(&d_off, 8 * (size_t) std::max<int64_t>(nseq, 1))); db->d_off = d_off;
-  S_CUDA(cudaMalloc(&d_len, 4 * (size_t) std::max<int64_t>(nseq, 1))); db->d_len = d_len;
-  cudaStream_t cs = ctx->copy_stream;
-  // everything queued here comes after what the caller already queued on the main stream
-  cudaEvent_t ev_main; S_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
-  S_CUDA(cudaEventRecord(ev_main, ctx->stream));
-  S_CUDA(cudaStreamWaitEvent(cs, ev_main, 0));
-  for (int l = 1; l <= 2; l++) S_CUDA(cudaStreamWaitEvent(ctx->lanes[l].stream, ev_main, 0));
-  S_CUDA(cudaMemsetAsync(d_res + (padded - 64), 0xff, 64, cs));
-  S_CUDA(cudaMemsetAsync(d_pass_count, 0, sizeof(unsigned int), cs));
-
-  const int64_t chunk_bytes = (int64_t) 48 << 20;
-  std::vector<cudaEvent_t> events;
-  int64_t nores_cap = 0;
-  // per-lane eslENORESULT pair lists, sized for the largest chunk (bounded by chunk_bytes / 1 byte per target)
+  Trace tr;
+  // ---- chunk plan: sizes grow from 8 MB (short exposed first copy) to 96 MB (few kernel tails) ----
+  struct Chunk { int64_t s_lo, s_hi; };
+  std::vector<Chunk> plan;
+  int64_t max_chunk_seqs = 1;
   {
-    int64_t s = 0;
+    int64_t s = 0, bytes = (int64_t) 8 << 20;
     while (s < nseq) {
-      int64_t e = s, lim = offsets[s] + chunk_bytes;
-      // bisect for the first target starting beyond lim
+      const int64_t lim = offsets[s] + bytes;
       int64_t lo = s + 1, hi = nseq;
       while (lo < hi) { int64_t mid = (lo + hi) / 2; if (offsets[mid] <= lim) lo = mid + 1; else hi = mid; }
-      e = lo;
-      nores_cap = std::max(nores_cap, e - s);
-      s = e;
+      plan.push_back({s, lo});
+      max_chunk_seqs = std::max(max_chunk_seqs, lo - s);
+      s = lo;
+      bytes = std::min<int64_t>(bytes * 2, (int64_t) 96 << 20);
     }
   }
-  int64_t *d_nores[3] = {nullptr, nullptr, nullptr};
-  for (int l = 1; l <= 2; l++) S_CUDA(cudaMalloc(&d_nores[l], 16 * (size_t) std::max<int64_t>(nores_cap, 1)));
-  auto cleanup = [&]() { for (auto e : events) cudaEventDestroy(e); cudaEventDestroy(ev_main); cudaFree(d_nores[1]); cudaFree(d_nores[2]); };
-#undef S_CUDA
-#define S_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); cudaDeviceSynchronize(); cleanup(); return fail(P7GPU_ESYS); } } while (0)
-#define S_CHECK(call) do { int s__ = (call); if (s__ != P7GPU_OK) { cudaDeviceSynchronize(); cleanup(); return fail(s__); } } while (0)
+  cudaStream_t ms = ctx->stream, cs = ctx->copy_stream;
+  p7gpu_seqdb *db = new p7gpu_seqdb();
+  db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->owns = true; db->pooled = true;
+  const size_t padded = ((size_t) nbytes + 15) / 16 * 16 + 32;
+  uint8_t *d_res = nullptr; int64_t *d_off = nullptr; int32_t *d_len = nullptr;
+  int64_t *d_nores[3] = {nullptr, nullptr, nullptr}; void *d_sorttmp[3] = {nullptr, nullptr, nullptr};
+  int32_t *d_keys_out[3] = {nullptr, nullptr, nullptr}, *d_iota[3] = {nullptr, nullptr, nullptr};
+  size_t sort_tmp_bytes = 0;
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t ev_main = nullptr;
+  auto cleanup = [&]() {
+    for (auto e : events) cudaEventDestroy(e);
+    if (ev_main) cudaEventDestroy(ev_main);
+    for (int l = 1; l <= 2; l++) {
+      if (d_nores[l]) cudaFreeAsync(d_nores[l], ms);
+      if (d_sorttmp[l]) cudaFreeAsync(d_sorttmp[l], ms);
+      if (d_keys_out[l]) cudaFreeAsync(d_keys_out[l], ms);
+      if (d_iota[l]) cudaFreeAsync(d_iota[l], ms);
+    }
+  };
+  auto fail = [&](int code) { cudaDeviceSynchronize(); cleanup(); p7gpu_seqdb_destroy(db); return code; };
+#define S_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(P7GPU_ESYS); } } while (0)
+#define S_CHECK(call) do { int s__ = (call); if (s__ != P7GPU_OK) return fail(s__); } while (0)
+  // stream-ordered allocations: after the first call they come back from the pool without touching the driver
+  S_CUDA(cudaMallocAsync((void **) &d_res, padded, ms));                                       db->d_res = d_res;
+  S_CUDA(cudaMallocAsync((void **) &d_off, 8 * (size_t) std::max<int64_t>(nseq, 1), ms));      db->d_off = d_off;
+  S_CUDA(cudaMallocAsync((void **) &d_len, 4 * (size_t) std::max<int64_t>(nseq, 1), ms));      db->d_len = d_len;
+  S_CUDA(cudaMallocAsync((void **) &db->d_order, 4 * (size_t) std::max<int64_t>(nseq, 1), ms));
+  S_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp_bytes, (const int32_t *) nullptr, (int32_t *) nullptr,
+                                                   (const int32_t *) nullptr, (int32_t *) nullptr, (int) max_chunk_seqs, 0, 32, ms));
+  for (int l = 1; l <= 2; l++) {
+    S_CUDA(cudaMallocAsync((void **) &d_nores[l], 16 * (size_t) max_chunk_seqs, ms));
+    S_CUDA(cudaMallocAsync(&d_sorttmp[l], std::max<size_t>(sort_tmp_bytes, 256), ms));
+    S_CUDA(cudaMallocAsync((void **) &d_keys_out[l], 4 * (size_t) max_chunk_seqs, ms));
+    S_CUDA(cudaMallocAsync((void **) &d_iota[l], 4 * (size_t) max_chunk_seqs, ms));
+  }
+  S_CUDA(cudaMemsetAsync(d_res + (padded - 64), 0xff, 64, ms));
+  S_CUDA(cudaMemsetAsync(d_pass_count, 0, sizeof(unsigned int), ms));
+  // everything queued on the copy stream and the lanes comes after what is already queued on the main stream
+  S_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+  S_CUDA(cudaEventRecord(ev_main, ms));
+  S_CUDA(cudaStreamWaitEvent(cs, ev_main, 0));
+  for (int l = 1; l <= 2; l++) S_CUDA(cudaStreamWaitEvent(ctx->lanes[l].stream, ev_main, 0));
+  tr.mark("stream: setup");
 
-  int64_t s_lo = 0, nres = 0; int32_t Lmax = 0; int chunk = 0;
-  while (s_lo < nseq) {
-    const int64_t lim = offsets[s_lo] + chunk_bytes;
-    int64_t lo = s_lo + 1, hi = nseq;
-    while (lo < hi) { int64_t mid = (lo + hi) / 2; if (offsets[mid] <= lim) lo = mid + 1; else hi = mid; }
-    const int64_t s_hi = lo;
+  int64_t nres = 0; int32_t Lmax = 0;
+  for (size_t c = 0; c < plan.size(); c++) {
+    const int64_t s_lo = plan[c].s_lo, s_hi = plan[c].s_hi, cn = s_hi - s_lo;
     // validate this chunk's targets (same checks as p7gpu_seqdb_upload) while earlier chunks run
-    int32_t cLmax = 0;
+    int32_t cLmax = 0; int64_t cres = 0; bool bad = false;
+    int64_t prev_end = s_lo > 0 ? offsets[s_lo - 1] + lengths[s_lo - 1] : 0;
     for (int64_t s = s_lo; s < s_hi; s++) {
       const int64_t o = offsets[s]; const int32_t L = lengths[s];
-      if (L < 0 || o < 1 || o + L >= nbytes || (s > s_lo && o < offsets[s - 1] + lengths[s - 1] + 1)) {
-        set_error("stream: target %lld (offset %lld, length %d) does not fit the packed array of %lld bytes / overlaps its predecessor",
-                  (long long) s, (long long) o, L, (long long) nbytes);
-        cudaDeviceSynchronize(); cleanup(); return fail(P7GPU_EINVAL);
-      }
-      cLmax = std::max(cLmax, L); nres += L;
+      bad |= (L < 0) | (o <= prev_end) | (o + L >= nbytes);
+      prev_end = o + (L > 0 ? L : 0);
+      cLmax = std::max(cLmax, L); cres += L;
     }
-    Lmax = std::max(Lmax, cLmax);
+    if (bad) {
+      set_error("stream: targets %lld..%lld: an (offset, length) pair does not fit the packed array of %lld bytes or overlaps its predecessor",
+                (long long) s_lo, (long long) s_hi - 1, (long long) nbytes);
+      return fail(P7GPU_EINVAL);
+    }
+    nres += cres; Lmax = std::max(Lmax, cLmax);
     S_CHECK(ensure_len_table(prof, Lmax, F1));
     const int64_t b_lo = (offsets[s_lo] - 1) & ~15LL;
     const int64_t b_hi = std::min<int64_t>(nbytes, (offsets[s_hi - 1] + lengths[s_hi - 1] + 1 + 15) & ~15LL);
     S_CUDA(cudaMemcpyAsync(d_res + b_lo, residues + b_lo, (size_t) (b_hi - b_lo), cudaMemcpyHostToDevice, cs));
-    S_CUDA(cudaMemcpyAsync(d_off + s_lo, offsets + s_lo, 8 * (size_t) (s_hi - s_lo), cudaMemcpyHostToDevice, cs));
-    S_CUDA(cudaMemcpyAsync(d_len + s_lo, lengths + s_lo, 4 * (size_t) (s_hi - s_lo), cudaMemcpyHostToDevice, cs));
+    S_CUDA(cudaMemcpyAsync(d_off + s_lo, offsets + s_lo, 8 * (size_t) cn, cudaMemcpyHostToDevice, cs));
+    S_CUDA(cudaMemcpyAsync(d_len + s_lo, lengths + s_lo, 4 * (size_t) cn, cudaMemcpyHostToDevice, cs));
     cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
     S_CUDA(cudaEventRecord(ev, cs));
-    const int lane = 1 + (chunk & 1);
+    const int lane = 1 + (int) (c & 1);
     const Lane &ln = ctx->lanes[lane];
     S_CUDA(cudaStreamWaitEvent(ln.stream, ev, 0));
-    DbView v; v.res = d_res; v.off = d_off; v.len = d_len; v.order = nullptr; v.first = s_lo; v.max_length = Lmax;
+    // work order of the chunk: longest target first, so the kernel's tail is short
+    iota_from_kernel<<<(unsigned) ((cn + 255) / 256), 256, 0, ln.stream>>>(d_iota[lane], (int32_t) s_lo, (int32_t) cn);
+    S_CUDA(cub::DeviceRadixSort::SortPairsDescending(d_sorttmp[lane], sort_tmp_bytes, d_len + s_lo, d_keys_out[lane],
+                                                     d_iota[lane], db->d_order + s_lo, (int) cn, 0, 32, ln.stream));
+    ctx->launches += 4;
+    DbView v; v.res = d_res; v.off = d_off; v.len = d_len; v.order = db->d_order + s_lo; v.first = s_lo; v.max_length = Lmax;
     unsigned int *d_nores_count = ln.counters + CTR_NORES_COUNT;
-    S_CHECK(launch_ssv(ctx, lane, prof, v, nullptr, s_hi - s_lo, d_sc, d_st, d_nores[lane], d_nores_count, d_pass, d_pass_count));
-    S_CHECK(launch_msv_j(ctx, lane, prof, v, d_nores[lane], d_nores_count, s_hi - s_lo, d_sc, d_st, d_pass, d_pass_count));
-    if (h_sc)     S_CUDA(cudaMemcpyAsync(h_sc + s_lo, d_sc + s_lo, 4 * (size_t) (s_hi - s_lo), cudaMemcpyDeviceToHost, ln.stream));
-    if (h_status) S_CUDA(cudaMemcpyAsync(h_status + s_lo, d_st + s_lo, 4 * (size_t) (s_hi - s_lo), cudaMemcpyDeviceToHost, ln.stream));
-    s_lo = s_hi; chunk++;
+    S_CHECK(launch_ssv(ctx, lane, prof, v, nullptr, cn, d_sc, d_st, d_nores[lane], d_nores_count, d_pass, d_pass_count));
+    S_CHECK(launch_msv_j(ctx, lane, prof, v, d_nores[lane], d_nores_count, cn, d_sc, d_st, d_pass, d_pass_count));
+    if (h_sc)     S_CUDA(cudaMemcpyAsync(h_sc + s_lo, d_sc + s_lo, 4 * (size_t) cn, cudaMemcpyDeviceToHost, ln.stream));
+    if (h_status) S_CUDA(cudaMemcpyAsync(h_status + s_lo, d_st + s_lo, 4 * (size_t) cn, cudaMemcpyDeviceToHost, ln.stream));
   }
-  // the main stream continues after both lanes
-  for (int l = 1; l <= 2; l++) {
+  // the main stream continues after both lanes and the copy stream
+  for (int l = 0; l <= 2; l++) {
     cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
-    S_CUDA(cudaEventRecord(ev, ctx->lanes[l].stream));
-    S_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    S_CUDA(cudaEventRecord(ev, l == 0 ? cs : ctx->lanes[l].stream));
+    S_CUDA(cudaStreamWaitEvent(ms, ev, 0));
   }
-  {
-    cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
-    S_CUDA(cudaEventRecord(ev, cs));
-    S_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
-  }
-  S_CUDA(cudaStreamSynchronize(ctx->stream));
+  tr.mark("stream: all chunks queued");
+  S_CUDA(cudaStreamSynchronize(ms));
+  tr.mark("stream: drained");
   cleanup();
 #undef S_CUDA
 #undef S_CHECK
+  // the per-chunk orders together are not a global longest-first order; later stages use explicit index lists
+  cudaFreeAsync(db->d_order, ms); db->d_order = nullptr;
   db->nres = nres; db->max_length = Lmax;
   *ret_db = db;
   return P7GPU_OK;
@@ -419,15 +465,23 @@ int p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uin
     cudaStream_t st = ctx->stream;
     unsigned npass = 0;
     unsigned int *d_pass_count = ctx->lanes[0].counters + CTR_PASS_COUNT;
+    Trace tr;
     auto body = [&]() -> int {
       P7G_CHECK(d_sc.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_st.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_pass.alloc(4 * (size_t) nseq, st));
+      tr.mark("alloc");
       P7G_CHECK(stream_msv(ctx, prof, residues, nbytes, offsets, lengths, nseq, F1, nullptr, nullptr,
                            d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), d_pass_count, &db));
+      tr.mark("stream_msv");
       P7G_CHECK(read_count(ctx, d_pass_count, &npass));
-      return pipeline_after_msv(ctx, prof, db, opts, d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), npass, res);
+      int rc = pipeline_after_msv(ctx, prof, db, opts, d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), npass, res);
+      tr.mark("after_msv");
+      return rc;
     };
     status = body();
     cudaStreamSynchronize(st);
+    tr.mark("sync");
+    p7gpu_seqdb_destroy(db); db = nullptr;
+    tr.mark("db destroy");
   }
   p7gpu_seqdb_destroy(db);
   if (status != P7GPU_OK) { delete res; return status; }

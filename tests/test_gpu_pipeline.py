@@ -89,7 +89,7 @@ def test_msv_only_mode_and_pass_list(ctx):
 
 
 def test_streamed_host_database_equals_resident(ctx):
-    """p7gpu_msvfilter_stream: several 48 MB chunks, copies overlapped with compute, same scores/statuses/pass list."""
+    """p7gpu_msvfilter_stream: several chunks, copies overlapped with compute, same scores/statuses/pass list."""
     g = golden_set("synth_M100")
     hdb = seqdb.synth_db(420000, mean=350, seed=5)          # ~147 MB of residues -> 4 chunks
     prof = engine.Profile(ctx, g.oprofile)
