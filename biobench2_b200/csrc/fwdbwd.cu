@@ -49,7 +49,9 @@ __device__ __forceinline__ void stage_tables(const FbParams &p, float *s_fb, con
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int C, bool SMEM>
+// TREG: the per-node transition vectors live in registers (C <= 16) so that the row loop is bound by the FP32 pipe
+// instead of by ~11 LDS per cell (see vit.cu).
+template <int C, bool SMEM, bool TREG>
 __global__ void __launch_bounds__(DP_THREADS) fwd_kernel(const FbParams p)
 {
   extern __shared__ __align__(16) float s_fb[];
@@ -59,6 +61,16 @@ __global__ void __launch_bounds__(DP_THREADS) fwd_kernel(const FbParams p)
   const float *tBM = tf + 0 * C * 32 + lane, *tMM = tf + 1 * C * 32 + lane, *tIM = tf + 2 * C * 32 + lane,
               *tDM = tf + 3 * C * 32 + lane, *tMD = tf + 4 * C * 32 + lane, *tMI = tf + 5 * C * 32 + lane,
               *tII = tf + 6 * C * 32 + lane, *tDD = tf + 7 * C * 32 + lane;
+  float rBM[TREG ? C : 1], rMM[TREG ? C : 1], rIM[TREG ? C : 1], rDM[TREG ? C : 1], rMD[TREG ? C : 1], rMI[TREG ? C : 1],
+        rII[TREG ? C : 1], rDD[TREG ? C : 1];
+  if (TREG) {
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+      rBM[j] = tBM[j * 32]; rMM[j] = tMM[j * 32]; rIM[j] = tIM[j * 32]; rDM[j] = tDM[j * 32];
+      rMD[j] = tMD[j * 32]; rMI[j] = tMI[j * 32]; rII[j] = tII[j * 32]; rDD[j] = tDD[j * 32];
+    }
+  }
+#define T_(name, j) (TREG ? r##name[j] : t##name[(j) * 32])
   long long s, out;
   while (next_target(p.c, lane, &s, &out)) {
     const int L = p.c.len[s];
@@ -81,17 +93,17 @@ __global__ void __launch_bounds__(DP_THREADS) fwd_kernel(const FbParams p)
       float sumM = 0.f, dcv = 0.f;
 #pragma unroll
       for (int j = 0; j < C; j++) {                                   // :318-345
-        float sv = xB * tBM[j * 32];
-        sv = sv + pm * tMM[j * 32];
-        sv = sv + pi * tIM[j * 32];
-        sv = sv + pd * tDM[j * 32];
+        float sv = xB * T_(BM, j);
+        sv = sv + pm * T_(MM, j);
+        sv = sv + pi * T_(IM, j);
+        sv = sv + pd * T_(DM, j);
         sv = sv * rfx[j * 32];
         sumM += sv;
         pm = mp[j]; pi = ip[j]; pd = dp[j];
         mp[j] = sv;
         dp[j] = dcv;                                                  // M(i,k-1) * tMD(k-1)
-        dcv = sv * tMD[j * 32];
-        ip[j] = pm * tMI[j * 32] + pi * tII[j * 32];
+        dcv = sv * T_(MD, j);
+        ip[j] = pm * T_(MI, j) + pi * T_(II, j);
       }
       {
         float d0 = __shfl_up_sync(0xffffffffu, dcv, 1);
@@ -100,7 +112,7 @@ __global__ void __launch_bounds__(DP_THREADS) fwd_kernel(const FbParams p)
       // D->D paths (:351-399): D_k = P_k + D_{k-1} * tDD_{k-1}.  Lane map: out = A + B * carry
       float A = 0.f, B = 1.f;
 #pragma unroll
-      for (int j = 0; j < C; j++) { const float t = tDD[j * 32]; A = (dp[j] + A) * t; B = B * t; }
+      for (int j = 0; j < C; j++) { const float t = T_(DD, j); A = (dp[j] + A) * t; B = B * t; }
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         float A2 = __shfl_up_sync(0xffffffffu, A, d), B2 = __shfl_up_sync(0xffffffffu, B, d);
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(DP_THREADS) fwd_kernel(const FbParams p)
 #pragma unroll
       for (int j = 0; j < C; j++) {
         dp[j] = dp[j] + carry;
-        carry = dp[j] * tDD[j * 32];
+        carry = dp[j] * T_(DD, j);
         sumD += dp[j];
       }
       xE = warp_sum(sumM + sumD);                                     // :402-411
@@ -141,6 +153,7 @@ __global__ void __launch_bounds__(DP_THREADS) fwd_kernel(const FbParams p)
       if (p.totscale) p.totscale[out] = totscale;
     }
   }
+#undef T_
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -299,7 +312,7 @@ static int launch_fb_c(p7gpu_ctx *ctx, cudaStream_t stream, const FbParams &p)
   const bool use_smem = smem + 1024 <= (size_t) ctx->smem_optin;
   void (*kern)(const FbParams);
   if (BWD) kern = use_smem ? bwd_kernel<C, true> : bwd_kernel<C, false>;
-  else     kern = use_smem ? fwd_kernel<C, true> : fwd_kernel<C, false>;
+  else     kern = use_smem ? fwd_kernel<C, true, (C <= 16)> : fwd_kernel<C, false, false>;
   const size_t dyn = use_smem ? smem : 0;
   if (use_smem) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
   int occ = 0;

@@ -14,7 +14,12 @@
 
 namespace p7g {
 
-constexpr int SSV_THREADS = 256;
+// Where the SSV gain table lives: 0 = global memory (L1/L2), 1 = all 30 rows in shared memory, 2 = "compact": the 20
+// canonical residues + the pad row in shared memory, the rare degenerate codes read from global (warp-uniform branch).
+constexpr int SSV_GLOBAL = 0, SSV_SMEM = 1, SSV_COMPACT = 2;
+constexpr int SSV_COMPACT_ROWS = 21;
+constexpr int ssv_mode_for(int Q)    { return Q <= 27 ? SSV_SMEM : (Q <= 41 ? SSV_COMPACT : SSV_GLOBAL); }
+constexpr int ssv_threads_for(int Q) { return Q <= 13 ? 256 : 512; }      // big tables leave room for one CTA per SM only
 constexpr int MSVJ_THREADS = 128;
 
 struct SsvParams {
@@ -71,13 +76,19 @@ __device__ __forceinline__ int ssv_epilogue(int maxu, int tjb, const MsvScalars 
   return P7GPU_OK;
 }
 
-template <int Q, bool SMEM>
-__global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvParams p)
+template <int Q, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
 {
   extern __shared__ __align__(16) uint32_t s_tab[];
-  if (SMEM) {
+  constexpr bool SMEM = MODE != SSV_GLOBAL;
+  if (MODE == SSV_SMEM) {
     const int nwords = NTABROWS * p.rowWords;
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_tab[i] = __ldg(p.tab + i);
+    __syncthreads();
+  } else if (MODE == SSV_COMPACT) {
+    const int nwords = 20 * p.rowWords;                                   // rows 0..19 as they are, the pad row as row 20
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_tab[i] = __ldg(p.tab + i);
+    for (int i = threadIdx.x; i < p.rowWords; i += blockDim.x) s_tab[nwords + i] = __ldg(p.tab + PADRES * p.rowWords + i);
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
@@ -127,8 +138,9 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvParams p)
         for (int r = 0; r < DIAG_CHUNK; r++) {
           const uint32_t x = __byte_perm(w[r >> 2], 0u, 0x4440u | (r & 3));
           uint32_t g[Q];
-          if (SMEM) {
-            const uint32_t a = x * rowBytes + cbase;
+          if (SMEM && (MODE == SSV_SMEM || x < 20u || x == (uint32_t) PADRES)) {
+            const uint32_t xr = (MODE == SSV_COMPACT) ? min(x, 20u) : x;
+            const uint32_t a = xr * rowBytes + cbase;
 #pragma unroll
             for (int q = 0; q < Q; q++) asm("ld.shared.u32 %0, [%1];" : "=r"(g[q]) : "r"(a + 4u * (uint32_t) (r + q)));
           } else {
@@ -246,29 +258,38 @@ __global__ void __launch_bounds__(MSVJ_THREADS) msvj_kernel(const MsvjParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int Q, bool SMEM>
-static int launch_ssv_q(p7gpu_ctx *ctx, cudaStream_t stream, const SsvParams &p, size_t tabBytes)
+template <int Q, int MODE, int THREADS>
+static int launch_ssv_q(p7gpu_ctx *ctx, cudaStream_t stream, const SsvParams &p, size_t smem)
 {
-  auto kern = ssv_kernel<Q, SMEM>;
-  size_t smem = SMEM ? tabBytes : 0;
+  auto kern = ssv_kernel<Q, MODE, THREADS>;
   static int occ_dev[64];                         // per template instance (one geometry), per device; 0 = unknown
   int &occ_cache = occ_dev[ctx->device & 63];
   if (occ_cache <= 0) {
-    if (SMEM) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (smem) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int occ = 0;
-    P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSV_THREADS, smem));
-    if (occ < 1) { set_error("ssv_kernel<%d>: zero occupancy (smem %zu)", Q, smem); return P7GPU_ESYS; }
+    P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    if (occ < 1) { set_error("ssv_kernel<%d,%d,%d>: zero occupancy (smem %zu)", Q, MODE, THREADS, smem); return P7GPU_ESYS; }
     occ_cache = occ;
   }
-  long long warps_needed = p.n;
   long long blocks = (long long) ctx->sm_count * occ_cache;
-  long long need_blocks = (warps_needed + (SSV_THREADS / 32) - 1) / (SSV_THREADS / 32);
+  long long need_blocks = (p.n + (THREADS / 32) - 1) / (THREADS / 32);
   if (need_blocks < blocks) blocks = need_blocks;
   if (blocks < 1) blocks = 1;
-  { LaunchTimer t(ctx, P7GPU_KERNEL_SSV, stream); kern<<<(unsigned) blocks, SSV_THREADS, smem, stream>>>(p); }
+  { LaunchTimer t(ctx, P7GPU_KERNEL_SSV, stream); kern<<<(unsigned) blocks, THREADS, smem, stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;
+}
+
+// the preferred placement for this Q when its shared-memory footprint fits the device, else the global-memory form
+template <int Q>
+static int launch_ssv_pick(p7gpu_ctx *ctx, cudaStream_t stream, const SsvParams &p)
+{
+  constexpr int MODE = ssv_mode_for(Q), THREADS = ssv_threads_for(Q);
+  const size_t rows = MODE == SSV_SMEM ? NTABROWS : (MODE == SSV_COMPACT ? SSV_COMPACT_ROWS : 0);
+  const size_t smem = rows * (size_t) p.rowWords * 4;
+  if (MODE != SSV_GLOBAL && smem + 1024 <= (size_t) ctx->smem_optin) return launch_ssv_q<Q, MODE, THREADS>(ctx, stream, p, smem);
+  return launch_ssv_q<Q, SSV_GLOBAL, 256>(ctx, stream, p, 0);
 }
 
 #define P7G_ODD_Q_CASES(X) \
@@ -291,10 +312,8 @@ int launch_ssv(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   p.work_counter = (unsigned long long *) (ln.counters + CTR_SSV_WORK);
   // work counter (2 words) + the lane's eslENORESULT count (CTR_NORES_COUNT = CTR_SSV_WORK + 2)
   P7G_CUDA(cudaMemsetAsync(ln.counters + CTR_SSV_WORK, 0, 4 * sizeof(unsigned int), ln.stream));
-  const size_t tabBytes = prof->geom.tableBytes();
-  const bool smem_ok = tabBytes + 1024 <= (size_t) ctx->smem_optin;
   switch (prof->geom.Q) {
-#define X(QV) case QV: return smem_ok ? launch_ssv_q<QV, true>(ctx, ln.stream, p, tabBytes) : launch_ssv_q<QV, false>(ctx, ln.stream, p, tabBytes);
+#define X(QV) case QV: return launch_ssv_pick<QV>(ctx, ln.stream, p);
     P7G_ODD_Q_CASES(X)
 #undef X
   default: set_error("SSV: unsupported Q=%d (M=%d too large; max M is %d)", prof->geom.Q, prof->M, 64 * MAX_Q - 1); return P7GPU_EINVAL;

@@ -21,10 +21,14 @@ struct VitParams {
 constexpr int VNEG = -32768;
 constexpr int VNOCARRY = -(1 << 28);
 
-template <int C, bool SMEM>
+// TREG: the 7 per-node transition vectors BM,MM,IM,DM,MD,MI,II live in registers (7*C per lane) instead of being
+// re-read from shared memory on every row: the row loop is then bound by the integer pipe (10 ops/cell), not by the
+// 9 LDS per cell of the table-in-smem form.  Used when 7*C registers fit (C <= 16, M <= 512).
+template <int C, bool SMEM, bool TREG>
 __global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
 {
   extern __shared__ __align__(16) int16_t s_vit[];
+  __shared__ int s_ptab[C * 32];
   const int16_t *tw = p.tw, *rw = p.rw;
   if (SMEM) {
     const int ntw = 8 * C * 32, nrw = NTABROWS * C * 32;
@@ -37,6 +41,30 @@ __global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
   const int16_t *tBM = tw + 0 * C * 32 + lane, *tMM = tw + 1 * C * 32 + lane, *tIM = tw + 2 * C * 32 + lane,
                 *tDM = tw + 3 * C * 32 + lane, *tMD = tw + 4 * C * 32 + lane, *tMI = tw + 5 * C * 32 + lane,
                 *tII = tw + 6 * C * 32 + lane, *tDD = tw + 7 * C * 32 + lane;
+
+  int rBM[TREG ? C : 1], rMM[TREG ? C : 1], rIM[TREG ? C : 1], rDM[TREG ? C : 1], rMD[TREG ? C : 1], rMI[TREG ? C : 1], rII[TREG ? C : 1];
+  if (TREG) {
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+      rBM[j] = tBM[j * 32]; rMM[j] = tMM[j * 32]; rIM[j] = tIM[j * 32]; rDM[j] = tDM[j * 32];
+      rMD[j] = tMD[j * 32]; rMI[j] = tMI[j * 32]; rII[j] = tII[j * 32];
+    }
+  }
+#define T_(name, j) (TREG ? r##name[j] : (int) t##name[(j) * 32])
+  // row-invariant sums of tDD for the lazy-F scan: PT[j] = sum of this lane's tDD[0..j-1] (shared memory, per lane),
+  // S_lane = sum over all earlier lanes' cells, S_next = S_lane + this lane's total
+  const int *s_pt = s_ptab + lane;
+  int S_lane, S_next;
+  {
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < C; j++) { if (threadIdx.x < 32) s_ptab[j * 32 + lane] = acc; acc += (int) tDD[j * 32]; }
+    int incl = acc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    S_next = incl; S_lane = incl - acc;
+    __syncthreads();
+  }
 
   long long s, out;
   while (next_target(p.c, lane, &s, &out)) {
@@ -59,18 +87,18 @@ __global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
       int xEl = VNEG, Dml = VNEG, dcv = VNEG;
 #pragma unroll
       for (int j = 0; j < C; j++) {
-        int sv = __viaddmax_s32(xB, (int) tBM[j * 32], VNEG);          // vitfilter.c:146-150
-        sv = __viaddmax_s32(pm, (int) tMM[j * 32], sv);
-        sv = __viaddmax_s32(pi, (int) tIM[j * 32], sv);
-        sv = __viaddmax_s32(pd, (int) tDM[j * 32], sv);
+        int sv = __viaddmax_s32(xB, T_(BM, j), VNEG);                  // vitfilter.c:146-150
+        sv = __viaddmax_s32(pm, T_(MM, j), sv);
+        sv = __viaddmax_s32(pi, T_(IM, j), sv);
+        sv = __viaddmax_s32(pd, T_(DM, j), sv);
         sv = __viaddmax_s32(sv, (int) rwx[j * 32], VNEG);
         xEl = max(xEl, sv);
         pm = mp[j]; pi = ip[j]; pd = dp[j];                           // :155-157
         mp[j] = sv;
         dp[j] = dcv;                                                  // D(i,k) = M(i,k-1)+tMD so far (:160-161)
-        dcv = __viaddmax_s32(sv, (int) tMD[j * 32], VNEG);            // :166
+        dcv = __viaddmax_s32(sv, T_(MD, j), VNEG);                    // :166
         Dml = max(Dml, dcv);
-        ip[j] = __viaddmax_s32(pi, (int) tII[j * 32], __viaddmax_s32(pm, (int) tMI[j * 32], VNEG));   // :170-171
+        ip[j] = __viaddmax_s32(pi, T_(II, j), __viaddmax_s32(pm, T_(MI, j), VNEG));   // :170-171
       }
       {
         int d0 = __shfl_up_sync(0xffffffffu, dcv, 1);
@@ -84,27 +112,19 @@ __global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
       xB = (short) max(xJ + xw_move, xN + xw_move);
       const int Dmax = __reduce_max_sync(0xffffffffu, Dml);
       if (Dmax + p.s.ddbound_w > xB) {                                // lazy F, :198-232
-        // lane-local map from the carry offered to cell 0 to the carry offered to the next lane:
-        // out = max(A, c + T)
-        int A = VNOCARRY, T = 0;
+        // D_k = max(D_k, D_{k-1} + tDD_{k-1}) to its fixed point = a max-plus prefix over k.  (1) lane-local prefix;
+        // (2) the carry a lane offers its successor, A, moved into a frame where the (row-invariant) sums of tDD
+        // cancel: B = A - S_{l+1}; an inclusive prefix-max over lanes (shfl_up hands a lane its own value when the
+        // source is out of range, so no guard); (3) c_l = PM_{l-1} + S_l enters cell j as c_l + PT[j].
 #pragma unroll
-        for (int j = 0; j < C; j++) {
-          const int t = (int) tDD[j * 32];
-          A = max(dp[j], A) + t;
-          T += t;
-        }
+        for (int j = 1; j < C; j++) dp[j] = __viaddmax_s32(dp[j - 1], (int) tDD[(j - 1) * 32], dp[j]);
+        int B = dp[C - 1] + (int) tDD[(C - 1) * 32] - S_next;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          int A2 = __shfl_up_sync(0xffffffffu, A, d), T2 = __shfl_up_sync(0xffffffffu, T, d);
-          if (lane >= d) { A = max(A, A2 + T); T = max(T + T2, VNOCARRY); }
-        }
-        int carry = __shfl_up_sync(0xffffffffu, A, 1);
+        for (int d = 1; d < 32; d <<= 1) B = max(B, __shfl_up_sync(0xffffffffu, B, d));
+        int carry = __shfl_up_sync(0xffffffffu, B, 1) + S_lane;
         if (lane == 0) carry = VNOCARRY;
 #pragma unroll
-        for (int j = 0; j < C; j++) {
-          dp[j] = max(dp[j], carry);
-          carry = dp[j] + (int) tDD[j * 32];
-        }
+        for (int j = 0; j < C; j++) dp[j] = __viaddmax_s32(carry, s_pt[j * 32], dp[j]);
       }
     }
     if (lane == 0) {
@@ -119,14 +139,16 @@ __global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
       p.c.status[out] = status;
     }
   }
+#undef T_
 }
 
 template <int C>
 static int launch_vit_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitParams &p)
 {
   const size_t smem = (size_t) (8 + NTABROWS) * C * 32 * sizeof(int16_t);
-  const bool use_smem = smem + 1024 <= (size_t) ctx->smem_optin;
-  auto kern = use_smem ? vit_kernel<C, true> : vit_kernel<C, false>;
+  const bool use_smem = smem + (size_t) C * 32 * 4 + 1024 <= (size_t) ctx->smem_optin;
+  constexpr bool TREG = (C <= 16);
+  auto kern = use_smem ? vit_kernel<C, true, TREG> : vit_kernel<C, false, false>;
   const size_t dyn = use_smem ? smem : 0;
   if (use_smem) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
   int occ = 0;
