@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stages", action="store_true", help="also time Viterbi/Forward/Backward on survivor-sized subsets")
+    ap.add_argument("--no-stages", action="store_true", help="skip the full-pipeline (config 3) and per-stage lines")
     return ap.parse_args()
 
 
@@ -170,6 +170,45 @@ class CpuMsv:
             self.p.stage_batch("msv", hdb)
         dt = time.perf_counter() - t0
         return dt, float(self.M) * float(hdb.nres)
+
+
+def write_fasta(hdb, path):
+    """Packed database -> FASTA (60 columns), vectorised."""
+    from biobench2_b200 import seqdb
+    sym = np.frombuffer(seqdb.AMINO_SYMS.encode(), np.uint8)
+    with open(path, "wb") as fh:
+        for s in range(hdb.nseq):
+            o, L = int(hdb.offsets[s]), int(hdb.lengths[s])
+            fh.write(b">seq%d\n" % s)
+            txt = sym[hdb.residues[o:o + L]].tobytes()
+            fh.write(b"\n".join(txt[i:i + 60] for i in range(0, L, 60)) + b"\n")
+
+
+def hmmsearch_cli_baseline(cpu, mean, nseq=200_000):
+    """The reference's own binary end to end (FASTA parse + whole pipeline), north_star's `hmmsearch --cpu N`:
+    oracle/_ref/hmmsearch on a FASTA file of a sample, with --cpu 1 and --cpu <all cores>.  Reports its own Mc/s line."""
+    import re, subprocess, tempfile
+    from oracle import ref
+    if cpu.kind != "reference" or not os.path.exists(ref.HMMSEARCH):
+        return None
+    tmp = tempfile.mkdtemp(prefix="p7bench_")
+    hmm = os.path.join(tmp, "q.hmm"); fa = os.path.join(tmp, "db.fa")
+    cpu.p.write_hmm(hmm)
+    hdb = cpu_sample(nseq, mean, seed=99)
+    write_fasta(hdb, fa)
+    out = {"sample": "%d iid targets, %d residues, FASTA file; whole pipeline incl. parsing" % (nseq, hdb.nres)}
+    for label, n in (("cpu1", 1), ("cpu%d" % cpu.cores, cpu.cores)):
+        t0 = time.perf_counter()
+        r = subprocess.run([ref.HMMSEARCH, "--cpu", str(n), "--tblout", os.path.join(tmp, "t.tbl"), hmm, fa],
+                           capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        m = re.search(r"# Mc/sec:\s+([0-9.]+)", r.stdout)
+        out[label] = {"elapsed_s": dt, "gcups": cpu.M * hdb.nres / dt / 1e9, "rc": r.returncode,
+                      "own_mc_per_sec_line": float(m.group(1)) if m else None}
+    for f in os.listdir(tmp):
+        os.remove(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    return out
 
 
 def cpu_sample(nseq, mean, seed=4242):
@@ -351,6 +390,52 @@ def main():
                     "lds_achieved_gbs": ssv_gcups * 2.0, "fp32_nofma_peak_gflops": fp32_peak,
                     "peak_source": "measured live (p7gpu_measure_peaks: dependent-free VIADDMNMX.S16x2 chains)"}
 
+    # ---- the whole filter pipeline on the same resident database (BASELINE.json configs[2]) and per-stage kernel rates ----
+    pipeline = None
+    if not args.no_stages and world == 1:
+        KINDS = (("ssv", engine.KERNEL_SSV), ("msvj", engine.KERNEL_MSVJ), ("bias", engine.KERNEL_BIAS), ("vit", engine.KERNEL_VIT),
+                 ("fwd", engine.KERNEL_FWD), ("bwd", engine.KERNEL_BWD))
+        STAGE_OF = {"ssv": "msv", "msvj": None, "bias": "bias", "vit": "vit", "fwd": "fwd", "bwd": "bwd"}
+
+        def timed_pipeline(dbx, **kw):
+            engine.pipeline_run(ctx, prof, dbx, **kw)                       # warm (allocator pool, per-L tables)
+            ctx.set_timing(True); ctx.reset_timing()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            r = engine.pipeline_run(ctx, prof, dbx, **kw)
+            torch.cuda.synchronize(); wall = time.perf_counter() - t0
+            km = {k: ctx.kernel_time(kind)[0] for k, kind in KINDS}
+            ctx.set_timing(False)
+            rates = {}
+            for k, _ in KINDS:
+                st_name = STAGE_OF[k]
+                if st_name and km[k] > 0 and r.stage_residues[st_name] > 0:
+                    rates[st_name + "_gcups"] = M * r.stage_residues[st_name] / (km[k] * 1e-3) / 1e9 if st_name != "bias" else None
+                    if st_name == "bias":
+                        rates["bias_gres_per_s"] = r.stage_residues["bias"] / (km[k] * 1e-3) / 1e9
+            return r, wall, km, {k: v for k, v in rates.items() if v is not None}
+
+        r, wall, km, rates = timed_pipeline(db, want_specials=True)
+        pipeline = {"workload": "full pipeline MSV->bias->Viterbi->Forward->Backward, default thresholds (F1=0.02,F2=1e-3,F3=1e-5), "
+                                "same profile and resident database (BASELINE.json configs[2])",
+                    "ms": wall * 1e3, "gcups_whole_db": cells / wall / 1e9, "counters": [int(x) for x in r.counters],
+                    "survivors": len(r.survivors), "kernel_ms": km, "stage_residues": r.stage_residues, "stage_kernel_rates": rates}
+        # Forward/Backward see almost nothing of a random database at default thresholds: rate them with --max on a slice
+        nsub = min(args.nseq, 100_000)
+        sub_lengths = lengths[:nsub]
+        sub_bytes = int(offsets[nsub - 1] + sub_lengths[-1] + 1) if nsub else 1
+        sub_res = torch.empty(sub_bytes + 32, dtype=torch.uint8, device=dev); sub_res[:sub_bytes] = res[:sub_bytes]; sub_res[sub_bytes:] = 255
+        sub_db = engine.SeqDB.adopt_torch(ctx, sub_res, d_off[:nsub].contiguous(), d_len[:nsub].contiguous(), int(sub_lengths.max()))
+        r2, wall2, km2, rates2 = timed_pipeline(sub_db, do_max=True, want_specials=False)
+        pipeline["max_mode_slice"] = {"workload": "--max (all filters off: Forward+Backward on every target) on the first %d targets" % nsub,
+                                      "ms": wall2 * 1e3, "kernel_ms": km2, "stage_kernel_rates": rates2,
+                                      "counters": [int(x) for x in r2.counters]}
+        vsc = engine.vitfilter_batch  # Viterbi on every target of the slice (kernel time only)
+        ctx.set_timing(True); ctx.reset_timing()
+        vsc(ctx, prof, sub_db)
+        vms = ctx.kernel_time(engine.KERNEL_VIT)[0]; ctx.set_timing(False)
+        pipeline["max_mode_slice"]["stage_kernel_rates"]["vit_gcups_all_targets"] = M * float(sub_lengths.astype(np.int64).sum()) / (vms * 1e-3) / 1e9
+        sub_db.close()
+
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
     if args.e2e_steps > 0:
@@ -386,13 +471,17 @@ def main():
         cpu_baseline = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": cpu.cores, "kind": cpu.kind,
                         "sample": "%d passes over %d iid targets (mean L=%d, %d residues), p7_MSVFilter on %d threads, %.1f s"
                                   % (reps, n, args.mean_len, sample_db.nres, cpu.cores, dt)}
+        try:
+            cpu_baseline["hmmsearch_cli"] = hmmsearch_cli_baseline(cpu, args.mean_len)
+        except Exception as e:                                       # the CLI leg is informative only
+            cpu_baseline["hmmsearch_cli"] = {"error": repr(e)}
 
     if rank == 0:
         line = {"metric": "hmmsearch MSV-filter GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "roofline_alu": roofline_alu,
-                "cpu_baseline": cpu_baseline,
+                "cpu_baseline": cpu_baseline, "pipeline": pipeline,
                 "detail": {"cells_per_step_per_gpu": cells, "residues_per_gpu": nres, "M": M,
                            "ssv_launches": int(ssv_n), "ssv_ms_total": ssv_ms, "msvj_launches": int(msvj_n), "msvj_ms_total": msvj_ms,
                            "msv_survivors_all_ranks": nsurv,

@@ -16,12 +16,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 struct p7gpu_pipeline_result {
   p7gpu_pipeline_counters counters;
   std::vector<p7gpu_survivor> survivors;
   std::vector<float> fwd_xmx, bck_xmx;
   std::vector<p7gpu_msv_survivor> msv_pass;       // only when opts->stop_after_msv
+  uint64_t stage_nres[5] = {0, 0, 0, 0, 0};       // residues seen by the MSV, bias, Viterbi, Forward, Backward stages
 };
 
 namespace p7g {
@@ -38,6 +40,18 @@ struct Trace {
     last = now;
   }
 };
+
+// the per-survivor host arithmetic (P-values in the reference's float/double expressions) is embarrassingly parallel:
+// the reference evaluates it inside its worker threads (hmmsearch.c:1372-1424), so do we
+template <class F> static void parallel_for(size_t n, F f)
+{
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>(hw ? hw : 1, 16);
+  if (n < 16384 || nt < 2) { f(0, n); return; }
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < nt; t++) th.emplace_back([=]() { f(n * t / nt, n * (t + 1) / nt); });
+  for (auto &x : th) x.join();
+}
 
 // stream-ordered device buffer
 struct DevBuf {
@@ -112,6 +126,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   const float *ev = prof->evparam;
   res->counters.nseqs = (uint64_t) db->nseq; res->counters.nres = (uint64_t) db->nres;
   res->counters.n_past_msv = npass;
+  res->stage_nres[0] = (uint64_t) db->nres;
 
   MsvPass mp;
   P7G_CHECK(fetch_msv_pass(ctx, db, d_usc, d_st, d_pass, npass, &mp));
@@ -125,31 +140,31 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   std::vector<float> filtersc(npass);
   if (do_bias && npass) {
     DevBuf d_f; P7G_CHECK(d_f.alloc(4 * (size_t) npass, st));
+    for (unsigned j = 0; j < npass; j++) res->stage_nres[1] += (uint64_t) mp.len[j];
     P7G_CHECK(launch_bias(ctx, 0, prof, dbv, mp.d_idx64.as<int64_t>(), npass, d_f.as<float>()));
     P7G_CUDA(cudaMemcpyAsync(filtersc.data(), d_f.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaStreamSynchronize(st));
   }
-  std::vector<Cand> cand; cand.reserve(npass);
-  for (unsigned j = 0; j < npass; j++) {
-    Cand c; memset(&c, 0, sizeof(c));
-    c.idx = mp.idx[j]; c.L = mp.len[j]; c.msv_st = mp.st[j]; c.usc = mp.usc[j]; c.nullsc = host_nullsc(c.L);
-    c.vit_st = -1; c.vfsc = NAN; c.fwdsc = NAN; c.bcksc = NAN;
-    if (do_bias) {
-      c.filtersc = filtersc[j];
+  std::vector<Cand> all(npass); std::vector<uint8_t> keep(npass);
+  parallel_for(npass, [&](size_t lo, size_t hi) {
+    for (size_t j = lo; j < hi; j++) {
+      Cand &c = all[j]; memset(&c, 0, sizeof(c));
+      c.idx = mp.idx[j]; c.L = mp.len[j]; c.msv_st = mp.st[j]; c.usc = mp.usc[j]; c.nullsc = prof->h_len[c.L].nullsc;
+      c.vit_st = -1; c.vfsc = NAN; c.fwdsc = NAN; c.bcksc = NAN;
+      c.filtersc = do_bias ? filtersc[j] : c.nullsc;
       c.P = host_filter_pvalue_gumbel(c.usc, c.filtersc, ev[0], ev[1]);
-      if (c.P > F1) continue;
-    } else {
-      c.filtersc = c.nullsc;
-      c.P = host_filter_pvalue_gumbel(c.usc, c.nullsc, ev[0], ev[1]);
+      keep[j] = !(do_bias && c.P > F1);
     }
-    cand.push_back(c);
-  }
+  });
+  std::vector<Cand> cand; cand.reserve(npass);
+  for (unsigned j = 0; j < npass; j++) if (keep[j]) cand.push_back(all[j]);
+  all.clear(); all.shrink_to_fit();
   res->counters.n_past_bias = cand.size();
 
   // ---- C. Viterbi filter for the candidates whose P still exceeds F2 (:716-723) ----
   {
     std::vector<int64_t> vidx; std::vector<size_t> where;
-    for (size_t j = 0; j < cand.size(); j++) if (cand[j].P > F2) { vidx.push_back(cand[j].idx); where.push_back(j); }
+    for (size_t j = 0; j < cand.size(); j++) if (cand[j].P > F2) { vidx.push_back(cand[j].idx); where.push_back(j); res->stage_nres[2] += (uint64_t) cand[j].L; }
     if (!vidx.empty()) {
       DevBuf d_idx, d_sc, d_stt;
       P7G_CHECK(upload_idx(ctx, vidx, &d_idx));
@@ -159,11 +174,13 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       P7G_CUDA(cudaMemcpyAsync(vsc.data(), d_sc.p, 4 * vidx.size(), cudaMemcpyDeviceToHost, st));
       P7G_CUDA(cudaMemcpyAsync(vst.data(), d_stt.p, 4 * vidx.size(), cudaMemcpyDeviceToHost, st));
       P7G_CUDA(cudaStreamSynchronize(st));
-      for (size_t k = 0; k < vidx.size(); k++) {
-        Cand &c = cand[where[k]];
-        c.vfsc = vsc[k]; c.vit_st = vst[k];
-        c.P = host_filter_pvalue_gumbel(c.vfsc, c.filtersc, ev[2], ev[3]);
-      }
+      parallel_for(vidx.size(), [&](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; k++) {
+          Cand &c = cand[where[k]];
+          c.vfsc = vsc[k]; c.vit_st = vst[k];
+          c.P = host_filter_pvalue_gumbel(c.vfsc, c.filtersc, ev[2], ev[3]);
+        }
+      });
       size_t w = 0;
       for (size_t j = 0; j < cand.size(); j++) { if (cand[j].vit_st >= 0 && cand[j].P > F2) continue; cand[w++] = cand[j]; }
       cand.resize(w);
@@ -179,7 +196,8 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     size_t hi = lo, ext = 0;
     std::vector<int64_t> idx, xoff;
     while (hi < cand.size() && (hi == lo || ext + (size_t) (cand[hi].L + 1) * 6 <= slice_floats)) {
-      idx.push_back(cand[hi].idx); xoff.push_back((int64_t) ext); ext += (size_t) (cand[hi].L + 1) * 6; hi++;
+      idx.push_back(cand[hi].idx); xoff.push_back((int64_t) ext); ext += (size_t) (cand[hi].L + 1) * 6;
+      res->stage_nres[3] += (uint64_t) cand[hi].L; hi++;
     }
     const size_t n = hi - lo;
     DevBuf d_idx, d_xoff, d_sc, d_stt, d_tot, d_fx;
@@ -198,7 +216,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       c.fwdsc = fsc[k]; c.ftot = ftot[k];
       c.P = host_filter_pvalue_exp(c.fwdsc, c.filtersc, ev[4], ev[5]);
       if (c.P > F3) continue;
-      bidx.push_back(c.idx); boff.push_back(xoff[k]); bwhere.push_back(lo + k);
+      bidx.push_back(c.idx); boff.push_back(xoff[k]); bwhere.push_back(lo + k); res->stage_nres[4] += (uint64_t) c.L;
     }
     res->counters.n_past_fwd += bidx.size();
     if (!bidx.empty()) {
@@ -531,6 +549,7 @@ int64_t p7gpu_result_nsurvivors(const p7gpu_pipeline_result *res) { return res ?
 const p7gpu_survivor *p7gpu_result_survivors(const p7gpu_pipeline_result *res) { return res ? res->survivors.data() : nullptr; }
 const float *p7gpu_result_fwd_xmx(const p7gpu_pipeline_result *res) { return res ? res->fwd_xmx.data() : nullptr; }
 const float *p7gpu_result_bck_xmx(const p7gpu_pipeline_result *res) { return res ? res->bck_xmx.data() : nullptr; }
+const uint64_t *p7gpu_result_stage_residues(const p7gpu_pipeline_result *res) { return res ? res->stage_nres : nullptr; }
 int64_t p7gpu_result_nmsvpass(const p7gpu_pipeline_result *res) { return res ? (int64_t) res->msv_pass.size() : 0; }
 const p7gpu_msv_survivor *p7gpu_result_msvpass(const p7gpu_pipeline_result *res) { return res ? res->msv_pass.data() : nullptr; }
 void p7gpu_result_destroy(p7gpu_pipeline_result *res) { delete res; }

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libp7gpu.so")
 
 OK, EMEM, EINVAL, ESYS, ERANGE, ENORESULT = 0, 5, 11, 12, 16, 19
-KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD = range(5)
+KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD, KERNEL_BIAS = range(6)
 
 EXPORTS = [
     "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
@@ -24,7 +24,7 @@ EXPORTS = [
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
     "p7gpu_backward_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
     "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser",
-    "p7gpu_pipeline_run", "p7gpu_pipeline_run_host", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
+    "p7gpu_pipeline_run", "p7gpu_pipeline_run_host", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
 ]
@@ -100,6 +100,8 @@ def lib():
         L.p7gpu_biasfilter_batch.argtypes = [vp, vp, vp, vp, i64, vp]
         L.p7gpu_msvfilter_stream.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.c_double, vp, vp, vp, C.POINTER(i64), C.POINTER(vp)]
         L.p7gpu_pipeline_run_host.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.POINTER(PipelineOpts), C.POINTER(vp)]
+        L.p7gpu_result_stage_residues.restype = C.POINTER(C.c_uint64)
+        L.p7gpu_result_stage_residues.argtypes = [vp]
         L.p7gpu_result_nmsvpass.restype = i64
         L.p7gpu_result_nmsvpass.argtypes = [vp]
         L.p7gpu_result_msvpass.restype = C.POINTER(MsvSurvivor)
@@ -329,6 +331,8 @@ class PipelineResult:
         L = lib()
         c = L.p7gpu_result_counters(h).contents
         self.counters = np.array([c.nseqs, c.nres, c.n_past_msv, c.n_past_bias, c.n_past_vit, c.n_past_fwd], np.uint64)
+        sr = L.p7gpu_result_stage_residues(h)
+        self.stage_residues = {k: int(sr[i]) for i, k in enumerate(("msv", "bias", "vit", "fwd", "bwd"))}
         n = L.p7gpu_result_nsurvivors(h)
         sv = L.p7gpu_result_survivors(h)
         names = [f[0] for f in Survivor._fields_]

@@ -230,6 +230,9 @@ int  p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_s
 int  p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
                              const int64_t *offsets, const int32_t *lengths, int64_t nseq,
                              const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+/* residues seen by each stage {MSV, bias, Viterbi, Forward, Backward}: the denominators of per-stage cells/s
+ * (the reference reports one Mc/s figure for the whole pipeline, p7_pipeline.c:1789-1793) */
+const uint64_t                *p7gpu_result_stage_residues(const p7gpu_pipeline_result *res);
 int64_t                        p7gpu_result_nmsvpass  (const p7gpu_pipeline_result *res);
 const p7gpu_msv_survivor      *p7gpu_result_msvpass   (const p7gpu_pipeline_result *res);
 const p7gpu_pipeline_counters *p7gpu_result_counters (const p7gpu_pipeline_result *res);

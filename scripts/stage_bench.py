@@ -22,7 +22,7 @@ def main():
         ms, n = ctx.kernel_time(engine.KERNEL_VIT); out["vit_gcups"] = cells / ms / 1e6; out["vit_ms"] = ms
         ctx.reset_timing()
         engine.biasfilter_batch(ctx, prof, db)
-        ms, n = ctx.kernel_time(5); out["bias_ms"] = ms; out["bias_gres_s"] = hdb.nres / ms / 1e6
+        ms, n = ctx.kernel_time(engine.KERNEL_BIAS); out["bias_ms"] = ms; out["bias_gres_s"] = hdb.nres / ms / 1e6
         ctx.reset_timing()
         t0 = time.perf_counter()
         r = engine.pipeline_run(ctx, prof, db, do_max=True, want_specials=False)
