@@ -1,0 +1,119 @@
+"""BASELINE.json's full size (config 2: M=400 vs 10^7 targets, 3.5 G residues) through size-independent properties.
+
+The CPU oracle needs minutes for this database, so parity here is: (1) bit-exact agreement with the oracle on a random
+sample of targets scored inside the full run; (2) idempotence (two passes give bit-identical arrays); (3) the streamed
+host path, the resident path and a permuted copy of the database agree (checksums of score bits and survivor sets);
+(4) the survivor fraction matches the design of the P-value threshold; (5) counters add up.  Needs a B200 with >= 20 GB free.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bits, golden_set, ROOT
+from biobench2_b200 import engine, seqdb
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+NSEQ = int(os.environ.get("P7_FULLSIZE_NSEQ", "10000000"))
+
+
+@pytest.fixture(scope="module")
+def full():
+    import sys
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    g = golden_set("synth_M400")
+    ctx = engine.Context(0)
+    prof = engine.Profile(ctx, g.oprofile)
+    dev = torch.device("cuda", 0)
+    res, d_off, d_len, lengths, offsets, nbytes = bench.synth_db_device(torch, dev, NSEQ, 350, 42)
+    torch.cuda.synchronize()
+    db = engine.SeqDB.adopt_torch(ctx, res, d_off, d_len, int(lengths.max()))
+    d_sc = torch.empty(NSEQ, dtype=torch.float32, device=dev); d_st = torch.empty(NSEQ, dtype=torch.int32, device=dev)
+    d_pass = torch.empty(NSEQ, dtype=torch.int32, device=dev); d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    engine.msvfilter_device(ctx, prof, db, d_sc.data_ptr(), d_st.data_ptr(), 0.02, d_pass.data_ptr(), d_cnt.data_ptr())
+    ctx.synchronize()
+    yield dict(g=g, ctx=ctx, prof=prof, db=db, torch=torch, res=res, d_off=d_off, d_len=d_len, lengths=lengths, offsets=offsets,
+               nbytes=nbytes, sc=d_sc, st=d_st, d_pass=d_pass, d_cnt=d_cnt)
+    db.close(); prof.close(); ctx.close()
+
+
+def _host_subset(f, idx):
+    """Pull the residues of a few targets back to the host as a PackedDB."""
+    seqs = []
+    for s in idx:
+        o, L = int(f["offsets"][s]), int(f["lengths"][s])
+        seqs.append(f["res"][o:o + L].cpu().numpy())
+    return seqdb.pack(seqs)
+
+
+def test_random_sample_of_the_full_run_is_bit_exact(full):
+    f = full
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(NSEQ, size=1500, replace=False))
+    # include the longest and the shortest targets of the database
+    idx = np.unique(np.concatenate([idx, np.argsort(f["lengths"])[:20], np.argsort(f["lengths"])[-20:]]))
+    hdb = _host_subset(f, idx)
+    o = port.OracleProfile(f["g"].oprofile.view(), f["g"].oprofile)
+    osc, ost = o.stage_batch("msv", hdb)
+    t_idx = f["torch"].from_numpy(idx).cuda()
+    sc = f["sc"][t_idx].cpu().numpy(); st = f["st"][t_idx].cpu().numpy()
+    assert np.array_equal(st, ost) and np.array_equal(bits(sc), bits(osc))
+    o.close()
+
+
+def test_idempotent_and_survivor_fraction(full):
+    f = full; torch = f["torch"]
+    sc2 = torch.empty_like(f["sc"]); st2 = torch.empty_like(f["st"]); p2 = torch.empty_like(f["d_pass"]); c2 = torch.zeros_like(f["d_cnt"])
+    engine.msvfilter_device(f["ctx"], f["prof"], f["db"], sc2.data_ptr(), st2.data_ptr(), 0.02, p2.data_ptr(), c2.data_ptr())
+    f["ctx"].synchronize()
+    assert torch.equal(sc2.view(torch.int32), f["sc"].view(torch.int32)) and torch.equal(st2, f["st"])
+    n1, n2 = int(f["d_cnt"].item()), int(c2.item())
+    assert n1 == n2
+    assert torch.equal(torch.sort(p2[:n2]).values, torch.sort(f["d_pass"][:n1]).values)
+    # F1 = 0.02: the calibrated Gumbel tail over-predicts a little on this profile (3.2% on 10^7 iid targets)
+    assert 0.01 < n1 / NSEQ < 0.05
+    assert int((f["st"] == 0).sum().item()) + int((f["st"] == 16).sum().item()) == NSEQ      # MSV returns eslOK or eslERANGE only
+
+
+def test_streamed_host_pass_and_pipeline_counters_agree_with_resident(full):
+    f = full; torch = f["torch"]
+    h_res = torch.empty(f["nbytes"], dtype=torch.uint8, pin_memory=True); h_res.copy_(f["res"][:f["nbytes"]]); torch.cuda.synchronize()
+    hdb = seqdb.PackedDB(h_res.numpy(), f["offsets"], f["lengths"])
+    r = engine.pipeline_run_host(f["ctx"], f["prof"], hdb, stop_after_msv=True)
+    n1 = int(f["d_cnt"].item())
+    assert list(r.counters[:3]) == [NSEQ, int(f["lengths"].astype(np.int64).sum()), n1]
+    want = torch.sort(f["d_pass"][:n1]).values.cpu().numpy()
+    assert np.array_equal(r.msv_pass["seqidx"], want)
+    assert np.array_equal(bits(r.msv_pass["usc"]), bits(f["sc"][torch.from_numpy(want).cuda().long()].cpu().numpy()))
+    # the full pipeline over the same database: stage counters are monotone and consistent with the MSV stage
+    rf = engine.pipeline_run(f["ctx"], f["prof"], f["db"], want_specials=False)
+    c = [int(x) for x in rf.counters]
+    assert c[0] == NSEQ and c[2] == n1 and c[2] >= c[3] >= c[4] >= c[5]
+    assert rf.stage_residues["msv"] == c[1] and rf.stage_residues["bias"] >= rf.stage_residues["vit"] >= rf.stage_residues["fwd"]
+
+
+def test_permutation_invariance_checksum(full):
+    """Scores are a function of (profile, target) only: a block-reversed copy of the database gives the same multiset."""
+    f = full; torch = f["torch"]
+    n = min(NSEQ, 2_000_000)
+    lengths = f["lengths"][:n][::-1].copy()
+    offs = np.concatenate([[0], np.cumsum(lengths.astype(np.int64) + 1)[:-1]]) + 1
+    nbytes = int(lengths.astype(np.int64).sum()) + n + 1
+    res = torch.full((nbytes + 32,), 255, dtype=torch.uint8, device="cuda")
+    # copy target s of the original to position n-1-s (vectorised gather through an index map built on the device)
+    src_off = torch.from_numpy(f["offsets"][:n][::-1].copy()).cuda(); dst_off = torch.from_numpy(offs).cuda(); L = torch.from_numpy(lengths).cuda().long()
+    rep = torch.repeat_interleave(torch.arange(n, device="cuda"), L)
+    within = torch.arange(int(L.sum().item()), device="cuda") - torch.repeat_interleave(torch.cumsum(L, 0) - L, L)
+    res[dst_off[rep] + within] = f["res"][src_off[rep] + within]
+    d_off = dst_off.contiguous(); d_len = torch.from_numpy(lengths).cuda()
+    db2 = engine.SeqDB.adopt_torch(f["ctx"], res, d_off, d_len, int(lengths.max()))
+    sc = torch.empty(n, dtype=torch.float32, device="cuda"); st = torch.empty(n, dtype=torch.int32, device="cuda")
+    engine.msvfilter_device(f["ctx"], f["prof"], db2, sc.data_ptr(), st.data_ptr())
+    f["ctx"].synchronize()
+    assert torch.equal(torch.flip(sc, [0]).view(torch.int32), f["sc"][:n].view(torch.int32))
+    assert torch.equal(torch.flip(st, [0]), f["st"][:n])
+    db2.close()
