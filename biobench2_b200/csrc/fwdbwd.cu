@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(DP_THREADS) fwd_kernel(const FbParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int C, bool SMEM>
+template <int C, bool SMEM, bool TREG>
 __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
 {
   extern __shared__ __align__(16) float s_fb[];
@@ -167,6 +167,12 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
   const float *tBM = tf + 0 * C * 32 + lane, *tMM = tf + 1 * C * 32 + lane, *tIM = tf + 2 * C * 32 + lane,
               *tDM = tf + 3 * C * 32 + lane, *tMD = tf + 4 * C * 32 + lane, *tMI = tf + 5 * C * 32 + lane,
               *tII = tf + 6 * C * 32 + lane, *tDD = tf + 7 * C * 32 + lane;
+  float rBM[TREG ? C : 1], rMD[TREG ? C : 1], rMI[TREG ? C : 1], rII[TREG ? C : 1], rDD[TREG ? C : 1];
+  if (TREG) {
+#pragma unroll
+    for (int j = 0; j < C; j++) { rBM[j] = tBM[j * 32]; rMD[j] = tMD[j * 32]; rMI[j] = tMI[j * 32]; rII[j] = tII[j * 32]; rDD[j] = tDD[j * 32]; }
+  }
+#define T_(name, j) (TREG ? r##name[j] : t##name[(j) * 32])
   long long s, out;
   while (next_target(p.c, lane, &s, &out)) {
     const int L = p.c.len[s];
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
       // suffix scan: lane map from carry (D of the next lane's first cell) to this lane's first D: out = A + B*carry
       float A = 0.f, B = 1.f;
 #pragma unroll
-      for (int j = C - 1; j >= 0; j--) { const float t = tDD[j * 32]; A = xE + t * A; B = t * B; }
+      for (int j = C - 1; j >= 0; j--) { const float t = T_(DD, j); A = xE + t * A; B = t * B; }
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         float A2 = __shfl_down_sync(0xffffffffu, A, d), B2 = __shfl_down_sync(0xffffffffu, B, d);
@@ -204,8 +210,8 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
       if (lane == 31) carry = 0.f;
 #pragma unroll
       for (int j = C - 1; j >= 0; j--) {
-        mp[j] = xE + carry * tMD[j * 32];
-        dp[j] = xE + carry * tDD[j * 32];
+        mp[j] = xE + carry * T_(MD, j);
+        dp[j] = xE + carry * T_(DD, j);
         ip[j] = 0.f;
         carry = dp[j];
       }
@@ -236,11 +242,11 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
 #pragma unroll
       for (int j = 0; j < C; j++) {
         const float mpv = (j + 1 < C) ? me[j + 1] : me_next;
-        sumB += me[j] * tBM[j * 32];
+        sumB += me[j] * T_(BM, j);
         const float ipv = ip[j];
-        ip[j] = ipv * tII[j * 32] + mpv * nIM[j];
+        ip[j] = ipv * T_(II, j) + mpv * nIM[j];
         dp[j] = mpv * nDM[j];
-        mp[j] = ipv * tMI[j * 32] + mpv * nMM[j];
+        mp[j] = ipv * T_(MI, j) + mpv * nMM[j];
       }
       xB = warp_sum(sumB);
       xC = xC * ploop;
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
       {
         float A = 0.f, B = 1.f;
 #pragma unroll
-        for (int j = C - 1; j >= 0; j--) { const float t = tDD[j * 32]; A = dp[j] + (t * A + xE); B = t * B; }
+        for (int j = C - 1; j >= 0; j--) { const float t = T_(DD, j); A = dp[j] + (t * A + xE); B = t * B; }
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           float A2 = __shfl_down_sync(0xffffffffu, A, d), B2 = __shfl_down_sync(0xffffffffu, B, d);
@@ -261,8 +267,8 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
         if (lane == 31) carry = 0.f;
 #pragma unroll
         for (int j = C - 1; j >= 0; j--) {
-          mp[j] = (mp[j] + xE) + carry * tMD[j * 32];
-          dp[j] = dp[j] + (carry * tDD[j * 32] + xE);
+          mp[j] = (mp[j] + xE) + carry * T_(MD, j);
+          dp[j] = dp[j] + (carry * T_(DD, j) + xE);
           carry = dp[j];
         }
       }
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
         const int x = __ldg(seq);
         const float *rfx = rf + (size_t) x * C * 32 + lane;
 #pragma unroll
-        for (int j = 0; j < C; j++) sumB += (mp[j] * rfx[j * 32]) * tBM[j * 32];
+        for (int j = 0; j < C; j++) sumB += (mp[j] * rfx[j * 32]) * T_(BM, j);
       }
       xB = warp_sum(sumB);
       xN = (xB * pmove) + (xN * ploop);
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
       if (p.totscale) p.totscale[out] = totscale;
     }
   }
+#undef T_
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -311,7 +318,7 @@ static int launch_fb_c(p7gpu_ctx *ctx, cudaStream_t stream, const FbParams &p)
   const size_t smem = (size_t) (8 + NTABROWS) * C * 32 * sizeof(float);
   const bool use_smem = smem + 1024 <= (size_t) ctx->smem_optin;
   void (*kern)(const FbParams);
-  if (BWD) kern = use_smem ? bwd_kernel<C, true> : bwd_kernel<C, false>;
+  if (BWD) kern = use_smem ? bwd_kernel<C, true, false> : bwd_kernel<C, false, false>;   // TREG costs Backward more in occupancy (190 regs) than it saves in LDS: measured 703 -> 602 GCUPS
   else     kern = use_smem ? fwd_kernel<C, true, (C <= 16)> : fwd_kernel<C, false, false>;
   const size_t dyn = use_smem ? smem : 0;
   if (use_smem) P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));

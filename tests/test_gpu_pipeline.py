@@ -167,3 +167,41 @@ def test_partition_independence_of_sharded_search(ctx):
     c1, r1 = search.sharded_pipeline(ctx, prof, g.db)                       # world size 1: no process group needed
     assert list(c1) == list(whole.counters) and np.array_equal(r1["seqidx"], rec["seqidx"])
     prof.close()
+
+
+def test_many_profiles_one_resident_database(ctx):
+    """hmmscan-style batch (BASELINE config 5): the database is uploaded once, each profile is a pipeline call on it
+    (the outer loop of hmmsearch.c:471 with the per-query FASTA rewind of :480-487 gone); counters match the oracle's chain."""
+    hdb = seqdb.synth_db(4000, mean=250, seed=31, degenerate_frac=0.003)
+    db = engine.SeqDB.upload(ctx, hdb)
+    for name in ("synth_M33", "synth_M100", "fn3", "globins4", "Pkinase", "synth_M400", "synth_M800"):
+        g = golden_set(name)
+        prof = engine.Profile(ctx, g.oprofile)
+        r = engine.pipeline_run(ctx, prof, db, want_specials=False)
+        o = port.OracleProfile(g.oprofile.view(), g.oprofile)
+        t, pi, eo, _ = g.oprofile.bg_filter
+        oc = o.pipeline(hdb, (t, pi, eo))
+        assert list(r.counters) == list(oc["counters"]), name
+        assert [s["seqidx"] for s in r.survivors] == list(np.nonzero(oc["stage"] == 4)[0]), name
+        o.close(); prof.close()
+    db.close()
+
+
+def test_unsupported_model_length_is_rejected(ctx):
+    """M beyond the slot geometry (64*65-1 = 4159 nodes) must fail loudly, not silently mis-score."""
+    import ctypes
+    from biobench2_b200.oprofile import OProfileView
+    g = golden_set("synth_M33")
+    v = g.oprofile.view()
+    big = OProfileView()
+    ctypes.memmove(ctypes.byref(big), ctypes.byref(v), ctypes.sizeof(OProfileView))
+    big.M = 5000
+
+    class Fake:
+        bg_filter = None
+
+        def view(self):
+            return big
+    with pytest.raises(engine.P7GpuError) as e:
+        engine.Profile(ctx, Fake())
+    assert e.value.code == engine.EINVAL
