@@ -12,12 +12,16 @@ namespace p7g {
 constexpr int DP_THREADS = 128;
 
 struct DpCommon {
-  const uint8_t *res; const int64_t *off; const int32_t *len; const int32_t *order; const int64_t *idx;
-  long long first;
-  long long n;
-  const LenConst *lc;
-  float *sc; int32_t *status;
-  unsigned long long *work_counter;
+  const uint8_t *res = nullptr; const int64_t *off = nullptr; const int32_t *len = nullptr;
+  const int32_t *order = nullptr; const int64_t *idx = nullptr;
+  long long first = 0;
+  long long n = 0;
+  const LenConst *lc = nullptr;
+  float *sc = nullptr; int32_t *status = nullptr;
+  unsigned long long *work_counter = nullptr;
+  // optional device-side work list of (target, output slot) pairs whose length is read on the device
+  // (the packed Viterbi kernel's "redo" list); when set it replaces idx/order/first and n
+  const long long *pairs = nullptr; const unsigned int *pair_count = nullptr;
 };
 
 // fetch the next work item for this warp; returns false when the queue is empty
@@ -26,6 +30,11 @@ __device__ __forceinline__ bool next_target(const DpCommon &p, int lane, long lo
   unsigned long long j = 0;
   if (lane == 0) j = atomicAdd(p.work_counter, 1ULL);
   j = __shfl_sync(0xffffffffu, j, 0);
+  if (p.pairs) {
+    if (j >= (unsigned long long) *p.pair_count) return false;
+    *s = p.pairs[2 * j]; *out = p.pairs[2 * j + 1];
+    return true;
+  }
   if (j >= (unsigned long long) p.n) return false;
   *s   = p.idx ? p.idx[j] : (p.order ? (long long) p.order[j] : p.first + (long long) j);
   *out = p.idx ? (long long) j : *s;

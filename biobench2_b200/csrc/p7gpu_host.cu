@@ -159,6 +159,73 @@ int dp_cells_per_lane(int M)
 
 static int nq_of(int M, int w) { int q = (M - 1) / w + 1; return q < 2 ? 2 : q; }   // impl_sse.h:25-27
 
+// Packed (2 x int16 per register) Viterbi tables and clamp window (vit.cu: vitp_kernel; proof in DESIGN.md 4.3).
+// Node k = 1 + h*32*C2 + lane*C2 + j for half h, register j.  Every transition / emission is clamped at -T; values live
+// in a per-target window [Fl, Fl+T] whose floor is Fl = base_w + xw_move(L) + floff; targets that leave the window are
+// redone by the exact 32-bit kernel.
+static int build_vit_packed(p7gpu_profile *prof, const p7gpu_oprofile_view *om, int Q8)
+{
+  const int M = prof->M, Kp = prof->Kp;
+  const int C2 = vit_packed_c2(M);
+  VitPacked &vp = prof->vitp;
+  vp.enabled = 0; vp.C2 = C2;
+  if (C2 < 1) return P7GPU_OK;
+  auto rw_at = [&](int x, int k) { return (int) om->rwv[((size_t) x * Q8 + (k - 1) % Q8) * 8 + (k - 1) / Q8]; };
+  auto tw_at = [&](int t, int k) {
+    const int q8 = (k - 1) % Q8, z8 = (k - 1) / Q8;
+    return (int) (t < 7 ? om->twv[((size_t) 7 * q8 + t) * 8 + z8] : om->twv[((size_t) 7 * Q8 + q8) * 8 + z8]);
+  };
+  int tbm_min = 32767, rw_max = 0, min_rwstar = 32767;
+  for (int k = 1; k <= M; k++) tbm_min = std::min(tbm_min, tw_at(0, k));
+  for (int x = 0; x < Kp; x++) {
+    int star = -32768;
+    for (int k = 1; k <= M; k++) { star = std::max(star, rw_at(x, k)); rw_max = std::max(rw_max, rw_at(x, k)); }
+    if (star > -32768) min_rwstar = std::min(min_rwstar, star);
+  }
+  for (int t = 0; t < 8; t++) for (int k = 1; k <= M; k++) if (tw_at(t, k) > 0) return P7GPU_OK;   // not log-probabilities: keep the exact kernel only
+  const int T = (65535 - rw_max) / 2;
+  int floff = std::min(0, tbm_min);
+  if (min_rwstar < 32767) floff = std::min(floff, tbm_min + min_rwstar - 1);
+  floff = std::min(floff, -(int) om->ddbound_w);
+  vp.T = T; vp.W0 = -32768 + T; vp.W1 = vp.W0 + T; vp.floff = floff;
+  if (tbm_min <= -32768 || -floff > T - 64 || C2 > 46) return P7GPU_OK;      // window cannot be placed / tables too large
+  auto cl = [&](int v) { return (uint32_t) (uint16_t) (int16_t) std::max(v, -T); };
+  const int H = 32 * C2;
+  std::vector<uint32_t> rwp((size_t) NTABROWS * C2 * 32), twp((size_t) 8 * C2 * 32), scanw((size_t) 6 * 32);
+  std::vector<int> tdd((size_t) 2 * H, -T);                                  // clamped tDD by node index k-1, pads = -T
+  for (int k = 1; k <= M; k++) tdd[k - 1] = std::max(tw_at(7, k), -T);
+  for (int lane = 0; lane < 32; lane++)
+    for (int j = 0; j < C2; j++) {
+      const int klo = 1 + lane * C2 + j, khi = klo + H;
+      for (int x = 0; x < NTABROWS; x++) {
+        const int lo = (x < Kp && klo <= M) ? rw_at(x, klo) : -32768, hi = (x < Kp && khi <= M) ? rw_at(x, khi) : -32768;
+        rwp[((size_t) x * C2 + j) * 32 + lane] = cl(lo) | (cl(hi) << 16);
+      }
+      for (int t = 0; t < 8; t++) {
+        const int lo = klo <= M ? tw_at(t, klo) : -32768, hi = khi <= M ? tw_at(t, khi) : -32768;
+        twp[((size_t) t * C2 + j) * 32 + lane] = cl(lo) | (cl(hi) << 16);
+      }
+    }
+  // lane totals TL(h,l) = sum of the lane's C2 tDD; W_d(l) = sum of TL over lanes l-d+1..l (or -T when l < d);
+  // WH(l) = sum of the high half's TL over lanes 0..l.  All clamped at -T (a clamped sum always reaches the floor).
+  auto TL = [&](int h, int l) { long long a = 0; for (int j = 0; j < C2; j++) a += tdd[(size_t) h * H + l * C2 + j]; return a; };
+  for (int l = 0; l < 32; l++) {
+    for (int di = 0; di < 5; di++) {
+      const int d = 1 << di;
+      long long lo = -T, hi = -T;
+      if (l >= d) { lo = 0; hi = 0; for (int m = l - d + 1; m <= l; m++) { lo += TL(0, m); hi += TL(1, m); } }
+      scanw[(size_t) di * 32 + l] = cl((int) std::max<long long>(lo, -T)) | (cl((int) std::max<long long>(hi, -T)) << 16);
+    }
+    long long wh = 0; for (int m = 0; m <= l; m++) wh += TL(1, m);
+    scanw[(size_t) 5 * 32 + l] = 0u | (cl((int) std::max<long long>(wh, -T)) << 16);
+  }
+  P7G_CUDA(cudaMalloc(&prof->d_rwp, rwp.size() * 4));     P7G_CUDA(cudaMemcpy(prof->d_rwp, rwp.data(), rwp.size() * 4, cudaMemcpyHostToDevice));
+  P7G_CUDA(cudaMalloc(&prof->d_twp, twp.size() * 4));     P7G_CUDA(cudaMemcpy(prof->d_twp, twp.data(), twp.size() * 4, cudaMemcpyHostToDevice));
+  P7G_CUDA(cudaMalloc(&prof->d_scanw, scanw.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_scanw, scanw.data(), scanw.size() * 4, cudaMemcpyHostToDevice));
+  vp.enabled = 1;
+  return P7GPU_OK;
+}
+
 }  // namespace p7g
 
 using namespace p7g;
@@ -241,6 +308,23 @@ int p7gpu_ctx_set_stream(p7gpu_ctx *ctx, void *cuda_stream)
 }
 
 int64_t p7gpu_ctx_launch_count(const p7gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value)
+{
+  if (!ctx || !name) return P7GPU_EINVAL;
+  if (!strcmp(name, "vit_exact_only")) { ctx->vit_exact_only = value; return P7GPU_OK; }
+  set_error("set_option: unknown option '%s'", name);
+  return P7GPU_EINVAL;
+}
+
+int64_t p7gpu_ctx_last_vit_redo(p7gpu_ctx *ctx)
+{
+  if (!ctx) return -1;
+  unsigned int v = 0;
+  if (cudaStreamSynchronize(ctx->lanes[0].stream) != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, ctx->lanes[0].counters + CTR_VIT_REDO, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t) v;
+}
 
 int p7gpu_ctx_synchronize(p7gpu_ctx *ctx)
 {
@@ -328,6 +412,7 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
     P7G_CUDA(cudaMalloc(&prof->d_tf, tf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
     prof->vit.xw_E_move = om->xw[0][0]; prof->vit.xw_E_loop = om->xw[0][1];
     prof->vit.base_w = om->base_w; prof->vit.ddbound_w = om->ddbound_w; prof->vit.scale_w = om->scale_w;
+    P7G_CHECK(build_vit_packed(prof, om, Q8));
     prof->scale_w = om->scale_w;
     prof->fwd.xf_E_move = om->xf[0][0]; prof->fwd.xf_E_loop = om->xf[0][1];
   }
@@ -342,6 +427,7 @@ void p7gpu_profile_destroy(p7gpu_profile *prof)
   cudaStreamSynchronize(prof->ctx->stream);
   cudaFree(prof->d_ssv_tab); cudaFree(prof->d_msv_tab);
   cudaFree(prof->d_rw); cudaFree(prof->d_tw); cudaFree(prof->d_rf); cudaFree(prof->d_tf);
+  cudaFree(prof->d_rwp); cudaFree(prof->d_twp); cudaFree(prof->d_scanw);
   cudaFree(prof->d_len);
   delete prof;
 }

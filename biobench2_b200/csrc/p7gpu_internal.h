@@ -38,7 +38,8 @@ struct DiagGeom {
   size_t tableBytes() const { return (size_t) NTABROWS * rowWords * 4; }
 };
 DiagGeom diag_geom(int M);
-int dp_cells_per_lane(int M);       // smallest supported C with 32*C >= M (dp_common.cuh)
+int dp_cells_per_lane(int M);
+int vit_packed_c2(int M);           // registers per lane of the packed Viterbi kernel (vit.cu), -1 = unsupported       // smallest supported C with 32*C >= M (dp_common.cuh)
 
 // ---- per-target-length constants: what p7_oprofile_ReconfigLength()/p7_bg_SetLength() derive ----
 // (impl_sse/p7_oprofile.c:1085-1127, p7_bg.c:190-199,358-363), built on the host with the host libm,
@@ -58,6 +59,8 @@ struct LenConst {
 // scalar parameters handed to kernels by value
 struct MsvScalars { int tbm_b, tec_b, base_b, bias_b; float scale_b; };
 struct VitScalars { int xw_E_move, xw_E_loop, base_w, ddbound_w; float scale_w; };
+// packed (2 x int16) Viterbi fast path: clamp window and table geometry (vit.cu)
+struct VitPacked  { int enabled, C2, T, W0, W1, floff; };
 struct FwdScalars { float xf_E_move, xf_E_loop; };
 struct BiasHmm    { float t[2][3]; float pi[3]; float eo[P7GPU_KP][2]; };   // bg->fhmm after p7_bg_SetFilter
 
@@ -68,7 +71,7 @@ struct Lane { cudaStream_t stream = nullptr; unsigned int *counters = nullptr; }
 
 // counter slots inside a lane (unsigned int words; 64-bit work counters take two)
 enum { CTR_SSV_WORK = 0, CTR_NORES_COUNT = 2, CTR_MSVJ_WORK = 4, CTR_VIT_WORK = 6, CTR_FWD_WORK = 8, CTR_BWD_WORK = 10,
-       CTR_PASS_COUNT = 12, CTR_BIAS_WORK = 14 };
+       CTR_PASS_COUNT = 12, CTR_BIAS_WORK = 14, CTR_VIT_REDO = 16, CTR_VIT_WORK2 = 18 };
 
 // what a kernel needs to know about the target set
 struct DbView {
@@ -98,6 +101,7 @@ struct p7gpu_ctx {
   p7g::Lane    lanes[p7g::NLANES];
   cudaStream_t copy_stream = nullptr;   // H2D staging for the streamed database path
   int64_t      launches = 0;
+  int          vit_exact_only = 0;      // option "vit_exact_only": skip the packed Viterbi fast path (tests)
   // growable scratch buffers (device + pinned host)
   void  *d_scratch = nullptr;  size_t d_scratch_bytes = 0;
   void  *h_pinned  = nullptr;  size_t h_pinned_bytes  = 0;
@@ -120,6 +124,10 @@ struct p7gpu_profile {
   int       dpC = 0;                   // cells per lane of the row-synchronous kernels (dp_common.cuh)
   int16_t  *d_rw = nullptr;            // [NTABROWS][dpC][32]  lane-transposed: node k = lane*dpC + j + 1
   int16_t  *d_tw = nullptr;            // [8][dpC][32]
+  p7g::VitPacked vitp = {0, 0, 0, 0, 0, 0};
+  uint32_t *d_rwp = nullptr;           // [NTABROWS][C2][32] (lo = node lane*C2+j+1, hi = that + 32*C2), clamped at -T
+  uint32_t *d_twp = nullptr;           // [8][C2][32]
+  uint32_t *d_scanw = nullptr;         // [6][32] lane-span sums of tDD for the packed D->D scan
   float    *d_rf = nullptr;            // [NTABROWS][dpC][32]
   float    *d_tf = nullptr;            // [8][dpC][32]
   // bias-filter HMM (p7_bg_SetFilter), optional

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
 {
   extern __shared__ __align__(16) int16_t s_vit[];
   __shared__ int s_ptab[C * 32];
+  if (p.c.pairs && *p.c.pair_count == 0u) return;                     // redo pass with nothing to redo
   const int16_t *tw = p.tw, *rw = p.rw;
   if (SMEM) {
     const int ntw = 8 * C * 32, nrw = NTABROWS * C * 32;
@@ -142,6 +143,193 @@ __global__ void __launch_bounds__(DP_THREADS) vit_kernel(const VitParams p)
 #undef T_
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Packed fast path: two model nodes per 32-bit register (DPX VIADDMNMX.S16x2 / VIMNMX3.S16x2).
+//
+// Lane l, register j, half h holds node k = 1 + h*32*C2 + l*C2 + j.  The reference's saturating int16 arithmetic
+// needs 17 bits of intermediate range, so values are kept in a per-target window instead: w = v - SH with
+// w in [W0, W1], W0 = -32768 + T, W1 = W0 + T, every transition / emission clamped at -T, so that no packed add can
+// wrap and a clamped ("minus infinity") add always lands on the floor W0.  The floor corresponds to the reference
+// value Fl = base_w + xw_move(L) + floff, chosen (p7gpu_host.cu: build_vit_packed) below everything that can influence
+// a later cell, xE, or the lazy-F test; stored cells then equal max(reference cell, Fl) and xE, xC, xJ, xB and the lazy-F
+// decisions are those of the reference (DESIGN.md 4.3 gives the induction).  A target whose row maximum leaves
+// (W0, W1] — a very high score, possible overflow, or a row of impossible residues — is appended to the redo list and
+// recomputed by the exact 32-bit kernel above.
+struct VitpParams {
+  DpCommon c;
+  const uint32_t *rwp, *twp, *scanw;
+  VitScalars s;
+  VitPacked w;
+  long long *redo_list; unsigned int *redo_count;
+};
+
+__device__ __forceinline__ uint32_t pack2(int v) { return (uint32_t) (v & 0xffff) * 0x00010001u; }
+// lane l receives lane l-1's register; lane 0 receives (floor, low half of lane 31) = nodes 0 and 32*C2
+__device__ __forceinline__ uint32_t rot_prev(uint32_t v, int lane, uint32_t FLv)
+{
+  const uint32_t r = __shfl_sync(0xffffffffu, v, (lane + 31) & 31);
+  return lane == 0 ? __byte_perm(r, FLv, 0x1054) : r;
+}
+__device__ __forceinline__ int warp_max16x2(uint32_t v)
+{
+  const uint32_t m = __vmaxs2(v, __byte_perm(v, 0u, 0x1032));          // both halves = max(lo, hi)
+  return __reduce_max_sync(0xffffffffu, (int) m) >> 16;
+}
+
+template <int C2, bool TREG>
+__global__ void __launch_bounds__(DP_THREADS) vitp_kernel(const VitpParams p)
+{
+  extern __shared__ __align__(16) uint32_t s_vp[];
+  {
+    const int nrw = NTABROWS * C2 * 32;
+    for (int i = threadIdx.x; i < nrw; i += blockDim.x) s_vp[i] = __ldg(p.rwp + i);
+    if (!TREG) { const int ntw = 8 * C2 * 32; for (int i = threadIdx.x; i < ntw; i += blockDim.x) s_vp[nrw + i] = __ldg(p.twp + i); }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const uint32_t *s_rw = s_vp + lane;
+  const uint32_t *s_tw = s_vp + NTABROWS * C2 * 32 + lane;
+  uint32_t rBM[TREG ? C2 : 1], rMM[TREG ? C2 : 1], rIM[TREG ? C2 : 1], rDM[TREG ? C2 : 1], rMD[TREG ? C2 : 1],
+           rMI[TREG ? C2 : 1], rII[TREG ? C2 : 1], rDD[TREG ? C2 : 1];
+  if (TREG) {
+#pragma unroll
+    for (int j = 0; j < C2; j++) {
+      rBM[j] = __ldg(p.twp + (0 * C2 + j) * 32 + lane); rMM[j] = __ldg(p.twp + (1 * C2 + j) * 32 + lane);
+      rIM[j] = __ldg(p.twp + (2 * C2 + j) * 32 + lane); rDM[j] = __ldg(p.twp + (3 * C2 + j) * 32 + lane);
+      rMD[j] = __ldg(p.twp + (4 * C2 + j) * 32 + lane); rMI[j] = __ldg(p.twp + (5 * C2 + j) * 32 + lane);
+      rII[j] = __ldg(p.twp + (6 * C2 + j) * 32 + lane); rDD[j] = __ldg(p.twp + (7 * C2 + j) * 32 + lane);
+    }
+  }
+#define TP_(name, t, j) (TREG ? r##name[j] : s_tw[((t) * C2 + (j)) * 32])
+  uint32_t wd[5];
+#pragma unroll
+  for (int d = 0; d < 5; d++) wd[d] = __ldg(p.scanw + d * 32 + lane);
+  const uint32_t wh = __ldg(p.scanw + 5 * 32 + lane);
+  const int W0 = p.w.W0;
+  const uint32_t FLv = pack2(W0);
+
+  long long s, out;
+  while (next_target(p.c, lane, &s, &out)) {
+    const int L = p.c.len[s];
+    const long long o = p.c.off[s];
+    const int xw_move = p.c.lc[L].xw_move;
+    const int Fl = p.s.base_w + xw_move + p.w.floff;
+    const int SH = Fl - W0;                                            // reference value = window value + SH
+    const int W1t = min(p.w.W1, 32766 - SH);                           // stay below the reference's overflow test as well
+    bool redo = Fl < -32768;
+    uint32_t mp[C2], ip[C2], dp[C2];
+#pragma unroll
+    for (int j = 0; j < C2; j++) mp[j] = ip[j] = dp[j] = FLv;
+    int xN = p.s.base_w, xB = (short) (xN + xw_move), xJ = VNEG, xC = VNEG;
+
+    // residues, four per aligned 32-bit load, one word prefetched ahead
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(p.c.res + (o & ~3LL));
+    int sh = (int) (o & 3) * 8;
+    uint32_t cur = __ldg(wp), nxt = __ldg(wp + 1);
+    wp += 2;
+    if (!redo)
+    for (int i = 0; i < L; i++) {
+      const uint32_t x = (cur >> sh) & 0xffu;
+      sh += 8;
+      if (sh == 32) { sh = 0; cur = nxt; nxt = __ldg(wp++); }
+      const uint32_t *rwx = s_rw + x * (C2 * 32);
+      const uint32_t xBv = pack2(xB - SH);
+      uint32_t pm = rot_prev(mp[C2 - 1], lane, FLv);
+      uint32_t pi = rot_prev(ip[C2 - 1], lane, FLv);
+      uint32_t pd = rot_prev(dp[C2 - 1], lane, FLv);
+      uint32_t xEl = FLv, Dml = FLv, dcv = FLv, pendE = 0u, pendD = 0u;
+      bool have = false;
+#pragma unroll
+      for (int j = 0; j < C2; j++) {
+        uint32_t sv = __viaddmax_s16x2(xBv, TP_(BM, 0, j), FLv);       // vitfilter.c:146-150
+        sv = __viaddmax_s16x2(pm, TP_(MM, 1, j), sv);
+        sv = __viaddmax_s16x2(pi, TP_(IM, 2, j), sv);
+        sv = __viaddmax_s16x2(pd, TP_(DM, 3, j), sv);
+        sv = __viaddmax_s16x2(sv, rwx[j * 32], FLv);
+        pm = mp[j]; pi = ip[j]; pd = dp[j];                            // :155-157
+        mp[j] = sv;
+        dp[j] = dcv;                                                   // D(i,k) = M(i,k-1)+tMD so far (:160-161)
+        dcv = __viaddmax_s16x2(sv, TP_(MD, 4, j), FLv);                // :166
+        ip[j] = __viaddmax_s16x2(pi, TP_(II, 6, j), __viaddmax_s16x2(pm, TP_(MI, 5, j), FLv));   // :170-171
+        if (have) { xEl = __vimax3_s16x2(xEl, pendE, sv); Dml = __vimax3_s16x2(Dml, pendD, dcv); have = false; }
+        else      { pendE = sv; pendD = dcv; have = true; }
+      }
+      if (have) { xEl = __vmaxs2(xEl, pendE); Dml = __vmaxs2(Dml, pendD); }
+      dp[0] = rot_prev(dcv, lane, FLv);
+      const int xEw = warp_max16x2(xEl);
+      if (xEw > W1t || xEw <= W0) { redo = true; break; }
+      const int xE = xEw + SH;
+      xC = (short) max(xC, xE + p.s.xw_E_move);                        // :178-181
+      xJ = (short) max(xJ, xE + p.s.xw_E_loop);
+      xB = (short) max(xJ + xw_move, xN + xw_move);
+      const int Dmax = warp_max16x2(Dml) + SH;
+      if (Dmax + p.s.ddbound_w > xB) {                                 // lazy F, :198-232
+        // max-plus prefix over k: (1) inside the lane; (2) X = value leaving the lane, Kogge-Stone over lanes with the
+        // row-invariant lane-span sums wd[] (both halves at once); (3) the low half's total enters the high half (wh);
+        // (4) the carry entering each lane runs down the lane again.
+#pragma unroll
+        for (int j = 1; j < C2; j++) dp[j] = __viaddmax_s16x2(dp[j - 1], TP_(DD, 7, j - 1), dp[j]);
+        uint32_t X = __viaddmax_s16x2(dp[C2 - 1], TP_(DD, 7, C2 - 1), FLv);
+#pragma unroll
+        for (int d = 0; d < 5; d++) X = __viaddmax_s16x2(__shfl_up_sync(0xffffffffu, X, 1 << d), wd[d], X);
+        const uint32_t u = __byte_perm(__shfl_sync(0xffffffffu, X, 31), FLv, 0x1054);   // (floor, X_lo(31))
+        X = __viaddmax_s16x2(u, wh, X);
+        uint32_t carry = __shfl_up_sync(0xffffffffu, X, 1);
+        if (lane == 0) carry = u;
+        dp[0] = __vmaxs2(dp[0], carry);
+#pragma unroll
+        for (int j = 1; j < C2; j++) dp[j] = __viaddmax_s16x2(dp[j - 1], TP_(DD, 7, j - 1), dp[j]);
+      }
+    }
+    if (lane == 0) {
+      if (redo) {
+        const unsigned int t = atomicAdd(p.redo_count, 1u);
+        p.redo_list[2 * (long long) t] = s; p.redo_list[2 * (long long) t + 1] = out;
+      } else {
+        float sc;
+        if (xC > -32768) {                                             // :240-247
+          sc = (float) xC + (float) xw_move - (float) p.s.base_w;
+          sc = __fdiv_rn(sc, p.s.scale_w);
+          sc = __fsub_rn(sc, 3.0f);
+        } else sc = -CUDART_INF_F;
+        p.c.sc[out] = sc;
+        p.c.status[out] = P7GPU_OK;
+      }
+    }
+  }
+#undef TP_
+}
+
+template <int C2>
+static int launch_vitp_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitpParams &p, bool *launched)
+{
+  constexpr bool TREG = (C2 <= 14);
+  const size_t smem = (size_t) (NTABROWS + (TREG ? 0 : 8)) * C2 * 32 * sizeof(uint32_t);
+  *launched = false;
+  if (smem + 1024 > (size_t) ctx->smem_optin) return P7GPU_OK;
+  auto kern = vitp_kernel<C2, TREG>;
+  static int occ_dev[64];
+  int &occ = occ_dev[ctx->device & 63];
+  if (occ <= 0) {
+    P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DP_THREADS, smem));
+    if (occ < 1) { set_error("vitp_kernel<%d>: zero occupancy", C2); return P7GPU_ESYS; }
+  }
+  long long blocks = (long long) ctx->sm_count * occ;
+  long long need = (p.c.n + (DP_THREADS / 32) - 1) / (DP_THREADS / 32);
+  if (need < blocks) blocks = need;
+  if (blocks < 1) blocks = 1;
+  { LaunchTimer t(ctx, P7GPU_KERNEL_VIT, stream); kern<<<(unsigned) blocks, DP_THREADS, smem, stream>>>(p); }
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  *launched = true;
+  return P7GPU_OK;
+}
+
+#define P7G_VITP_C2_CASES(X) \
+  X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(16) X(18) X(20) X(24) X(28) X(32) X(40) X(46)
+
 template <int C>
 static int launch_vit_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitParams &p)
 {
@@ -164,6 +352,14 @@ static int launch_vit_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitParams &p)
   return P7GPU_OK;
 }
 
+static int vitp_tables_c2(int C2)
+{
+  static const int cs[] = {1,2,3,4,5,6,7,8,9,10,11,12,13,14,16,18,20,24,28,32,40,46};
+  for (int c : cs) if (c >= C2) return c;
+  return -1;
+}
+int vit_packed_c2(int M) { return vitp_tables_c2((M + 63) / 64); }
+
 int launch_vit(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                float *d_sc, int32_t *d_status)
 {
@@ -175,13 +371,40 @@ int launch_vit(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   p.c.n = n; p.c.lc = prof->d_len; p.c.sc = d_sc; p.c.status = d_status;
   p.c.work_counter = (unsigned long long *) (ln.counters + CTR_VIT_WORK);
   p.rw = prof->d_rw; p.tw = prof->d_tw; p.s = prof->vit;
+  // CTR_VIT_WORK (2 words) .. CTR_VIT_REDO (2) .. CTR_VIT_WORK2 (2) are not contiguous with each other: clear both ranges
   P7G_CUDA(cudaMemsetAsync(ln.counters + CTR_VIT_WORK, 0, 2 * sizeof(unsigned int), ln.stream));
+
+  long long *d_redo = nullptr;
+  if (prof->vitp.enabled && !ctx->vit_exact_only) {
+    // fast path over every work item; what it cannot decide comes back as (target, slot) pairs for the exact kernel
+    P7G_CUDA(cudaMemsetAsync(ln.counters + CTR_VIT_REDO, 0, 4 * sizeof(unsigned int), ln.stream));
+    P7G_CUDA(cudaMallocAsync((void **) &d_redo, (size_t) n * 2 * sizeof(long long), ln.stream));
+    VitpParams q;
+    q.c = p.c; q.rwp = prof->d_rwp; q.twp = prof->d_twp; q.scanw = prof->d_scanw; q.s = prof->vit; q.w = prof->vitp;
+    q.redo_list = d_redo; q.redo_count = ln.counters + CTR_VIT_REDO;
+    bool launched = false;
+    int rc = P7GPU_OK;
+    switch (prof->vitp.C2) {
+#define X(CV) case CV: rc = launch_vitp_c<CV>(ctx, ln.stream, q, &launched); break;
+      P7G_VITP_C2_CASES(X)
+#undef X
+    default: break;
+    }
+    if (rc != P7GPU_OK) { cudaFreeAsync(d_redo, ln.stream); return rc; }
+    if (launched) {
+      p.c.pairs = d_redo; p.c.pair_count = ln.counters + CTR_VIT_REDO;
+      p.c.work_counter = (unsigned long long *) (ln.counters + CTR_VIT_WORK2);
+    }
+  }
+  int rc;
   switch (prof->dpC) {
-#define X(CV) case CV: return launch_vit_c<CV>(ctx, ln.stream, p);
+#define X(CV) case CV: rc = launch_vit_c<CV>(ctx, ln.stream, p); break;
     P7G_DP_C_CASES(X)
 #undef X
-  default: set_error("vit: unsupported cells-per-lane %d", prof->dpC); return P7GPU_EINVAL;
+  default: set_error("vit: unsupported cells-per-lane %d", prof->dpC); rc = P7GPU_EINVAL;
   }
+  if (d_redo) cudaFreeAsync(d_redo, ln.stream);
+  return rc;
 }
 
 }  // namespace p7g

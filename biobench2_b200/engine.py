@@ -17,7 +17,7 @@ KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD, KERNEL_BIAS = range
 
 EXPORTS = [
     "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
-    "p7gpu_ctx_launch_count", "p7gpu_ctx_synchronize",
+    "p7gpu_ctx_launch_count", "p7gpu_ctx_synchronize", "p7gpu_ctx_set_option", "p7gpu_ctx_last_vit_redo",
     "p7gpu_ctx_set_timing", "p7gpu_ctx_reset_timing", "p7gpu_ctx_kernel_time", "p7gpu_measure_peaks",
     "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M", "p7gpu_profile_set_biasfilter",
     "p7gpu_seqdb_upload", "p7gpu_seqdb_adopt_device", "p7gpu_seqdb_destroy", "p7gpu_seqdb_nseq", "p7gpu_seqdb_nres",
@@ -77,6 +77,9 @@ def lib():
         L.p7gpu_ctx_launch_count.restype = i64
         L.p7gpu_ctx_launch_count.argtypes = [vp]
         L.p7gpu_ctx_synchronize.argtypes = [vp]
+        L.p7gpu_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+        L.p7gpu_ctx_last_vit_redo.restype = i64
+        L.p7gpu_ctx_last_vit_redo.argtypes = [vp]
         L.p7gpu_ctx_set_timing.argtypes = [vp, C.c_int]
         L.p7gpu_ctx_reset_timing.argtypes = [vp]
         L.p7gpu_ctx_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
@@ -166,6 +169,14 @@ class Context:
     @property
     def launches(self):
         return lib().p7gpu_ctx_launch_count(self.h)
+
+    def set_option(self, name, value):
+        _check(lib().p7gpu_ctx_set_option(self.h, name.encode(), int(value)))
+
+    @property
+    def last_vit_redo(self):
+        """targets of the last Viterbi launch that left the packed kernel's window and were redone exactly"""
+        return lib().p7gpu_ctx_last_vit_redo(self.h)
 
     def set_timing(self, on=True):
         _check(lib().p7gpu_ctx_set_timing(self.h, int(on)))

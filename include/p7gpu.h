@@ -83,6 +83,12 @@ int         p7gpu_ctx_set_stream(p7gpu_ctx *ctx, void *cuda_stream);
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches claim) */
 int64_t     p7gpu_ctx_launch_count(const p7gpu_ctx *ctx);
 int         p7gpu_ctx_synchronize(p7gpu_ctx *ctx);
+/* engine options (no reference counterpart).  "vit_exact_only"=1: p7gpu_vitfilter_* skips the packed 2 x int16 fast
+ * path and runs the exact 32-bit kernel on every target (the two must agree bit for bit; tests use this). */
+int         p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value);
+/* how many targets of the last Viterbi launch on the ctx's main stream left the packed kernel's window and were
+ * recomputed by the exact kernel (diagnostic) */
+int64_t     p7gpu_ctx_last_vit_redo(p7gpu_ctx *ctx);
 
 /* Diagnostics for bench.py's roofline line (no reference counterpart; cf. the Mc/s drivers msvfilter.c:512-600).
  * With timing on, every kernel launch is bracketed by CUDA events on the launching stream;

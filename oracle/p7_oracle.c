@@ -190,6 +190,7 @@ int p7o_msvfilter(const P7O_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc
 }
 
 /* ---- ViterbiFilter: vitfilter.c:83-249 ----------------------------------------------------- */
+long long p7o_dbg_vit_rows = 0, p7o_dbg_vit_ddrows = 0;   /* diagnostics: how often lazy-F evaluates D->D */
 static int16_t adds16(int a, int b) { int s = a + b; return (int16_t) (s > 32767 ? 32767 : (s < -32768 ? -32768 : s)); }
 
 static int vit_engine(const P7O_PROFILE *p, const uint8_t *dsq, int L, int always_dd, float *ret_sc)
@@ -231,7 +232,9 @@ static int vit_engine(const P7O_PROFILE *p, const uint8_t *dsq, int L, int alway
     xC = (int16_t) IMAX(xC + 0, xE + p->xw_E_move);
     xJ = (int16_t) IMAX(xJ + 0, xE + p->xw_E_loop);
     xB = (int16_t) IMAX(xJ + xw_move, xN + xw_move);
+    p7o_dbg_vit_rows++;
     if (always_dd || Dmax + p->ddbound_w > xB) {                      /* lazy F, :198-232 */
+      p7o_dbg_vit_ddrows++;
       for (k = 2; k <= M; k++) nd[k] = IMAX(nd[k], adds16(nd[k-1], tDD[k-2]));
     }
     { int16_t *t; t = mmx; mmx = nm; nm = t; t = imx; imx = ni; ni = t; t = dmx; dmx = nd; nd = t; }

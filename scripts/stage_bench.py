@@ -20,6 +20,11 @@ def main():
         ctx.reset_timing()
         engine.vitfilter_batch(ctx, prof, db)
         ms, n = ctx.kernel_time(engine.KERNEL_VIT); out["vit_gcups"] = cells / ms / 1e6; out["vit_ms"] = ms
+        out["vit_redo"] = int(ctx.last_vit_redo)
+        ctx.set_option("vit_exact_only", 1); ctx.reset_timing()
+        engine.vitfilter_batch(ctx, prof, db)
+        ms, n = ctx.kernel_time(engine.KERNEL_VIT); out["vit_exact32_gcups"] = cells / ms / 1e6
+        ctx.set_option("vit_exact_only", 0)
         ctx.reset_timing()
         engine.biasfilter_batch(ctx, prof, db)
         ms, n = ctx.kernel_time(engine.KERNEL_BIAS); out["bias_ms"] = ms; out["bias_gres_s"] = hdb.nres / ms / 1e6
