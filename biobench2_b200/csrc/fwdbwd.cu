@@ -7,6 +7,7 @@
 // recurrence) is evaluated exactly-in-structure by an affine prefix scan over the warp.  Compiled with
 // -fmad=false -ftz=true: the reference's SSE2 build has no FMA and runs with FTZ/DAZ (impl_sse.h:356-376).
 #include "dp_common.cuh"
+#include "fwdbwd_mw.cuh"
 #include <math_constants.h>
 
 namespace p7g {
@@ -355,6 +356,11 @@ int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   FbParams p;
   P7G_CHECK(fill_common(ln, prof, db, d_idx, n, d_sc, d_status, CTR_FWD_WORK, &p));
   p.xmx = d_xmx; p.fwd_xmx = nullptr; p.xmx_off = d_xmx_off; p.totscale = d_totscale;
+  if (prof->mwW > 0 && !ctx->fb_one_warp) {                           // long model: one CTA per target
+    FbMwParams q; q.c = p.c; q.rf = prof->d_rf_mw; q.tf = prof->d_tf_mw; q.G = 32 * prof->mwW; q.s = p.s;
+    q.xmx = p.xmx; q.fwd_xmx = nullptr; q.xmx_off = p.xmx_off; q.totscale = p.totscale;
+    return launch_fwd_mw(ctx, ln.stream, prof, q);
+  }
   switch (prof->dpC) {
 #define X(CV) case CV: return launch_fb_c<CV, false>(ctx, ln.stream, p);
     P7G_DP_C_CASES(X)
@@ -372,6 +378,11 @@ int launch_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   FbParams p;
   P7G_CHECK(fill_common(ln, prof, db, d_idx, n, d_sc, d_status, CTR_BWD_WORK, &p));
   p.xmx = d_bck_xmx; p.fwd_xmx = d_fwd_xmx; p.xmx_off = d_xmx_off; p.totscale = d_totscale;
+  if (prof->mwW > 0 && !ctx->fb_one_warp) {
+    FbMwParams q; q.c = p.c; q.rf = prof->d_rf_mw; q.tf = prof->d_tf_mw; q.G = 32 * prof->mwW; q.s = p.s;
+    q.xmx = p.xmx; q.fwd_xmx = p.fwd_xmx; q.xmx_off = p.xmx_off; q.totscale = p.totscale;
+    return launch_bwd_mw(ctx, ln.stream, prof, q);
+  }
   switch (prof->dpC) {
 #define X(CV) case CV: return launch_fb_c<CV, true>(ctx, ln.stream, p);
     P7G_DP_C_CASES(X)

@@ -157,6 +157,27 @@ int dp_cells_per_lane(int M)
   return -1;
 }
 
+// CTA-per-target geometry of the long-model Forward/Backward kernels (fwdbwd_mw.cuh): W warps x 32 lanes x C cells >= M.
+// Instances exist for (W <= 4, 9 <= C <= 16), (W <= 8, 7 <= C <= 14), (W <= 12, 6 <= C <= 11).  Environment (tuning only):
+// P7GPU_MW_MINM = smallest M that uses these kernels (default 513), P7GPU_MW_CMAX = upper bound on C.
+bool mw_geometry(int M, int *C, int *W, int *Wmax)
+{
+  static const int wmax[3] = {4, 8, 12}, cmax[3] = {16, 14, 11}, cmin[3] = {9, 7, 6};
+  const char *e1 = getenv("P7GPU_MW_MINM"), *e2 = getenv("P7GPU_MW_CMAX");
+  const int minM = e1 ? atoi(e1) : 513, cap = e2 ? atoi(e2) : 0;
+  if (M < minM) return false;
+  for (int t = 0; t < 3; t++) {
+    int cm = cmax[t]; if (cap > 0 && cap < cm) cm = cap;
+    if (cm < cmin[t]) continue;
+    int w = (M + 32 * cm - 1) / (32 * cm); if (w < 2) w = 2;
+    if (w > wmax[t]) continue;
+    int c = (M + 32 * w - 1) / (32 * w); if (c < cmin[t]) c = cmin[t];
+    *C = c; *W = w; *Wmax = wmax[t];
+    return true;
+  }
+  return false;
+}
+
 static int nq_of(int M, int w) { int q = (M - 1) / w + 1; return q < 2 ? 2 : q; }   // impl_sse.h:25-27
 
 // Packed (2 x int16 per register) Viterbi tables and clamp window (vit.cu: vitp_kernel; proof in DESIGN.md 4.3).
@@ -313,6 +334,7 @@ int p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value)
 {
   if (!ctx || !name) return P7GPU_EINVAL;
   if (!strcmp(name, "vit_exact_only")) { ctx->vit_exact_only = value; return P7GPU_OK; }
+  if (!strcmp(name, "fb_one_warp"))    { ctx->fb_one_warp = value; return P7GPU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return P7GPU_EINVAL;
 }
@@ -410,6 +432,20 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
     P7G_CUDA(cudaMalloc(&prof->d_tw, tw.size() * 2)); P7G_CUDA(cudaMemcpy(prof->d_tw, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
     P7G_CUDA(cudaMalloc(&prof->d_rf, rf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rf, rf.data(), rf.size() * 4, cudaMemcpyHostToDevice));
     P7G_CUDA(cudaMalloc(&prof->d_tf, tf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
+    int mc = 0, mw = 0, mwmax = 0;
+    if (mw_geometry(M, &mc, &mw, &mwmax)) {                                   // long models: [row][j][g], node k = g*mc + j + 1
+      const int G = 32 * mw;
+      std::vector<float> rfm((size_t) NTABROWS * mc * G, 0.0f), tfm((size_t) 8 * mc * G, 0.0f);
+      for (int k = 1; k <= M; k++) {
+        const int gl = (k - 1) / mc, j = (k - 1) % mc, q4 = (k - 1) % Q4, z4 = (k - 1) / Q4;
+        for (int x = 0; x < Kp; x++) rfm[((size_t) x * mc + j) * G + gl] = om->rfv[((size_t) x * Q4 + q4) * 4 + z4];
+        for (int t = 0; t < 7; t++)  tfm[((size_t) t * mc + j) * G + gl] = om->tfv[((size_t) 7 * q4 + t) * 4 + z4];
+        tfm[((size_t) 7 * mc + j) * G + gl] = om->tfv[((size_t) 7 * Q4 + q4) * 4 + z4];
+      }
+      P7G_CUDA(cudaMalloc(&prof->d_rf_mw, rfm.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rf_mw, rfm.data(), rfm.size() * 4, cudaMemcpyHostToDevice));
+      P7G_CUDA(cudaMalloc(&prof->d_tf_mw, tfm.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf_mw, tfm.data(), tfm.size() * 4, cudaMemcpyHostToDevice));
+      prof->mwC = mc; prof->mwW = mw; prof->mwWmax = mwmax;
+    }
     prof->vit.xw_E_move = om->xw[0][0]; prof->vit.xw_E_loop = om->xw[0][1];
     prof->vit.base_w = om->base_w; prof->vit.ddbound_w = om->ddbound_w; prof->vit.scale_w = om->scale_w;
     P7G_CHECK(build_vit_packed(prof, om, Q8));
@@ -427,6 +463,7 @@ void p7gpu_profile_destroy(p7gpu_profile *prof)
   cudaStreamSynchronize(prof->ctx->stream);
   cudaFree(prof->d_ssv_tab); cudaFree(prof->d_msv_tab);
   cudaFree(prof->d_rw); cudaFree(prof->d_tw); cudaFree(prof->d_rf); cudaFree(prof->d_tf);
+  cudaFree(prof->d_rf_mw); cudaFree(prof->d_tf_mw);
   cudaFree(prof->d_rwp); cudaFree(prof->d_twp); cudaFree(prof->d_scanw);
   cudaFree(prof->d_len);
   delete prof;

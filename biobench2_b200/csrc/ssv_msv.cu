@@ -48,6 +48,16 @@ __device__ __forceinline__ uint32_t patch_word(uint32_t w, long long wpos, long 
   return w;
 }
 
+// 16 residues per load; the L2::128B hint makes the L2 fetch the whole 128-byte line from HBM once, so that the
+// seven later 16-byte loads of the same line (16..112 DP rows later) hit in L2 instead of re-reading DRAM sectors
+// (ncu r1f: 7.4 GB read per launch for 3.7 GB of database without the hint).
+__device__ __forceinline__ uint4 ldg_res16(const uint8_t *ptr)
+{
+  uint4 v;
+  asm("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+
 __device__ __forceinline__ int hmax16(uint32_t x)
 {
   int lo = (int) (short) (x & 0xffff), hi = (int) (short) (x >> 16);
@@ -120,11 +130,11 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
       int c = lane * Q;
       const long long end = o + L;
       long long pos = o & ~15LL;
-      uint4 cur = __ldg(reinterpret_cast<const uint4 *>(p.res + pos));
+      uint4 cur = ldg_res16(p.res + pos);
       int since_check = 0;
       for (; pos < end; pos += DIAG_CHUNK) {
         uint4 nxt = cur;
-        if (pos + DIAG_CHUNK < end) nxt = __ldg(reinterpret_cast<const uint4 *>(p.res + pos + DIAG_CHUNK));
+        if (pos + DIAG_CHUNK < end) nxt = ldg_res16(p.res + pos + DIAG_CHUNK);
         uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         if (pos < o || pos + DIAG_CHUNK > end) {
 #pragma unroll
