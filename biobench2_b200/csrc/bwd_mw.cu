@@ -3,15 +3,16 @@
 
 namespace p7g {
 
-template <int C, int WMAX>
-__global__ void __launch_bounds__(32 * WMAX) bwd_mw_kernel(const FbMwParams p)
+template <int C, int W>
+__global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
 {
   __shared__ long long s_work[2];
-  __shared__ float s_me[WMAX];          // M(i+1,k) e_k(x_{i+1}) of a warp's first node (the k+1 neighbour of the warp below)
-  __shared__ float s_scan[WMAX][2];     // D of a warp's first node as a map of what enters behind its last node
-  __shared__ float s_sum[WMAX];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
-  const int G = p.G, g = threadIdx.x;
+  __shared__ float s_me[W];          // M(i+1,k) e_k(x_{i+1}) of a warp's first node (the k+1 neighbour of the warp below)
+  __shared__ float s_scan[W][2];     // D of a warp's first node as a map of what enters behind its last node
+  __shared__ float s_sum[W];
+  constexpr int G = 32 * W;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = threadIdx.x;
   float rBM[C], rMD[C], rMI[C], rII[C], rDD[C], nMM[C], nIM[C], nDM[C];
 #pragma unroll
   for (int j = 0; j < C; j++) {
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(32 * WMAX) bwd_mw_kernel(const FbMwParams p)
 #pragma unroll
     for (int j = 0; j < C; j++) e[j] = 0.0f;
     if (L > 0) {                                          // emissions of x_L: used by row L-1 (or by the termination if L = 1)
-      const float *rfx = rfg + (size_t) __ldg(seq + L - 1) * C * G;
+      const float *rfx = rfg + (size_t) __ldg(seq + L - 1) * (C * G);
 #pragma unroll
       for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
     }
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(32 * WMAX) bwd_mw_kernel(const FbMwParams p)
         mp[j] = ipv * rMI[j] + mpv * nMM[j];
       }
       {                                                               // emissions of x_i for the next row / the termination
-        const float *rfx = rfg + (size_t) __ldg(seq + i - 1) * C * G;
+        const float *rfx = rfg + (size_t) __ldg(seq + i - 1) * (C * G);
 #pragma unroll
         for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
       }
@@ -184,18 +185,17 @@ __global__ void __launch_bounds__(32 * WMAX) bwd_mw_kernel(const FbMwParams p)
   }
 }
 
-template <int C, int WMAX>
+template <int C, int W>
 static int launch_bwd_mw_c(p7gpu_ctx *ctx, cudaStream_t stream, const FbMwParams &p)
 {
-  auto kern = bwd_mw_kernel<C, WMAX>;
-  const int threads = p.G;
+  auto kern = bwd_mw_kernel<C, W>;
   int occ = 0;
-  P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
-  if (occ < 1) { set_error("bwd_mw_kernel<%d,%d>: zero occupancy at %d threads", C, WMAX, threads); return P7GPU_ESYS; }
+  P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, 0));
+  if (occ < 1) { set_error("bwd_mw_kernel<%d,%d>: zero occupancy", C, W); return P7GPU_ESYS; }
   long long blocks = (long long) ctx->sm_count * occ;
   if (p.c.n < blocks) blocks = p.c.n;
   if (blocks < 1) blocks = 1;
-  { LaunchTimer t(ctx, P7GPU_KERNEL_BWD, stream); kern<<<(unsigned) blocks, threads, 0, stream>>>(p); }
+  { LaunchTimer t(ctx, P7GPU_KERNEL_BWD, stream); kern<<<(unsigned) blocks, 32 * W, 0, stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   return P7GPU_OK;
@@ -203,9 +203,9 @@ static int launch_bwd_mw_c(p7gpu_ctx *ctx, cudaStream_t stream, const FbMwParams
 
 int launch_bwd_mw(p7gpu_ctx *ctx, cudaStream_t stream, const p7gpu_profile *prof, const FbMwParams &p)
 {
-  const int C = prof->mwC, W = prof->mwW, key = C * 100 + prof->mwWmax;
-  switch (key) {
-#define X(CV, WM) case CV * 100 + WM: return launch_bwd_mw_c<CV, WM>(ctx, stream, p);
+  const int C = prof->mwC, W = prof->mwW;
+  switch (C * 100 + W) {
+#define X(CV, WV) case CV * 100 + WV: return launch_bwd_mw_c<CV, WV>(ctx, stream, p);
     P7G_MW_CASES(X)
 #undef X
   default: set_error("bwd_mw: no kernel for C=%d W=%d", C, W); return P7GPU_EINVAL;

@@ -357,7 +357,7 @@ int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   P7G_CHECK(fill_common(ln, prof, db, d_idx, n, d_sc, d_status, CTR_FWD_WORK, &p));
   p.xmx = d_xmx; p.fwd_xmx = nullptr; p.xmx_off = d_xmx_off; p.totscale = d_totscale;
   if (prof->mwW > 0 && !ctx->fb_one_warp) {                           // long model: one CTA per target
-    FbMwParams q; q.c = p.c; q.rf = prof->d_rf_mw; q.tf = prof->d_tf_mw; q.G = 32 * prof->mwW; q.s = p.s;
+    FbMwParams q; q.c = p.c; q.rf = prof->d_rf_mw; q.tf = prof->d_tf_mw; q.s = p.s;
     q.xmx = p.xmx; q.fwd_xmx = nullptr; q.xmx_off = p.xmx_off; q.totscale = p.totscale;
     return launch_fwd_mw(ctx, ln.stream, prof, q);
   }
@@ -379,7 +379,7 @@ int launch_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   P7G_CHECK(fill_common(ln, prof, db, d_idx, n, d_sc, d_status, CTR_BWD_WORK, &p));
   p.xmx = d_bck_xmx; p.fwd_xmx = d_fwd_xmx; p.xmx_off = d_xmx_off; p.totscale = d_totscale;
   if (prof->mwW > 0 && !ctx->fb_one_warp) {
-    FbMwParams q; q.c = p.c; q.rf = prof->d_rf_mw; q.tf = prof->d_tf_mw; q.G = 32 * prof->mwW; q.s = p.s;
+    FbMwParams q; q.c = p.c; q.rf = prof->d_rf_mw; q.tf = prof->d_tf_mw; q.s = p.s;
     q.xmx = p.xmx; q.fwd_xmx = p.fwd_xmx; q.xmx_off = p.xmx_off; q.totscale = p.totscale;
     return launch_bwd_mw(ctx, ln.stream, prof, q);
   }

@@ -19,7 +19,6 @@ struct FbMwParams {
   DpCommon c;
   const float *rf;      // [NTABROWS][C][G]
   const float *tf;      // [8][C][G]
-  int G;                // 32 * W
   FwdScalars s;
   float *xmx;           // output specials of this direction (may be null)
   const float *fwd_xmx; // backward only: forward specials (scale factors)
@@ -58,11 +57,12 @@ __device__ __forceinline__ bool mw_next_target(const DpCommon &c, long long *sh,
   return *s >= 0;
 }
 
-// (cells per lane, warp bound) instances: W <= 4 leaves 255 registers per thread for C <= 16; the wider CTAs use fewer cells
+// (cells per lane C, warps per CTA W) instances; G = 32*W is a compile-time constant so that table loads have immediate offsets
 #define P7G_MW_CASES(X) \
+  X(9, 2) X(10, 2) X(11, 2) X(12, 2) X(13, 2) X(14, 2) X(15, 2) X(16, 2) \
   X(9, 4) X(10, 4) X(11, 4) X(12, 4) X(13, 4) X(14, 4) X(15, 4) X(16, 4) \
-  X(7, 8) X(8, 8) X(9, 8) X(10, 8) X(11, 8) X(12, 8) X(13, 8) X(14, 8) \
-  X(6, 12) X(7, 12) X(8, 12) X(9, 12) X(10, 12) X(11, 12)
+  X(9, 8) X(10, 8) X(11, 8) X(12, 8) X(13, 8) X(14, 8) \
+  X(10, 12) X(11, 12)
 
 int launch_fwd_mw(p7gpu_ctx *ctx, cudaStream_t stream, const p7gpu_profile *prof, const FbMwParams &p);
 int launch_bwd_mw(p7gpu_ctx *ctx, cudaStream_t stream, const p7gpu_profile *prof, const FbMwParams &p);

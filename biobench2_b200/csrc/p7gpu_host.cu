@@ -158,21 +158,19 @@ int dp_cells_per_lane(int M)
 }
 
 // CTA-per-target geometry of the long-model Forward/Backward kernels (fwdbwd_mw.cuh): W warps x 32 lanes x C cells >= M.
-// Instances exist for (W <= 4, 9 <= C <= 16), (W <= 8, 7 <= C <= 14), (W <= 12, 6 <= C <= 11).  Environment (tuning only):
-// P7GPU_MW_MINM = smallest M that uses these kernels (default 513), P7GPU_MW_CMAX = upper bound on C.
-bool mw_geometry(int M, int *C, int *W, int *Wmax)
+// Instances exist for W = 2, 4 (9 <= C <= 16), W = 8 (9 <= C <= 14), W = 12 (10 <= C <= 11).  Environment (tuning and tests
+// only): P7GPU_MW_MINM = smallest M that uses these kernels (default 513), P7GPU_MW_CMAX = upper bound on C when choosing W.
+bool mw_geometry(int M, int *C, int *W)
 {
-  static const int wmax[3] = {4, 8, 12}, cmax[3] = {16, 14, 11}, cmin[3] = {9, 7, 6};
+  static const int ws[4] = {2, 4, 8, 12}, cmax[4] = {16, 16, 14, 11}, cmin[4] = {9, 9, 9, 10};
   const char *e1 = getenv("P7GPU_MW_MINM"), *e2 = getenv("P7GPU_MW_CMAX");
   const int minM = e1 ? atoi(e1) : 513, cap = e2 ? atoi(e2) : 0;
   if (M < minM) return false;
-  for (int t = 0; t < 3; t++) {
+  for (int t = 0; t < 4; t++) {
     int cm = cmax[t]; if (cap > 0 && cap < cm) cm = cap;
-    if (cm < cmin[t]) continue;
-    int w = (M + 32 * cm - 1) / (32 * cm); if (w < 2) w = 2;
-    if (w > wmax[t]) continue;
-    int c = (M + 32 * w - 1) / (32 * w); if (c < cmin[t]) c = cmin[t];
-    *C = c; *W = w; *Wmax = wmax[t];
+    const int c = (M + 32 * ws[t] - 1) / (32 * ws[t]);
+    if (c > cm) continue;
+    *C = c < cmin[t] ? cmin[t] : c; *W = ws[t];
     return true;
   }
   return false;
@@ -432,8 +430,8 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
     P7G_CUDA(cudaMalloc(&prof->d_tw, tw.size() * 2)); P7G_CUDA(cudaMemcpy(prof->d_tw, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
     P7G_CUDA(cudaMalloc(&prof->d_rf, rf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rf, rf.data(), rf.size() * 4, cudaMemcpyHostToDevice));
     P7G_CUDA(cudaMalloc(&prof->d_tf, tf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
-    int mc = 0, mw = 0, mwmax = 0;
-    if (mw_geometry(M, &mc, &mw, &mwmax)) {                                   // long models: [row][j][g], node k = g*mc + j + 1
+    int mc = 0, mw = 0;
+    if (mw_geometry(M, &mc, &mw)) {                                   // long models: [row][j][g], node k = g*mc + j + 1
       const int G = 32 * mw;
       std::vector<float> rfm((size_t) NTABROWS * mc * G, 0.0f), tfm((size_t) 8 * mc * G, 0.0f);
       for (int k = 1; k <= M; k++) {
@@ -444,7 +442,7 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
       }
       P7G_CUDA(cudaMalloc(&prof->d_rf_mw, rfm.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rf_mw, rfm.data(), rfm.size() * 4, cudaMemcpyHostToDevice));
       P7G_CUDA(cudaMalloc(&prof->d_tf_mw, tfm.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf_mw, tfm.data(), tfm.size() * 4, cudaMemcpyHostToDevice));
-      prof->mwC = mc; prof->mwW = mw; prof->mwWmax = mwmax;
+      prof->mwC = mc; prof->mwW = mw;
     }
     prof->vit.xw_E_move = om->xw[0][0]; prof->vit.xw_E_loop = om->xw[0][1];
     prof->vit.base_w = om->base_w; prof->vit.ddbound_w = om->ddbound_w; prof->vit.scale_w = om->scale_w;

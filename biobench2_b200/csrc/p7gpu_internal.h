@@ -39,7 +39,7 @@ struct DiagGeom {
 };
 DiagGeom diag_geom(int M);
 int dp_cells_per_lane(int M);
-bool mw_geometry(int M, int *C, int *W, int *Wmax);   // Forward/Backward CTA-per-target geometry for long models; false = use one warp
+bool mw_geometry(int M, int *C, int *W);   // Forward/Backward CTA-per-target geometry for long models; false = use one warp
 int vit_packed_c2(int M);           // registers per lane of the packed Viterbi kernel (vit.cu), -1 = unsupported       // smallest supported C with 32*C >= M (dp_common.cuh)
 
 // ---- per-target-length constants: what p7_oprofile_ReconfigLength()/p7_bg_SetLength() derive ----
@@ -133,7 +133,7 @@ struct p7gpu_profile {
   float    *d_rf = nullptr;            // [NTABROWS][dpC][32]
   float    *d_tf = nullptr;            // [8][dpC][32]
   // long models (M > 512): Forward/Backward with one CTA of mwW warps per target (fwdbwd_mw.cuh); 0 = not used
-  int       mwC = 0, mwW = 0, mwWmax = 0;   // cells per lane, warps per CTA, kernel family (4, 8 or 12 warps at most)
+  int       mwC = 0, mwW = 0;            // cells per lane, warps per CTA
   float    *d_rf_mw = nullptr;         // [NTABROWS][mwC][32*mwW]  node k = g*mwC + j + 1
   float    *d_tf_mw = nullptr;         // [8][mwC][32*mwW]
   // bias-filter HMM (p7_bg_SetFilter), optional
