@@ -1,4 +1,14 @@
 // bwd_mw.cu — p7_BackwardParser for long models, one CTA of W warps per target (see fwdbwd_mw.cuh).
+//
+// One CTA barrier per DP row.  A Backward row (fwdback.c:566-692) has two serial parts: the B-state sum
+// xB = sum_k M(i+1,k) e_k(x_{i+1}) tBM_k, from which xE follows, and the D<-D chain D_k = P_k + xE + tDD_k D_{k+1}.
+// The chain is affine in xE and in what enters a lane from above, with ROW-INVARIANT coefficients:
+//   D_k = Dz_k + xE * Q_k,   Q_k = 1 + tDD_k Q_{k+1}  (whole model, built once per CTA),   Dz = the chain over P alone,
+//   Dz[j] = Dploc[j] + PPs[j] * Yin,   PPs[j] = prod_{j'>=j} tDD[j'],   Dploc = the lane's own chain, Yin = Dz entering it,
+// so the scan over P (one Kogge-Stone pass with constant multipliers, the xB partial sums riding along) runs BEFORE xE is
+// known; lane 0 publishes the warp's map and sum, and after the barrier every thread finishes the row from shared memory.
+// The k+1 neighbour across a warp boundary is rebuilt by the reader from three published numbers (Ma + xE*Mq + Mk*Yz).
+// Arithmetic inside a cell is that of fwdbwd.cu (no FMA, FTZ); only the association order of the D<-D sums differs.
 #include "fwdbwd_mw.cuh"
 
 namespace p7g {
@@ -6,11 +16,16 @@ namespace p7g {
 template <int C, int W>
 __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
 {
-  __shared__ long long s_work[2];
-  __shared__ float s_me[W];          // M(i+1,k) e_k(x_{i+1}) of a warp's first node (the k+1 neighbour of the warp below)
-  __shared__ float s_scan[W][2];     // D of a warp's first node as a map of what enters behind its last node
-  __shared__ float s_sum[W];
+  static_assert(C >= 2, "the warp-boundary reconstruction uses the lane's second node");
   constexpr int G = 32 * W;
+  __shared__ long long s_work[2];
+  __shared__ float2 s_pq[C][G];         // (PPs[j], Q[j]) per thread
+  __shared__ float s_kB[5][G];
+  __shared__ float s_qa[G], s_qb[G], s_qin[G + 1];
+  __shared__ float s_wB[W], s_wMq[W], s_wMk[W];
+  __shared__ float s_pub[2][W][4];      // per row parity: P (Dz of the warp's first node, nothing entering), sumB, Ma
+  __shared__ float s_first[W];          // M of a warp's first node after the row-L initialisation
+  __shared__ float s_sum[W];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int g = threadIdx.x;
   float rBM[C], rMD[C], rMI[C], rII[C], rDD[C], nMM[C], nIM[C], nDM[C];
@@ -28,9 +43,43 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
       nDM[j] = __ldg(p.tf + (3 * C) * G + g + 1);
     } else nMM[j] = nIM[j] = nDM[j] = 0.0f;
   }
+  // ---- row-invariant coefficients ----
+  float Bexc, Qn;                       // Bexc: product of tDD over the lanes above me in my warp; Qn: Q of the next lane's first node
+  {
+    float pps = 1.0f, qa = 0.f;         // lane map of Q: Q_first = qa + pps * Q_in
+#pragma unroll
+    for (int j = C - 1; j >= 0; j--) { pps = rDD[j] * pps; s_pq[j][g].x = pps; qa = 1.0f + rDD[j] * qa; }
+    s_qa[g] = qa; s_qb[g] = pps;
+    float B = pps;
+#pragma unroll
+    for (int d = 0; d < 5; d++) {
+      s_kB[d][g] = B;                                                 // this lane's segment before step d
+      const float Bn = __shfl_down_sync(0xffffffffu, B, 1 << d);
+      if (lane + (1 << d) < 32) B = B * Bn;
+    }
+    Bexc = __shfl_down_sync(0xffffffffu, B, 1);
+    if (lane == 31) Bexc = 1.0f;
+    if (lane == 0) s_wB[w] = B;
+    __syncthreads();
+    if (g == 0) {                                                     // Q over the whole model, once per CTA
+      float q = 0.f;
+      for (int t = G - 1; t >= 0; t--) { s_qin[t + 1] = q; q = s_qa[t] + s_qb[t] * q; }
+      s_qin[0] = q;
+    }
+    __syncthreads();
+    Qn = s_qin[g + 1];
+    float q = Qn;
+#pragma unroll
+    for (int j = C - 1; j >= 0; j--) { q = 1.0f + rDD[j] * q; s_pq[j][g].y = q; }
+    if (lane == 0) {
+      s_wMq[w] = 1.0f + rMD[0] * s_pq[1][g].y;
+      s_wMk[w] = (rMD[0] * s_pq[1][g].x) * Bexc;
+    }
+  }
   const float *rfg = p.rf + g;
+  const bool has_next = (g + 1 < G);
   long long s, out;
-  while (mw_next_target(p.c, s_work, &s, &out)) {
+  while (mw_next_target(p.c, s_work, &s, &out)) {         // (its barriers also order the coefficient stores above)
     const int L = p.c.len[s];
     const uint8_t *seq = p.c.res + p.c.off[s];            // seq[i-1] = x_i
     const float pmove = p.c.lc[L].pmove, ploop = 1.0f - pmove;
@@ -38,6 +87,7 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
     float *brow = p.xmx ? p.xmx + p.xmx_off[out] : nullptr;
     float mp[C], ip[C], dp[C], e[C];
     float xJ = 0.f, xB = 0.f, xN = 0.f, xC = pmove, xE = xC * p.s.xf_E_move, totscale;   // row L, :492-500
+    float nm = 0.f, en = 0.f;           // M(i+1,.) and emission of the node after this lane's last node (lane 31 uses them)
     bool own_scales = false;
 #pragma unroll
     for (int j = 0; j < C; j++) e[j] = 0.0f;
@@ -45,31 +95,16 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
       const float *rfx = rfg + (size_t) __ldg(seq + L - 1) * (C * G);
 #pragma unroll
       for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
+      if (has_next) en = __ldg(rfx + 1);
     }
 
-    // ---- row L: D_k = xE + tDD_k D_{k+1};  M_k = xE + tMD_k D_{k+1};  I_k = 0  (:501-533) ----
+    // ---- row L: D_k = xE + tDD_k D_{k+1} = xE Q_k;  M_k = xE + tMD_k D_{k+1};  I_k = 0  (:501-533) ----
     {
-      float A = 0.f, B = 1.f;
-#pragma unroll
-      for (int j = C - 1; j >= 0; j--) { const float t = rDD[j]; A = xE + t * A; B = t * B; }
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float A2 = __shfl_down_sync(0xffffffffu, A, d), B2 = __shfl_down_sync(0xffffffffu, B, d);
-        if (lane + d < 32) { A = A + B * A2; B = B * B2; }
-      }
-      if (lane == 0) { s_scan[w][0] = A; s_scan[w][1] = B; }
-      __syncthreads();
-      float Y = 0.f;                                                  // D of the first node of the warp above
-      for (int v = W - 1; v > w; v--) Y = s_scan[v][0] + s_scan[v][1] * Y;
-      float carry;
-      {
-        const float An = __shfl_down_sync(0xffffffffu, A, 1), Bn = __shfl_down_sync(0xffffffffu, B, 1);
-        carry = (lane == 31) ? Y : An + Bn * Y;
-      }
+      float carry = xE * Qn;
 #pragma unroll
       for (int j = C - 1; j >= 0; j--) {
         mp[j] = xE + carry * rMD[j];
-        dp[j] = xE + carry * rDD[j];
+        dp[j] = xE * s_pq[j][g].y;
         ip[j] = 0.f;
         carry = dp[j];
       }
@@ -85,23 +120,19 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
       totscale = (float) log((double) scale);
       if (brow && g == 0) mw_store_specials(brow + (size_t) L * 6, xE, xN, xJ, xB, xC, scale);
     }
+    if (lane == 0) s_first[w] = mp[0];
+    __syncthreads();
+    if (w + 1 < W) nm = s_first[w + 1];
 
     // ---- rows L-1 .. 1 (:566-692) ----
     for (int i = L - 1; i >= 1; i--) {
       const float fscale = frow[(size_t) i * 6 + 5];
       // e[j] <- M(i+1,k) * e_k(x_{i+1})
-      float sumB = 0.f;
+      float S = 0.f;
 #pragma unroll
-      for (int j = 0; j < C; j++) { e[j] = mp[j] * e[j]; sumB += e[j] * rBM[j]; }
-      {
-        const float part = mw_warp_sum(sumB);
-        if (lane == 0) { s_sum[w] = part; s_me[w] = e[0]; }
-      }
-      __syncthreads();                                                // ---- barrier 1 ----
-      xB = s_sum[0];
-      for (int v = 1; v < W; v++) xB += s_sum[v];
+      for (int j = 0; j < C; j++) { e[j] = mp[j] * e[j]; S += e[j] * rBM[j]; }
       float me_next = __shfl_down_sync(0xffffffffu, e[0], 1);         // cell k+1 of the last cell of this lane
-      if (lane == 31) me_next = (w + 1 < W) ? s_me[w + 1] : 0.f;
+      if (lane == 31) me_next = nm * en;
 #pragma unroll
       for (int j = 0; j < C; j++) {
         const float mpv = (j + 1 < C) ? e[j + 1] : me_next;
@@ -114,37 +145,52 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
         const float *rfx = rfg + (size_t) __ldg(seq + i - 1) * (C * G);
 #pragma unroll
         for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
+        if (has_next) en = __ldg(rfx + 1);
       }
+      // the lane's own chain over P alone: dp[j] <- Dploc[j]
+#pragma unroll
+      for (int j = C - 2; j >= 0; j--) dp[j] = dp[j] + rDD[j] * dp[j + 1];
+      float P = dp[0];
+#pragma unroll
+      for (int d = 0; d < 5; d++) {                                   // lane maps -> inclusive warp suffix; xB partial sums ride along
+        const float Pn = __shfl_down_sync(0xffffffffu, P, 1 << d), Sn = __shfl_down_sync(0xffffffffu, S, 1 << d);
+        if (lane + (1 << d) < 32) { P = P + s_kB[d][g] * Pn; S = S + Sn; }
+      }
+      float Yin = __shfl_down_sync(0xffffffffu, P, 1);                // Dz of the next lane's first node when nothing enters the warp
+      if (lane == 31) Yin = 0.f;
+      const int par = i & 1;
+      if (lane == 0) {
+        float *pub = s_pub[par][w];
+        pub[0] = P; pub[1] = S;
+        pub[2] = mp[0] + rMD[0] * (dp[1] + s_pq[1][g].x * Yin);       // Ma: M of my first node without its xE and Yz_w terms
+      }
+      __syncthreads();                                                // ---- the row's only barrier ----
+      xB = 0.f;
+#pragma unroll
+      for (int v = 0; v < W; v++) xB += s_pub[par][v][1];
       xC = xC * ploop;
       xJ = (xB * pmove) + (xJ * ploop);
       xN = (xB * pmove) + (xN * ploop);
       xE = (xC * p.s.xf_E_move) + (xJ * p.s.xf_E_loop);
-      // D_k = P_k + xE + tDD_k D_{k+1}: suffix scan
+      float Yz = 0.f, Ymine = 0.f, Ynext = 0.f;                       // Yz_v = Dz entering warp v from above
+#pragma unroll
+      for (int v = W - 1; v >= 0; v--) {
+        if (v == w) Ymine = Yz;
+        if (v == w + 1) Ynext = Yz;
+        Yz = s_pub[par][v][0] + s_wB[v] * Yz;
+      }
+      Yin = Yin + Bexc * Ymine;
       {
-        float A = 0.f, B = 1.f;
-#pragma unroll
-        for (int j = C - 1; j >= 0; j--) { const float t = rDD[j]; A = dp[j] + (t * A + xE); B = t * B; }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const float A2 = __shfl_down_sync(0xffffffffu, A, d), B2 = __shfl_down_sync(0xffffffffu, B, d);
-          if (lane + d < 32) { A = A + B * A2; B = B * B2; }
-        }
-        if (lane == 0) { s_scan[w][0] = A; s_scan[w][1] = B; }
-        __syncthreads();                                              // ---- barrier 2 ----
-        float Y = 0.f;
-        for (int v = W - 1; v > w; v--) Y = s_scan[v][0] + s_scan[v][1] * Y;
-        float carry;
-        {
-          const float An = __shfl_down_sync(0xffffffffu, A, 1), Bn = __shfl_down_sync(0xffffffffu, B, 1);
-          carry = (lane == 31) ? Y : An + Bn * Y;
-        }
+        float carry = Yin + xE * Qn;                                  // full D of the node behind this lane's last node
 #pragma unroll
         for (int j = C - 1; j >= 0; j--) {
+          const float2 pq = s_pq[j][g];
           mp[j] = (mp[j] + xE) + carry * rMD[j];
-          dp[j] = dp[j] + (carry * rDD[j] + xE);
+          dp[j] = (dp[j] + pq.x * Yin) + xE * pq.y;
           carry = dp[j];
         }
       }
+      if (w + 1 < W) nm = (s_pub[par][w + 1][2] + xE * s_wMq[w + 1]) + s_wMk[w + 1] * Ynext;
       if (xB > 1.0e16f) own_scales = true;                            // :661
       float scale;
       if (own_scales) scale = (xB > 1.0e4f) ? xB : 1.0f;
@@ -154,6 +200,7 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
         xE /= scale; xN /= scale; xJ /= scale; xB /= scale; xC /= scale;
 #pragma unroll
         for (int j = 0; j < C; j++) { mp[j] *= inv; dp[j] *= inv; ip[j] *= inv; }
+        nm *= inv;
         totscale = (float) ((double) totscale + log((double) scale));
       }
       if (brow && g == 0) mw_store_specials(brow + (size_t) i * 6, xE, xN, xJ, xB, xC, scale);
@@ -167,9 +214,10 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
         for (int j = 0; j < C; j++) sumB += (mp[j] * e[j]) * rBM[j];
       }
       const float part = mw_warp_sum(sumB);
-      if (lane == 0) s_sum[w] = part;                                 // (row 1's readers of s_sum are behind its barrier 2)
+      if (lane == 0) s_sum[w] = part;
       __syncthreads();
       xB = s_sum[0];
+#pragma unroll
       for (int v = 1; v < W; v++) xB += s_sum[v];
       xN = (xB * pmove) + (xN * ploop);
       if (brow && g == 0) mw_store_specials(brow, 0.f, xN, 0.f, xB, 0.f, 1.0f);

@@ -59,7 +59,7 @@ __device__ __forceinline__ bool mw_next_target(const DpCommon &c, long long *sh,
 
 // (cells per lane C, warps per CTA W) instances; G = 32*W is a compile-time constant so that table loads have immediate offsets
 #define P7G_MW_CASES(X) \
-  X(9, 2) X(10, 2) X(11, 2) X(12, 2) X(13, 2) X(14, 2) X(15, 2) X(16, 2) \
+  X(5, 2) X(6, 2) X(7, 2) X(8, 2) X(9, 2) X(10, 2) X(11, 2) X(12, 2) X(13, 2) X(14, 2) X(15, 2) X(16, 2) \
   X(9, 4) X(10, 4) X(11, 4) X(12, 4) X(13, 4) X(14, 4) X(15, 4) X(16, 4) \
   X(9, 8) X(10, 8) X(11, 8) X(12, 8) X(13, 8) X(14, 8) \
   X(10, 12) X(11, 12)
