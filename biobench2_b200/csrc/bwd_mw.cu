@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
       p.c.sc[out] = sc;
       p.c.status[out] = status;
       if (p.totscale) p.totscale[out] = totscale;
+      if (p.own) p.own[out] = own_scales ? 1 : 0;
     }
   }
 }

@@ -21,6 +21,7 @@ struct FbParams {
   const float *fwd_xmx; // backward only: forward specials (scale factors)
   const int64_t *xmx_off;
   float *totscale;      // per-target total log scale (may be null)
+  int32_t *own;         // backward only: has_own_scales per target (may be null)
 };
 
 __device__ __forceinline__ float warp_sum(float v)
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(DP_THREADS) bwd_kernel(const FbParams p)
       p.c.sc[out] = sc;
       p.c.status[out] = status;
       if (p.totscale) p.totscale[out] = totscale;
+      if (p.own) p.own[out] = own_scales ? 1 : 0;
     }
   }
 #undef T_
@@ -355,10 +357,10 @@ int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   const Lane &ln = ctx->lanes[lane];
   FbParams p;
   P7G_CHECK(fill_common(ln, prof, db, d_idx, n, d_sc, d_status, CTR_FWD_WORK, &p));
-  p.xmx = d_xmx; p.fwd_xmx = nullptr; p.xmx_off = d_xmx_off; p.totscale = d_totscale;
+  p.xmx = d_xmx; p.fwd_xmx = nullptr; p.xmx_off = d_xmx_off; p.totscale = d_totscale; p.own = nullptr;
   if (prof->mwW > 0 && !ctx->fb_one_warp) {                           // long model: one CTA per target
     FbMwParams q; q.c = p.c; q.rf = prof->d_rf_mw; q.tf = prof->d_tf_mw; q.s = p.s;
-    q.xmx = p.xmx; q.fwd_xmx = nullptr; q.xmx_off = p.xmx_off; q.totscale = p.totscale;
+    q.xmx = p.xmx; q.fwd_xmx = nullptr; q.xmx_off = p.xmx_off; q.totscale = p.totscale; q.own = nullptr;
     return launch_fwd_mw(ctx, ln.stream, prof, q);
   }
   switch (prof->dpC) {
@@ -371,16 +373,16 @@ int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
 
 int launch_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                const float *d_fwd_xmx, const int64_t *d_xmx_off, float *d_sc, int32_t *d_status,
-               float *d_bck_xmx, float *d_totscale)
+               float *d_bck_xmx, float *d_totscale, int32_t *d_own)
 {
   if (n <= 0) return P7GPU_OK;
   const Lane &ln = ctx->lanes[lane];
   FbParams p;
   P7G_CHECK(fill_common(ln, prof, db, d_idx, n, d_sc, d_status, CTR_BWD_WORK, &p));
-  p.xmx = d_bck_xmx; p.fwd_xmx = d_fwd_xmx; p.xmx_off = d_xmx_off; p.totscale = d_totscale;
+  p.xmx = d_bck_xmx; p.fwd_xmx = d_fwd_xmx; p.xmx_off = d_xmx_off; p.totscale = d_totscale; p.own = d_own;
   if (prof->mwW > 0 && !ctx->fb_one_warp) {
     FbMwParams q; q.c = p.c; q.rf = prof->d_rf_mw; q.tf = prof->d_tf_mw; q.s = p.s;
-    q.xmx = p.xmx; q.fwd_xmx = p.fwd_xmx; q.xmx_off = p.xmx_off; q.totscale = p.totscale;
+    q.xmx = p.xmx; q.fwd_xmx = p.fwd_xmx; q.xmx_off = p.xmx_off; q.totscale = p.totscale; q.own = d_own;
     return launch_bwd_mw(ctx, ln.stream, prof, q);
   }
   switch (prof->dpC) {

@@ -24,6 +24,7 @@ struct FbMwParams {
   const float *fwd_xmx; // backward only: forward specials (scale factors)
   const int64_t *xmx_off;
   float *totscale;      // per-target total log scale (may be null)
+  int32_t *own;         // backward only: has_own_scales per target (may be null)
 };
 
 __device__ __forceinline__ float mw_warp_sum(float v)

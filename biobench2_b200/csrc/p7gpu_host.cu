@@ -755,6 +755,41 @@ int p7gpu_backward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_
   return fetch_batch(ctx, b, sc, status);
 }
 
+// The region trigger of p7_domaindef_ByPosteriorHeuristics for targets whose specials are on the host (decode.cu).
+int p7gpu_region_trigger_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                               const int64_t *idx, int64_t n, const float *fwd_xmx, const float *bck_xmx,
+                               const int64_t *xmx_offsets, const int32_t *bck_own_scales, float *mocc_max, int32_t *flag)
+{
+  if (!ctx || !prof || !db || !fwd_xmx || !bck_xmx || !xmx_offsets || !mocc_max || !flag) return P7GPU_EINVAL;
+  P7G_CUDA(cudaSetDevice(ctx->device));
+  BatchBufs b;
+  P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
+  if (b.n == 0) return P7GPU_OK;
+  std::vector<int32_t> lens;
+  P7G_CHECK(lengths_of(ctx, db, idx, b.n, lens));
+  const int64_t ext = xmx_extent(db, xmx_offsets, b.n, lens.data());
+  const size_t nb = (size_t) b.n;
+  const size_t off_bytes = (nb * 8 + 255) / 256 * 256, w_bytes = (nb * 4 + 255) / 256 * 256;
+  const size_t x_bytes = ((size_t) ext * 4 + 255) / 256 * 256;
+  P7G_CHECK(ensure_scratch2(ctx, off_bytes + 3 * w_bytes + 2 * x_bytes + 256));
+  char *base = (char *) ctx->d_scratch2;
+  int64_t *d_xoff = (int64_t *) base;
+  int32_t *d_own = (int32_t *) (base + off_bytes), *d_flag = (int32_t *) (base + off_bytes + w_bytes);
+  float *d_mocc = (float *) (base + off_bytes + 2 * w_bytes);
+  float *d_fx = (float *) (base + off_bytes + 3 * w_bytes), *d_bx = (float *) (base + off_bytes + 3 * w_bytes + x_bytes);
+  cudaStream_t st = ctx->stream;
+  P7G_CUDA(cudaMemcpyAsync(d_xoff, xmx_offsets, 8 * nb, cudaMemcpyHostToDevice, st));
+  if (bck_own_scales) P7G_CUDA(cudaMemcpyAsync(d_own, bck_own_scales, 4 * nb, cudaMemcpyHostToDevice, st));
+  P7G_CUDA(cudaMemcpyAsync(d_fx, fwd_xmx, 4 * (size_t) ext, cudaMemcpyHostToDevice, st));
+  P7G_CUDA(cudaMemcpyAsync(d_bx, bck_xmx, 4 * (size_t) ext, cudaMemcpyHostToDevice, st));
+  P7G_CHECK(launch_region_trigger(ctx, 0, prof, db->view(), b.d_idx, b.n, d_fx, d_bx, d_xoff, bck_own_scales ? d_own : nullptr,
+                                  d_mocc, d_flag, nullptr));
+  P7G_CUDA(cudaMemcpyAsync(mocc_max, d_mocc, 4 * nb, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaMemcpyAsync(flag, d_flag, 4 * nb, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaStreamSynchronize(st));
+  return P7GPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Signature-level wrappers: one target per call (impl_sse.h:309-344)
 // ---------------------------------------------------------------------------------------------------

@@ -202,7 +202,13 @@ int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
                float *d_sc, int32_t *d_status, float *d_xmx, const int64_t *d_xmx_off, float *d_totscale);
 int launch_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                const float *d_fwd_xmx, const int64_t *d_xmx_off, float *d_sc, int32_t *d_status,
-               float *d_bck_xmx, float *d_totscale);
+               float *d_bck_xmx, float *d_totscale, int32_t *d_own = nullptr);
+// decode.cu: the region trigger of p7_domaindef_ByPosteriorHeuristics (max_i mocc[i] >= rt1) and the gather of selected specials
+int launch_region_trigger(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+                          const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int32_t *d_own,
+                          float *d_mocc_max, int32_t *d_flag, unsigned int *d_nflag);
+int launch_gather_xmx(p7gpu_ctx *ctx, int lane, const float *d_fx, const float *d_bx, const int64_t *d_src, const int64_t *d_dst,
+                      const int32_t *d_nfloats, int64_t n, float *d_ofx, float *d_obx);
 int launch_bias(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                 float *d_filtersc);
 }  // namespace p7g

@@ -24,6 +24,7 @@ struct p7gpu_pipeline_result {
   std::vector<float> fwd_xmx, bck_xmx;
   std::vector<p7gpu_msv_survivor> msv_pass;       // only when opts->stop_after_msv
   uint64_t stage_nres[5] = {0, 0, 0, 0, 0};       // residues seen by the MSV, bias, Viterbi, Forward, Backward stages
+  uint64_t n_region_flagged = 0;                  // survivors whose specials were returned
 };
 
 namespace p7g {
@@ -221,48 +222,75 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     res->counters.n_past_fwd += bidx.size();
     if (!bidx.empty()) {
       const size_t nb = bidx.size();
-      DevBuf d_bidx, d_boff, d_bsc, d_bst, d_btot, d_bx;
+      DevBuf d_bidx, d_boff, d_bsc, d_bst, d_btot, d_bx, d_own, d_mocc, d_flag;
       P7G_CHECK(upload_idx(ctx, bidx, &d_bidx)); P7G_CHECK(upload_idx(ctx, boff, &d_boff));
       P7G_CHECK(d_bsc.alloc(4 * nb, st)); P7G_CHECK(d_bst.alloc(4 * nb, st)); P7G_CHECK(d_btot.alloc(4 * nb, st));
-      P7G_CHECK(d_bx.alloc(o->want_specials ? 4 * ext : 256, st));
+      P7G_CHECK(d_own.alloc(4 * nb, st));
+      const bool keep_bx = o->want_specials || o->region_trigger;
+      P7G_CHECK(d_bx.alloc(keep_bx ? 4 * ext : 256, st));
       P7G_CHECK(launch_bwd(ctx, 0, prof, dbv, d_bidx.as<int64_t>(), (int64_t) nb, d_fx.as<float>(), d_boff.as<int64_t>(),
-                           d_bsc.as<float>(), d_bst.as<int32_t>(), o->want_specials ? d_bx.as<float>() : nullptr, d_btot.as<float>()));
-      std::vector<float> bsc(nb), btot(nb);
+                           d_bsc.as<float>(), d_bst.as<int32_t>(), keep_bx ? d_bx.as<float>() : nullptr, d_btot.as<float>(),
+                           d_own.as<int32_t>()));
+      std::vector<float> bsc(nb), btot(nb), mocc(nb, NAN); std::vector<int32_t> own(nb), flag(nb, -1);
       P7G_CUDA(cudaMemcpyAsync(bsc.data(), d_bsc.p, 4 * nb, cudaMemcpyDeviceToHost, st));
       P7G_CUDA(cudaMemcpyAsync(btot.data(), d_btot.p, 4 * nb, cudaMemcpyDeviceToHost, st));
-      if (o->want_specials) {
-        size_t need = 0;
-        for (size_t k = 0; k < nb; k++) need += (size_t) (cand[bwhere[k]].L + 1) * 6;
+      P7G_CUDA(cudaMemcpyAsync(own.data(), d_own.p, 4 * nb, cudaMemcpyDeviceToHost, st));
+      if (o->region_trigger) {                                       // p7_domaindef.c:419 on the device (decode.cu)
+        P7G_CHECK(d_mocc.alloc(4 * nb, st)); P7G_CHECK(d_flag.alloc(4 * nb, st));
+        P7G_CHECK(launch_region_trigger(ctx, 0, prof, dbv, d_bidx.as<int64_t>(), (int64_t) nb, d_fx.as<float>(), d_bx.as<float>(),
+                                        d_boff.as<int64_t>(), d_own.as<int32_t>(), d_mocc.as<float>(), d_flag.as<int32_t>(), nullptr));
+        P7G_CUDA(cudaMemcpyAsync(mocc.data(), d_mocc.p, 4 * nb, cudaMemcpyDeviceToHost, st));
+        P7G_CUDA(cudaMemcpyAsync(flag.data(), d_flag.p, 4 * nb, cudaMemcpyDeviceToHost, st));
+      }
+      P7G_CUDA(cudaStreamSynchronize(st));
+      // which survivors' specials go to the host: all of them, or those whose region trigger fired
+      std::vector<int64_t> src, dst; std::vector<int32_t> nfl; std::vector<int64_t> host_off(nb, -1);
+      size_t need = 0;
+      if (o->want_specials)
+        for (size_t k = 0; k < nb; k++) {
+          if (o->region_trigger && flag[k] == 0) continue;
+          const size_t len = (size_t) (cand[bwhere[k]].L + 1) * 6;
+          src.push_back(boff[k]); dst.push_back((int64_t) need); nfl.push_back((int32_t) len);
+          host_off[k] = (int64_t) (host_floats + need);
+          need += len;
+        }
+      if (need) {
         if ((host_floats + need) * 8 > ((size_t) 48 << 30)) {
-          set_error("pipeline: Forward/Backward specials of the survivors exceed 48 GiB of host memory; run with want_specials=0 "
-                    "(the on-device region trigger that would avoid this is SURVEY.md 8f-2, not built yet)");
+          set_error("pipeline: Forward/Backward specials of the survivors exceed 48 GiB of host memory; run with region_trigger=1 "
+                    "(specials only for targets that can have a domain) or want_specials=0");
           return P7GPU_EMEM;
         }
         res->fwd_xmx.resize(host_floats + need); res->bck_xmx.resize(host_floats + need);
-        if (nb == n) {                                           // everything survived (e.g. --max): one bulk copy each
+        if (src.size() == n) {                                       // every target of the slice: one bulk copy each
           P7G_CUDA(cudaMemcpyAsync(res->fwd_xmx.data() + host_floats, d_fx.p, 4 * need, cudaMemcpyDeviceToHost, st));
           P7G_CUDA(cudaMemcpyAsync(res->bck_xmx.data() + host_floats, d_bx.p, 4 * need, cudaMemcpyDeviceToHost, st));
-        } else {
-          size_t pos = host_floats;
-          for (size_t k = 0; k < nb; k++) {
-            const size_t len = (size_t) (cand[bwhere[k]].L + 1) * 6;
-            P7G_CUDA(cudaMemcpyAsync(res->fwd_xmx.data() + pos, d_fx.as<float>() + boff[k], 4 * len, cudaMemcpyDeviceToHost, st));
-            P7G_CUDA(cudaMemcpyAsync(res->bck_xmx.data() + pos, d_bx.as<float>() + boff[k], 4 * len, cudaMemcpyDeviceToHost, st));
-            pos += len;
-          }
+        } else {                                                     // dense copy on the device first, then one bulk copy each
+          DevBuf d_src, d_dst, d_nfl, d_ofx, d_obx;
+          P7G_CHECK(upload_idx(ctx, src, &d_src)); P7G_CHECK(upload_idx(ctx, dst, &d_dst));
+          P7G_CHECK(d_nfl.alloc(4 * nfl.size(), st));
+          P7G_CUDA(cudaMemcpyAsync(d_nfl.p, nfl.data(), 4 * nfl.size(), cudaMemcpyHostToDevice, st));
+          P7G_CHECK(d_ofx.alloc(4 * need, st)); P7G_CHECK(d_obx.alloc(4 * need, st));
+          P7G_CHECK(launch_gather_xmx(ctx, 0, d_fx.as<float>(), d_bx.as<float>(), d_src.as<int64_t>(), d_dst.as<int64_t>(),
+                                      d_nfl.as<int32_t>(), (int64_t) src.size(), d_ofx.as<float>(), d_obx.as<float>()));
+          P7G_CUDA(cudaMemcpyAsync(res->fwd_xmx.data() + host_floats, d_ofx.p, 4 * need, cudaMemcpyDeviceToHost, st));
+          P7G_CUDA(cudaMemcpyAsync(res->bck_xmx.data() + host_floats, d_obx.p, 4 * need, cudaMemcpyDeviceToHost, st));
+          P7G_CUDA(cudaStreamSynchronize(st));                       // the staging vectors and buffers die with this scope
         }
+        P7G_CUDA(cudaStreamSynchronize(st));
       }
-      P7G_CUDA(cudaStreamSynchronize(st));
       for (size_t k = 0; k < nb; k++) {
         const Cand &c = cand[bwhere[k]];
         p7gpu_survivor s;
         s.seqidx = c.idx; s.L = c.L; s.msv_status = c.msv_st; s.vit_status = c.vit_st;
         s.usc = c.usc; s.vfsc = c.vfsc; s.fwdsc = c.fwdsc; s.bcksc = bsc[k]; s.nullsc = c.nullsc; s.filtersc = c.filtersc;
         s.fwd_totscale = c.ftot; s.bck_totscale = btot[k];
-        s.xmx_offset = o->want_specials ? (int64_t) host_floats : -1;
-        if (o->want_specials) host_floats += (size_t) (c.L + 1) * 6;
+        s.bck_own_scales = own[k];
+        s.xmx_offset = host_off[k];
+        s.region_flag = flag[k]; s.mocc_max = mocc[k];
         res->survivors.push_back(s);
       }
+      host_floats += need;
+      res->n_region_flagged += (uint64_t) src.size();
     }
     lo = hi;
   }

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libp7gpu.so")
 
 OK, EMEM, EINVAL, ESYS, ERANGE, ENORESULT = 0, 5, 11, 12, 16, 19
-KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD, KERNEL_BIAS = range(6)
+KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD, KERNEL_BIAS, KERNEL_TRIG = range(7)
 
 EXPORTS = [
     "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
@@ -22,7 +22,7 @@ EXPORTS = [
     "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M", "p7gpu_profile_set_biasfilter",
     "p7gpu_seqdb_upload", "p7gpu_seqdb_adopt_device", "p7gpu_seqdb_destroy", "p7gpu_seqdb_nseq", "p7gpu_seqdb_nres",
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
-    "p7gpu_backward_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
+    "p7gpu_backward_batch", "p7gpu_region_trigger_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
     "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser",
     "p7gpu_pipeline_run", "p7gpu_pipeline_run_host", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
@@ -39,7 +39,7 @@ class P7GpuError(RuntimeError):
 class PipelineOpts(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double),
                 ("do_biasfilter", C.c_int32), ("do_max", C.c_int32), ("want_specials", C.c_int32),
-                ("stop_after_msv", C.c_int32)]
+                ("stop_after_msv", C.c_int32), ("region_trigger", C.c_int32), ("reserved", C.c_int32)]
 
 
 class MsvSurvivor(C.Structure):
@@ -55,7 +55,14 @@ class Survivor(C.Structure):
     _fields_ = [("seqidx", C.c_int64), ("L", C.c_int32), ("msv_status", C.c_int32), ("vit_status", C.c_int32),
                 ("usc", C.c_float), ("vfsc", C.c_float), ("fwdsc", C.c_float), ("bcksc", C.c_float),
                 ("nullsc", C.c_float), ("filtersc", C.c_float), ("fwd_totscale", C.c_float), ("bck_totscale", C.c_float),
-                ("xmx_offset", C.c_int64)]
+                ("bck_own_scales", C.c_int32), ("xmx_offset", C.c_int64), ("region_flag", C.c_int32), ("mocc_max", C.c_float)]
+
+
+SURVIVOR_NP = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("vit_status", "<i4"),
+                        ("usc", "<f4"), ("vfsc", "<f4"), ("fwdsc", "<f4"), ("bcksc", "<f4"), ("nullsc", "<f4"),
+                        ("filtersc", "<f4"), ("fwd_totscale", "<f4"), ("bck_totscale", "<f4"), ("bck_own_scales", "<i4"),
+                        ("xmx_offset", "<i8"), ("region_flag", "<i4"), ("mocc_max", "<f4")])
+assert SURVIVOR_NP.itemsize == C.sizeof(Survivor) == 72
 
 
 _lib = None
@@ -101,6 +108,7 @@ def lib():
         L.p7gpu_msvfilter_device.argtypes = [vp, vp, vp, C.c_double, vp, vp, vp, vp]
         L.p7gpu_profile_set_biasfilter.argtypes = [vp, vp, vp, vp]
         L.p7gpu_biasfilter_batch.argtypes = [vp, vp, vp, vp, i64, vp]
+        L.p7gpu_region_trigger_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
         L.p7gpu_msvfilter_stream.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.c_double, vp, vp, vp, C.POINTER(i64), C.POINTER(vp)]
         L.p7gpu_pipeline_run_host.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.POINTER(PipelineOpts), C.POINTER(vp)]
         L.p7gpu_result_stage_residues.restype = C.POINTER(C.c_uint64)
@@ -306,6 +314,17 @@ def backward_batch(ctx, prof, db, fwd_xmx, xoff, idx=None):
     return sc, st, bx, tot
 
 
+def region_trigger_batch(ctx, prof, db, fwd_xmx, bck_xmx, xoff, idx=None, own_scales=None):
+    """max_i mocc[i] and the region-trigger flag of p7_domaindef_ByPosteriorHeuristics per target (p7gpu_region_trigger_batch)."""
+    n = len(idx) if idx is not None else db.nseq
+    idx_a = np.ascontiguousarray(idx, np.int64) if idx is not None else None
+    own = np.ascontiguousarray(own_scales, np.int32) if own_scales is not None else None
+    mocc = np.zeros(n, np.float32); flag = np.zeros(n, np.int32)
+    _check(lib().p7gpu_region_trigger_batch(ctx.h, prof.h, db.h, _p(idx_a), n, _p(fwd_xmx), _p(bck_xmx),
+                                            _p(np.ascontiguousarray(xoff, np.int64)), _p(own), _p(mocc), _p(flag)))
+    return mocc, flag
+
+
 def msvfilter_device(ctx, prof, db, d_sc_ptr, d_status_ptr, F1=0.02, d_pass_list_ptr=None, d_pass_count_ptr=None):
     """MSV stage with results left in HBM (device pointers: nseq floats / int32; optional pass list int32[nseq] + uint32 count)."""
     _check(lib().p7gpu_msvfilter_device(ctx.h, prof.h, db.h, F1, C.c_void_p(d_sc_ptr), C.c_void_p(d_status_ptr),
@@ -346,12 +365,13 @@ class PipelineResult:
         self.stage_residues = {k: int(sr[i]) for i, k in enumerate(("msv", "bias", "vit", "fwd", "bwd"))}
         n = L.p7gpu_result_nsurvivors(h)
         sv = L.p7gpu_result_survivors(h)
-        names = [f[0] for f in Survivor._fields_]
-        self.survivors = [{k: getattr(sv[i], k) for k in names} for i in range(n)]
-        ext = 0
-        for s in self.survivors:
-            if s["xmx_offset"] >= 0:
-                ext = max(ext, s["xmx_offset"] + (s["L"] + 1) * 6)
+        if n:                                  # one structured array (a --max run returns millions of records)
+            raw = np.ctypeslib.as_array(C.cast(sv, C.POINTER(C.c_uint8)), shape=(n * C.sizeof(Survivor),))
+            self.survivors = raw.view(SURVIVOR_NP).copy()
+        else:
+            self.survivors = np.zeros(0, SURVIVOR_NP)
+        have = self.survivors["xmx_offset"] >= 0
+        ext = int((self.survivors["xmx_offset"][have] + (self.survivors["L"][have].astype(np.int64) + 1) * 6).max()) if have.any() else 0
         if ext:
             self.fwd_xmx = np.ctypeslib.as_array(L.p7gpu_result_fwd_xmx(h), shape=(ext,)).copy()
             self.bck_xmx = np.ctypeslib.as_array(L.p7gpu_result_bck_xmx(h), shape=(ext,)).copy()
@@ -367,23 +387,23 @@ class PipelineResult:
         L.p7gpu_result_destroy(h)
 
 
-def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv):
-    return PipelineOpts(F1, F2, F3, int(do_biasfilter), int(do_max), int(want_specials), int(stop_after_msv))
+def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger=False):
+    return PipelineOpts(F1, F2, F3, int(do_biasfilter), int(do_max), int(want_specials), int(stop_after_msv), int(region_trigger), 0)
 
 
 def pipeline_run(ctx, prof, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                 stop_after_msv=False):
+                 stop_after_msv=False, region_trigger=False):
     """The batched p7_Pipeline() over a resident database (defaults: p7_pipeline.c:214-216)."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run(ctx.h, prof.h, db.h, C.byref(o), C.byref(h)))
     return PipelineResult(h)
 
 
 def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False):
+                      stop_after_msv=False, region_trigger=False):
     """Same for a HOST PackedDB: the upload is streamed under the MSV stage."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
                                          _p(packed.lengths), packed.nseq, C.byref(o), C.byref(h)))

@@ -12,9 +12,10 @@ import numpy as np
 SURVIVOR_DTYPE = np.dtype([
     ("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("vit_status", "<i4"),
     ("usc", "<f4"), ("vfsc", "<f4"), ("fwdsc", "<f4"), ("bcksc", "<f4"), ("nullsc", "<f4"), ("filtersc", "<f4"),
-    ("fwd_totscale", "<f4"), ("bck_totscale", "<f4"), ("_pad", "<i4"), ("xmx_offset", "<i8")])     # = p7gpu_survivor, 64 bytes
+    ("fwd_totscale", "<f4"), ("bck_totscale", "<f4"), ("bck_own_scales", "<i4"), ("xmx_offset", "<i8"),
+    ("region_flag", "<i4"), ("mocc_max", "<f4")])                                                    # = p7gpu_survivor, 72 bytes
 MSV_DTYPE = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")])
-assert SURVIVOR_DTYPE.itemsize == 64 and MSV_DTYPE.itemsize == 24
+assert SURVIVOR_DTYPE.itemsize == 72 and MSV_DTYPE.itemsize == 24
 
 
 def shard_ranges(lengths, world):
@@ -41,10 +42,9 @@ def shard_db(packed, rank, world):
 def survivors_to_records(result, first_index=0):
     """engine.PipelineResult -> structured array with GLOBAL target indices."""
     rec = np.zeros(len(result.survivors), SURVIVOR_DTYPE)
-    for j, s in enumerate(result.survivors):
-        for k in SURVIVOR_DTYPE.names:
-            if k != "_pad":
-                rec[k][j] = s[k]
+    for k in SURVIVOR_DTYPE.names:
+        if k != "_pad":
+            rec[k] = result.survivors[k]
     rec["seqidx"] += first_index
     return rec
 

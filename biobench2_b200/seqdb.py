@@ -82,6 +82,11 @@ def pack(seqs, names=None):
     return PackedDB(residues, offsets, lengths, names)
 
 
+def concat(dbs):
+    """Several PackedDBs one after the other as one PackedDB."""
+    return pack([d.residues[int(d.offsets[s]):int(d.offsets[s]) + int(d.lengths[s])] for d in dbs for s in range(d.nseq)])
+
+
 def pack_from_lengths(lengths, flat_residues):
     """Vectorised pack: `flat_residues` are all residues back to back (sum(lengths) bytes)."""
     lengths = np.ascontiguousarray(lengths, dtype=np.int32)

@@ -100,7 +100,8 @@ int64_t     p7gpu_ctx_last_vit_redo(p7gpu_ctx *ctx);
 #define P7GPU_KERNEL_FWD  3
 #define P7GPU_KERNEL_BWD  4
 #define P7GPU_KERNEL_BIAS 5
-#define P7GPU_NKERNELS    6
+#define P7GPU_KERNEL_TRIG 6
+#define P7GPU_NKERNELS    7
 int         p7gpu_ctx_set_timing  (p7gpu_ctx *ctx, int on);
 int         p7gpu_ctx_reset_timing(p7gpu_ctx *ctx);
 int         p7gpu_ctx_kernel_time (p7gpu_ctx *ctx, int kind, double *ms_total, int64_t *nlaunches);
@@ -162,6 +163,14 @@ int p7gpu_backward_batch (p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu
                           const int64_t *idx, int64_t n, const float *fwd_xmx, const int64_t *xmx_offsets,
                           float *sc, int32_t *status, float *bck_xmx, float *bck_totscale);
 
+/* The region trigger of the domain-definition step: for each selected target, from its Forward and Backward
+ * specials, max_i ddef->mocc[i] as p7_DomainDecoding computes it (impl_sse/decoding.c:166-200) and flag = 1 where
+ * p7_domaindef_ByPosteriorHeuristics can open a region (mocc[i] >= rt1 = 0.25 for some i, p7_domaindef.c:109,419), or where
+ * the host must decide (Backward used its own scale factors, bck_own_scales[j] != 0; non-finite scale product).  flag = 0
+ * means ddef->nregions = 0: p7_Pipeline drops the target (p7_pipeline.c:739).  bck_own_scales may be NULL (all zero). */
+int p7gpu_region_trigger_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                               const int64_t *idx, int64_t n, const float *fwd_xmx, const float *bck_xmx,
+                               const int64_t *xmx_offsets, const int32_t *bck_own_scales, float *mocc_max, int32_t *flag);
 /* p7_bg_FilterScore (p7_bg.c:472-484): the bias-filter null score of the selected targets */
 int p7gpu_biasfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
                            const int64_t *idx, int64_t n, float *filtersc);
@@ -208,6 +217,12 @@ typedef struct p7gpu_pipeline_opts {   /* the fields of P7_PIPELINE the path rea
   int32_t do_max;                      /* --max: F1=F2=F3=1, bias off (p7_pipeline.c:222-229)         */
   int32_t want_specials;               /* 1: return fwd/bck xmx for Forward survivors                  */
   int32_t stop_after_msv;              /* 1: MSV stage only (BASELINE config 2): counters + the MSV survivors */
+  int32_t region_trigger;              /* 1: evaluate the region trigger of p7_domaindef_ByPosteriorHeuristics
+                                        *    (p7_DomainDecoding, impl_sse/decoding.c:166-200; mocc[i] >= rt1, p7_domaindef.c:419)
+                                        *    on the device and return specials only for survivors on which it fires: the
+                                        *    others have nregions = 0 and p7_Pipeline drops them (p7_pipeline.c:739).
+                                        *    Meant for --max, where every target reaches this point.   */
+  int32_t reserved;
 } p7gpu_pipeline_opts;
 
 typedef struct p7gpu_pipeline_counters { /* P7_PIPELINE accounting (hmmer.h:1224-1231), merged like p7_pipeline_Merge */
@@ -221,7 +236,11 @@ typedef struct p7gpu_survivor {        /* one per target that passed the Forward
   float   usc, vfsc, fwdsc, bcksc;     /* nats; vfsc = NaN when the Viterbi stage was skipped (:716)  */
   float   nullsc, filtersc;            /* p7_bg_NullOne / p7_bg_FilterScore                            */
   float   fwd_totscale, bck_totscale;
+  int32_t bck_own_scales;              /* P7_OMX.has_own_scales of the Backward matrix (fwdback.c:661-663)        */
   int64_t xmx_offset;                  /* float offset of this target's (L+1)*6 block in fwd_xmx/bck_xmx, or -1 */
+  int32_t region_flag;                 /* -1 not evaluated; 0: mocc[i] < rt1 everywhere, no region (nregions = 0);
+                                        *  1: the trigger fires somewhere (or the host must decide): specials returned */
+  float   mocc_max;                    /* max_i ddef->mocc[i] (NaN when not evaluated)                            */
 } p7gpu_survivor;
 
 typedef struct p7gpu_msv_survivor {    /* stop_after_msv: one per target with P(MSV) <= F1 (p7_pipeline.c:693-694) */

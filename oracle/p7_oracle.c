@@ -386,6 +386,37 @@ int p7o_backward(const P7O_PROFILE *p, const uint8_t *dsq, int L, const float *f
   return P7O_OK;
 }
 
+
+/* p7_DomainDecoding (impl_sse/decoding.c:166-200) restated on plain arrays; the N/J/C loop probabilities are the
+ * length-L values p7_oprofile_ReconfigRestLength sets (p7_oprofile.c:1112-1116), all three equal to ploop.
+ * The trigger is the rt1 test of p7_domaindef_ByPosteriorHeuristics (p7_domaindef.c:109,419). */
+int p7o_domain_decoding(const P7O_PROFILE *p, int L, const float *fx, const float *bx, int own,
+                        float *btot, float *etot, float *mocc, float *mocc_max, int *triggered)
+{
+  float pmove, ploop, scaleproduct = 1.0 / bx[1], njcp, b = 0.0f, e = 0.0f, m, mx = -INFINITY;
+  int i, trig = 0;
+  p7o_xf_ncj(p, L, &pmove, &ploop);
+  if (btot) btot[0] = 0.0f;
+  if (etot) etot[0] = 0.0f;
+  if (mocc) mocc[0] = 0.0f;
+  for (i = 1; i <= L; i++) {
+    b = b + (fx[(i-1)*6+3] * bx[(i-1)*6+3] * fx[(i-1)*6+5] * scaleproduct);
+    if (own) scaleproduct *= fx[(i-1)*6+5] / bx[(i-1)*6+5];
+    e = e + (fx[i*6+0] * bx[i*6+0] * fx[i*6+5] * scaleproduct);
+    njcp  = fx[(i-1)*6+1] * bx[i*6+1] * ploop * scaleproduct;
+    njcp += fx[(i-1)*6+2] * bx[i*6+2] * ploop * scaleproduct;
+    njcp += fx[(i-1)*6+4] * bx[i*6+4] * ploop * scaleproduct;
+    m = 1. - njcp;
+    if (btot) btot[i] = b;
+    if (etot) etot[i] = e;
+    if (mocc) mocc[i] = m;
+    if (m > mx) mx = m;
+    if (m >= 0.25f) trig = 1;
+  }
+  if (mocc_max) *mocc_max = mx;
+  if (triggered) *triggered = trig;
+  return isinf(scaleproduct) ? 16 : 0;
+}
 /* ---- bias filter: esl_hmm_Forward with M=2 (easel/esl_hmm.c:351-409) + p7_bg_FilterScore (p7_bg.c:472-484) ---- */
 float p7o_filtersc(const float *t6, const float *pi3, const float *eo, const uint8_t *dsq, int L)
 {

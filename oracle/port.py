@@ -39,6 +39,8 @@ def lib():
         L.p7o_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
                                    C.POINTER(C.c_int), C.POINTER(C.c_float)]
         L.p7o_filtersc.restype = C.c_float
+        L.p7o_domain_decoding.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.p7o_filtersc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         for nm in ("p7o_gumbel_surv", "p7o_exp_surv"):
             getattr(L, nm).restype = C.c_double
@@ -95,6 +97,14 @@ class OracleProfile:
         fwd_xmx = np.ascontiguousarray(fwd_xmx, np.float32)
         st = lib().p7o_backward(self.h, _p(dsq), L, _p(fwd_xmx), _p(xmx), C.byref(tot), C.byref(own), C.byref(sc))
         return st, np.float32(sc.value), xmx, np.float32(tot.value), own.value
+
+    def domain_decoding(self, L, fwd_xmx, bck_xmx, own_scales=0):
+        """-> dict(status, btot, etot, mocc [(L+1) each], mocc_max, triggered)"""
+        fx = np.ascontiguousarray(fwd_xmx, np.float32); bx = np.ascontiguousarray(bck_xmx, np.float32)
+        bt = np.zeros(L + 1, np.float32); et = np.zeros(L + 1, np.float32); mo = np.zeros(L + 1, np.float32)
+        mx = C.c_float(0); tr = C.c_int(0)
+        st = lib().p7o_domain_decoding(self.h, L, _p(fx), _p(bx), int(own_scales), _p(bt), _p(et), _p(mo), C.byref(mx), C.byref(tr))
+        return dict(status=st, btot=bt, etot=et, mocc=mo, mocc_max=np.float32(mx.value), triggered=tr.value)
 
     def tjb_b(self, L): return lib().p7o_tjb_b(self.h, L)
     def xw_move(self, L): return lib().p7o_xw_move(self.h, L)

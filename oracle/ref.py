@@ -67,6 +67,8 @@ def lib():
         for nm in ("p7ref_ssv", "p7ref_msv", "p7ref_vit"):
             getattr(L, nm).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         L.p7ref_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_float)]
+        L.p7ref_domain_decoding.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.p7ref_fwdbck.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.p7ref_nullsc.restype = C.c_float
@@ -185,6 +187,15 @@ class RefProfile:
                                 C.byref(ft), C.byref(bt), C.byref(own))
         return dict(status=st, fwdsc=np.float32(fsc.value), bcksc=np.float32(bsc.value), fwd_xmx=fx, bck_xmx=bx,
                     fwd_totscale=np.float32(ft.value), bck_totscale=np.float32(bt.value), bck_own_scales=own.value)
+
+    def domain_decoding(self, L, fwd_xmx, bck_xmx, own_scales=0):
+        """The reference's p7_DomainDecoding on the given specials + the region walk of p7_domaindef_ByPosteriorHeuristics
+        -> dict(status, btot, etot, mocc, nregions, triggered)."""
+        fx = np.ascontiguousarray(fwd_xmx, np.float32); bx = np.ascontiguousarray(bck_xmx, np.float32)
+        bt = np.zeros(L + 1, np.float32); et = np.zeros(L + 1, np.float32); mo = np.zeros(L + 1, np.float32)
+        nr = C.c_int(0); tr = C.c_int(0)
+        st = lib().p7ref_domain_decoding(self.h, L, _p(fx), _p(bx), int(own_scales), _p(bt), _p(et), _p(mo), C.byref(nr), C.byref(tr))
+        return dict(status=st, btot=bt, etot=et, mocc=mo, nregions=nr.value, triggered=tr.value)
 
     def nullsc(self, L):
         return np.float32(lib().p7ref_nullsc(self.h, L))

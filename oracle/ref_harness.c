@@ -219,6 +219,39 @@ int p7ref_fwdbck(void *vh, const uint8_t *dsq, int L, float *fsc, float *bsc, fl
   return st;
 }
 
+/* p7_DomainDecoding (impl_sse/decoding.c:166-200) on externally supplied specials, then the region walk of
+ * p7_domaindef_ByPosteriorHeuristics (p7_domaindef.c:412-487) WITHOUT the per-region rescoring: returns mocc/btot/etot
+ * [(L+1) each, optional], the number of regions the walk would open, and whether the rt1 trigger ever fired. */
+int p7ref_domain_decoding(void *vh, int L, const float *fxmx, const float *bxmx, int b_own_scales,
+                          float *btot, float *etot, float *mocc, int *nregions, int *triggered_any)
+{
+  P7REF *h = vh; int st, i, j, trig = FALSE, any = FALSE, nreg = 0;
+  ESL_RANDOMNESS *rng = esl_randomness_CreateFast(42);
+  P7_DOMAINDEF *ddef = p7_domaindef_Create(rng);
+  set_length(h, L); p7_omx_GrowTo(h->ox, h->om->M, 0, L); p7_omx_GrowTo(h->oxb, h->om->M, 0, L);
+  memcpy(h->ox->xmx,  fxmx, sizeof(float) * (size_t)(L+1) * p7X_NXCELLS);
+  memcpy(h->oxb->xmx, bxmx, sizeof(float) * (size_t)(L+1) * p7X_NXCELLS);
+  h->ox->M = h->oxb->M = h->om->M; h->ox->L = h->oxb->L = L;
+  h->ox->has_own_scales = TRUE; h->oxb->has_own_scales = b_own_scales;
+  p7_domaindef_GrowTo(ddef, L);
+  st = p7_DomainDecoding(h->om, h->ox, h->oxb, ddef);
+  if (btot) memcpy(btot, ddef->btot, sizeof(float) * (L+1));
+  if (etot) memcpy(etot, ddef->etot, sizeof(float) * (L+1));
+  if (mocc) memcpy(mocc, ddef->mocc, sizeof(float) * (L+1));
+  i = -1;
+  for (j = 1; j <= L; j++) {
+    if (! trig) {
+      if      (ddef->mocc[j] - (ddef->btot[j] - ddef->btot[j-1]) < ddef->rt2) i = j;
+      else if (i == -1)                                                       i = j;
+      if      (ddef->mocc[j] >= ddef->rt1) { trig = TRUE; any = TRUE; }
+    } else if (ddef->mocc[j] - (ddef->etot[j] - ddef->etot[j-1]) < ddef->rt2) { nreg++; i = -1; trig = FALSE; }
+  }
+  if (nregions) *nregions = nreg;
+  if (triggered_any) *triggered_any = any;
+  p7_domaindef_Destroy(ddef); esl_randomness_Destroy(rng);
+  return st;
+}
+
 float p7ref_nullsc(void *vh, int L)
 { P7REF *h = vh; float sc; p7_bg_SetLength(h->bg, L); p7_bg_NullOne(h->bg, NULL, L, &sc); return sc; }
 
