@@ -380,8 +380,16 @@ def main():
     hbm_achieved = alg_bytes / (ssv_avg_ms * 1e-3) / 1e9
     int_peak, fp32_peak, lds_peak = ctx.measure_peaks()
     ssv_gcups = cells / (ssv_avg_ms * 1e-3) / 1e9
+    # DRAM bytes per launch from the committed ncu --set full capture of this very launch (same profile and database size)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ssv_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("profile") == args.profile and tj.get("nseq") == args.nseq and tj.get("mean_len") == args.mean_len:
+            traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                "traffic": None, "kernel": "ssv_kernel", "avg_launch_ms": ssv_avg_ms,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/ssv_traffic.json)",
+                "algorithmic_bytes": alg_bytes, "kernel": "ssv_kernel", "avg_launch_ms": ssv_avg_ms,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "note": "the path moves 1 byte per M cells, so HBM is NOT the binding roof; see roofline_alu (integer issue)"}
     roofline_alu = {"bound": "int16x2-alu", "kernel": "ssv_kernel", "achieved": ssv_gcups * 2.0, "peak": int_peak,
@@ -394,10 +402,10 @@ def main():
     pipeline = None
     if not args.no_stages and world == 1:
         KINDS = (("ssv", engine.KERNEL_SSV), ("msvj", engine.KERNEL_MSVJ), ("bias", engine.KERNEL_BIAS), ("vit", engine.KERNEL_VIT),
-                 ("fwd", engine.KERNEL_FWD), ("bwd", engine.KERNEL_BWD))
-        STAGE_OF = {"ssv": "msv", "msvj": None, "bias": "bias", "vit": "vit", "fwd": "fwd", "bwd": "bwd"}
+                 ("fwd", engine.KERNEL_FWD), ("bwd", engine.KERNEL_BWD), ("region_trigger", engine.KERNEL_TRIG))
+        STAGE_OF = {"ssv": "msv", "msvj": None, "bias": "bias", "vit": "vit", "fwd": "fwd", "bwd": "bwd", "region_trigger": None}
 
-        def timed_pipeline(dbx, **kw):
+        def timed_pipeline(dbx, prof=prof, M=M, **kw):
             engine.pipeline_run(ctx, prof, dbx, **kw)                       # warm (allocator pool, per-L tables)
             ctx.set_timing(True); ctx.reset_timing()
             torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -434,6 +442,20 @@ def main():
         vsc(ctx, prof, sub_db)
         vms = ctx.kernel_time(engine.KERNEL_VIT)[0]; ctx.set_timing(False)
         pipeline["max_mode_slice"]["stage_kernel_rates"]["vit_gcups_all_targets"] = M * float(sub_lengths.astype(np.int64).sum()) / (vms * 1e-3) / 1e9
+        # BASELINE.json configs[3]: long-model stress, M=2000, --max (Forward+Backward on every target), with the region
+        # trigger of the domain-definition step on the device so that specials come back only where a domain is possible
+        p2000 = os.path.join(ROOT, "tests", "golden", "prof_synth_M2000.npz")
+        if os.path.exists(p2000):
+            op4 = OProfile.load(p2000); prof4 = engine.Profile(ctx, op4)
+            r4, wall4, km4, rates4 = timed_pipeline(sub_db, prof=prof4, M=op4.M, do_max=True, want_specials=True, region_trigger=True)
+            nflag = int((r4.survivors["region_flag"] == 1).sum())
+            pipeline["config4_slice"] = {
+                "workload": "long-model stress (BASELINE.json configs[3]): synth_M2000, --max on the first %d targets, region trigger "
+                            "on the device, specials returned for flagged targets only" % nsub,
+                "ms": wall4 * 1e3, "gcups_fwd_plus_bwd_wall": 2.0 * op4.M * r4.stage_residues["fwd"] / wall4 / 1e9,
+                "kernel_ms": km4, "stage_kernel_rates": rates4, "counters": [int(x) for x in r4.counters],
+                "region_flagged": nflag, "specials_floats_returned": int(r4.fwd_xmx.shape[0] * 2)}
+            prof4.close()
         sub_db.close()
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----

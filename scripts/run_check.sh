@@ -1,3 +1,7 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py > gpurun_out/bench_s4.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_s4.log | cut -c1-600
+timeout 900 python bench.py > gpurun_out/bench_s5.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_s5.log | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline']); p=d['pipeline']; print(p['ms'], p['kernel_ms']); print(json.dumps(p.get('config4_slice'), indent=1)); print(json.dumps(p.get('max_mode_slice'), indent=1))"
+T=/tmp/p7prof; mkdir -p $T
+timeout 900 ncu --set full --clock-control none -k regex:ssv_kernel -s 1 -c 1 -o $T/prof_ssv -f python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --no-stages > gpurun_out/bench_ncu_full.log 2>&1; echo "ncu full rc=$?"
+python profiles/summarize.py kernel $T/prof_ssv.ncu-rep > gpurun_out/ssv_kernel_full.txt; grep -E "dram__bytes|time_duration|t_sector_hit" gpurun_out/ssv_kernel_full.txt
