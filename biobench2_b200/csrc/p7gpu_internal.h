@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <memory>
 #include "../../include/p7gpu.h"
 
 namespace p7g {
@@ -108,6 +109,7 @@ struct p7gpu_ctx {
   void  *d_scratch = nullptr;  size_t d_scratch_bytes = 0;
   void  *h_pinned  = nullptr;  size_t h_pinned_bytes  = 0;
   void  *d_scratch2 = nullptr; size_t d_scratch2_bytes = 0;
+  std::shared_ptr<void> host_scratch;   // pipeline.cu: persistent host working arrays of the batched pipeline
 };
 
 struct p7gpu_profile {

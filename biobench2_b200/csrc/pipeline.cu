@@ -75,8 +75,26 @@ __global__ void gather_pass_kernel(const int32_t *pass, unsigned n, const float 
   idx64[j] = s; o_usc[j] = usc[s]; o_st[j] = st[s]; o_len[j] = len[s];
 }
 
-// sorted survivors of the MSV stage on the host
-struct MsvPass { std::vector<int64_t> idx; std::vector<float> usc; std::vector<int32_t> st, len; DevBuf d_idx64; };
+struct Cand {              // a target still alive after the bias stage
+  int64_t idx; int32_t L, msv_st, vit_st; float usc, nullsc, filtersc, vfsc, fwdsc, bcksc, ftot, btot; double P;
+};
+
+// Host-side working arrays of the batched pipeline, kept with the context: a database-sized search allocates tens of MB of
+// them per call, and fresh allocations of that size are mmap'ed and page-faulted every time (16 ms per call at 3e5 MSV
+// survivors before they were made persistent).
+struct HostScratch {
+  std::vector<int64_t> idx, vidx; std::vector<float> usc, filtersc, vsc; std::vector<int32_t> st, len, vst;
+  std::vector<double> P; std::vector<size_t> where; std::vector<Cand> cand;
+};
+static HostScratch &host_scratch(p7gpu_ctx *ctx)
+{
+  if (!ctx->host_scratch) ctx->host_scratch = std::shared_ptr<void>(new HostScratch(), [](void *p) { delete (HostScratch *) p; });
+  return *(HostScratch *) ctx->host_scratch.get();
+}
+
+// sorted survivors of the MSV stage on the host (arrays live in the context's HostScratch)
+struct MsvPass { std::vector<int64_t> &idx; std::vector<float> &usc; std::vector<int32_t> &st, &len; DevBuf d_idx64;
+                 explicit MsvPass(HostScratch &h) : idx(h.idx), usc(h.usc), st(h.st), len(h.len) {} };
 
 static int fetch_msv_pass(p7gpu_ctx *ctx, const p7gpu_seqdb *db, const float *d_usc, const int32_t *d_st,
                           int32_t *d_pass, unsigned npass, MsvPass *out)
@@ -112,10 +130,6 @@ static int upload_idx(p7gpu_ctx *ctx, const std::vector<int64_t> &idx, DevBuf *d
   return P7GPU_OK;
 }
 
-struct Cand {              // a target still alive after the bias stage
-  int64_t idx; int32_t L, msv_st, vit_st; float usc, nullsc, filtersc, vfsc, fwdsc, bcksc, ftot, btot; double P;
-};
-
 // Stages B..E on a resident database, given the MSV stage's outputs.
 static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db, const p7gpu_pipeline_opts *o,
                               const float *d_usc, const int32_t *d_st, int32_t *d_pass, unsigned npass, p7gpu_pipeline_result *res)
@@ -129,8 +143,11 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   res->counters.n_past_msv = npass;
   res->stage_nres[0] = (uint64_t) db->nres;
 
-  MsvPass mp;
+  Trace tr;
+  HostScratch &hs = host_scratch(ctx);
+  MsvPass mp(hs);
   P7G_CHECK(fetch_msv_pass(ctx, db, d_usc, d_st, d_pass, npass, &mp));
+  tr.mark("after_msv: fetch msv pass");
   if (o->stop_after_msv) {
     res->msv_pass.resize(npass);
     for (unsigned j = 0; j < npass; j++) res->msv_pass[j] = {mp.idx[j], mp.len[j], mp.st[j], mp.usc[j]};
@@ -138,7 +155,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   }
 
   // ---- B. bias filter (p7_pipeline.c:697-705) ----
-  std::vector<float> filtersc(npass);
+  std::vector<float> &filtersc = hs.filtersc; filtersc.resize(npass);
   if (do_bias && npass) {
     DevBuf d_f; P7G_CHECK(d_f.alloc(4 * (size_t) npass, st));
     for (unsigned j = 0; j < npass; j++) res->stage_nres[1] += (uint64_t) mp.len[j];
@@ -146,32 +163,34 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     P7G_CUDA(cudaMemcpyAsync(filtersc.data(), d_f.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaStreamSynchronize(st));
   }
-  std::vector<Cand> all(npass); std::vector<uint8_t> keep(npass);
+  tr.mark("after_msv: bias kernel");
+  std::vector<double> &Pv = hs.P; Pv.resize(npass);
+  const LenConst *hl = prof->h_len.data();
   parallel_for(npass, [&](size_t lo, size_t hi) {
-    for (size_t j = lo; j < hi; j++) {
-      Cand &c = all[j]; memset(&c, 0, sizeof(c));
-      c.idx = mp.idx[j]; c.L = mp.len[j]; c.msv_st = mp.st[j]; c.usc = mp.usc[j]; c.nullsc = prof->h_len[c.L].nullsc;
-      c.vit_st = -1; c.vfsc = NAN; c.fwdsc = NAN; c.bcksc = NAN;
-      c.filtersc = do_bias ? filtersc[j] : c.nullsc;
-      c.P = host_filter_pvalue_gumbel(c.usc, c.filtersc, ev[0], ev[1]);
-      keep[j] = !(do_bias && c.P > F1);
-    }
+    for (size_t j = lo; j < hi; j++)
+      Pv[j] = host_filter_pvalue_gumbel(mp.usc[j], do_bias ? filtersc[j] : hl[mp.len[j]].nullsc, ev[0], ev[1]);
   });
-  std::vector<Cand> cand; cand.reserve(npass);
-  for (unsigned j = 0; j < npass; j++) if (keep[j]) cand.push_back(all[j]);
-  all.clear(); all.shrink_to_fit();
+  std::vector<Cand> &cand = hs.cand; cand.clear();
+  for (unsigned j = 0; j < npass; j++) {
+    if (do_bias && Pv[j] > F1) continue;
+    Cand c;
+    c.idx = mp.idx[j]; c.L = mp.len[j]; c.msv_st = mp.st[j]; c.vit_st = -1; c.usc = mp.usc[j]; c.nullsc = hl[c.L].nullsc;
+    c.filtersc = do_bias ? filtersc[j] : c.nullsc; c.vfsc = NAN; c.fwdsc = NAN; c.bcksc = NAN; c.ftot = 0.f; c.btot = 0.f; c.P = Pv[j];
+    cand.push_back(c);
+  }
   res->counters.n_past_bias = cand.size();
+  tr.mark("after_msv: bias P-values");
 
   // ---- C. Viterbi filter for the candidates whose P still exceeds F2 (:716-723) ----
   {
-    std::vector<int64_t> vidx; std::vector<size_t> where;
+    std::vector<int64_t> &vidx = hs.vidx; std::vector<size_t> &where = hs.where; vidx.clear(); where.clear();
     for (size_t j = 0; j < cand.size(); j++) if (cand[j].P > F2) { vidx.push_back(cand[j].idx); where.push_back(j); res->stage_nres[2] += (uint64_t) cand[j].L; }
     if (!vidx.empty()) {
       DevBuf d_idx, d_sc, d_stt;
       P7G_CHECK(upload_idx(ctx, vidx, &d_idx));
       P7G_CHECK(d_sc.alloc(4 * vidx.size(), st)); P7G_CHECK(d_stt.alloc(4 * vidx.size(), st));
       P7G_CHECK(launch_vit(ctx, 0, prof, dbv, d_idx.as<int64_t>(), (int64_t) vidx.size(), d_sc.as<float>(), d_stt.as<int32_t>()));
-      std::vector<float> vsc(vidx.size()); std::vector<int32_t> vst(vidx.size());
+      std::vector<float> &vsc = hs.vsc; std::vector<int32_t> &vst = hs.vst; vsc.resize(vidx.size()); vst.resize(vidx.size());
       P7G_CUDA(cudaMemcpyAsync(vsc.data(), d_sc.p, 4 * vidx.size(), cudaMemcpyDeviceToHost, st));
       P7G_CUDA(cudaMemcpyAsync(vst.data(), d_stt.p, 4 * vidx.size(), cudaMemcpyDeviceToHost, st));
       P7G_CUDA(cudaStreamSynchronize(st));
@@ -188,6 +207,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     }
   }
   res->counters.n_past_vit = cand.size();
+  tr.mark("after_msv: viterbi stage");
 
   // ---- D + E. Forward parser, F3 test, Backward parser for the survivors (:727-735), in slices bounded by the
   //      size of the specials ((L+1)*6 floats per target and direction) ----
@@ -294,6 +314,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     }
     lo = hi;
   }
+  tr.mark("after_msv: forward/backward");
   return P7GPU_OK;
 }
 
@@ -474,6 +495,7 @@ int p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_se
     unsigned npass = 0;
     unsigned int *d_pass_count = ctx->lanes[0].counters + CTR_PASS_COUNT;
     unsigned int *d_nores_count = ctx->lanes[0].counters + CTR_NORES_COUNT;
+    Trace tr;
     auto body = [&]() -> int {
       const size_t nn = (size_t) std::max<int64_t>(n, 1);
       P7G_CHECK(d_sc.alloc(4 * nn, st)); P7G_CHECK(d_st.alloc(4 * nn, st)); P7G_CHECK(d_pass.alloc(4 * nn, st)); P7G_CHECK(d_nores.alloc(16 * nn, st));
@@ -482,7 +504,9 @@ int p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_se
                            d_pass.as<int32_t>(), d_pass_count));
       P7G_CHECK(launch_msv_j(ctx, 0, prof, db->view(), d_nores.as<int64_t>(), d_nores_count, n, d_sc.as<float>(), d_st.as<int32_t>(),
                              d_pass.as<int32_t>(), d_pass_count));
+      tr.mark("run: msv queued");
       P7G_CHECK(read_count(ctx, d_pass_count, &npass));
+      tr.mark("run: msv done");
       return pipeline_after_msv(ctx, prof, db, opts, d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), npass, res);
     };
     status = body();
