@@ -472,6 +472,7 @@ def main():
         def e2e_step():
             r = engine.pipeline_run_host(ctx, prof, hdb, F1=F1, stop_after_msv=True)
             e2e_out["survivors"] = len(r.msv_pass); e2e_out["counters"] = [int(x) for x in r.counters]
+            r.close()
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -482,7 +483,7 @@ def main():
         e2e = {"value": total_cells * args.e2e_steps / dt / 1e9, "unit": "GCUPS", "steps": args.e2e_steps,
                "h2d_bytes_per_step": int(nbytes + args.nseq * 12), "d2h_bytes_per_step": int(e2e_out["survivors"] * 24 + 4),
                "ms_per_step": dt / args.e2e_steps * 1e3, "survivors": e2e_out["survivors"], "counters": e2e_out["counters"],
-               "api": "p7gpu_pipeline_run_host(stop_after_msv): pinned host packed DB streamed in 8-96 MB chunks (each sorted longest-first on the device) under the "
+               "api": "p7gpu_pipeline_run_host(stop_after_msv): pinned host packed DB streamed in 16-256 MB chunks (database order; the last chunk longest-first) under the "
                       "SSV/MSV kernels; the MSV survivor records (index, L, status, score) come back to the host"}
 
     cpu_baseline = None

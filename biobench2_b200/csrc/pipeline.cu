@@ -19,6 +19,7 @@
 #include <thread>
 
 struct p7gpu_pipeline_result {
+  p7gpu_ctx *ctx = nullptr;                       // the MSV-survivor buffer goes back to this context's cache on destroy
   p7gpu_pipeline_counters counters;
   std::vector<p7gpu_survivor> survivors;
   std::vector<float> fwd_xmx, bck_xmx;
@@ -85,6 +86,7 @@ struct Cand {              // a target still alive after the bias stage
 struct HostScratch {
   std::vector<int64_t> idx, vidx; std::vector<float> usc, filtersc, vsc; std::vector<int32_t> st, len, vst;
   std::vector<double> P; std::vector<size_t> where; std::vector<Cand> cand;
+  std::vector<p7gpu_msv_survivor> msv_cache;
 };
 static HostScratch &host_scratch(p7gpu_ctx *ctx)
 {
@@ -149,8 +151,12 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   P7G_CHECK(fetch_msv_pass(ctx, db, d_usc, d_st, d_pass, npass, &mp));
   tr.mark("after_msv: fetch msv pass");
   if (o->stop_after_msv) {
+    res->ctx = ctx;
+    res->msv_pass.swap(hs.msv_cache);             // a buffer a previous result gave back: already mapped, no page faults
     res->msv_pass.resize(npass);
-    for (unsigned j = 0; j < npass; j++) res->msv_pass[j] = {mp.idx[j], mp.len[j], mp.st[j], mp.usc[j]};
+    parallel_for(npass, [&](size_t lo, size_t hi) {
+      for (size_t j = lo; j < hi; j++) res->msv_pass[j] = {mp.idx[j], mp.len[j], mp.st[j], mp.usc[j]};
+    });
     return P7GPU_OK;
   }
 
@@ -335,12 +341,15 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
 {
   if (nseq > 0x7fffffffLL) { set_error("stream: more than 2^31-1 targets per device"); return P7GPU_EINVAL; }
   Trace tr;
-  // ---- chunk plan: sizes grow from 8 MB (short exposed first copy) to 96 MB (few kernel tails) ----
+  // ---- chunk plan: 16 MB first (0.3 ms of exposed copy), then x4/3 up to 256 MB.  A chunk can only be computed once it
+  //      is copied completely, so while chunk c is in flight the GPU has chunk c-1 to work on: growth must stay below the
+  //      ratio of copy rate (55 GB/s measured) to SSV consumption rate (38 GB/s of residues at M=400), or the kernels
+  //      starve during the ramp (doubling lost 5 ms of a 96 ms pass) ----
   struct Chunk { int64_t s_lo, s_hi; };
   std::vector<Chunk> plan;
   int64_t max_chunk_seqs = 1;
   {
-    int64_t s = 0, bytes = (int64_t) 8 << 20;
+    int64_t s = 0, bytes = (int64_t) 16 << 20;
     while (s < nseq) {
       const int64_t lim = offsets[s] + bytes;
       int64_t lo = s + 1, hi = nseq;
@@ -348,7 +357,7 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
       plan.push_back({s, lo});
       max_chunk_seqs = std::max(max_chunk_seqs, lo - s);
       s = lo;
-      bytes = std::min<int64_t>(bytes * 2, (int64_t) 96 << 20);
+      bytes = std::min<int64_t>(bytes + bytes / 3, (int64_t) 256 << 20);
     }
   }
   cudaStream_t ms = ctx->stream, cs = ctx->copy_stream;
@@ -425,12 +434,18 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
     const int lane = 1 + (int) (c & 1);
     const Lane &ln = ctx->lanes[lane];
     S_CUDA(cudaStreamWaitEvent(ln.stream, ev, 0));
-    // work order of the chunk: longest target first, so the kernel's tail is short
-    iota_from_kernel<<<(unsigned) ((cn + 255) / 256), 256, 0, ln.stream>>>(d_iota[lane], (int32_t) s_lo, (int32_t) cn);
-    S_CUDA(cub::DeviceRadixSort::SortPairsDescending(d_sorttmp[lane], sort_tmp_bytes, d_len + s_lo, d_keys_out[lane],
-                                                     d_iota[lane], db->d_order + s_lo, (int) cn, 0, 32, ln.stream));
-    ctx->launches += 4;
-    DbView v; v.res = d_res; v.off = d_off; v.len = d_len; v.order = db->d_order + s_lo; v.first = s_lo; v.max_length = Lmax;
+    // Work order.  The persistent SSV grid of the previous chunk leaves a sort no SM until it ends, so a per-chunk sort is
+    // exposed at every chunk boundary (0.2 ms each); in database order the next chunk's CTAs fill the SMs as the previous
+    // kernel's CTAs retire, and the accesses to offsets/lengths/outputs are sequential.  Only the last chunk, whose tail
+    // nothing overlaps, is taken longest target first.
+    const bool sorted = (c + 1 == plan.size());
+    if (sorted) {
+      iota_from_kernel<<<(unsigned) ((cn + 255) / 256), 256, 0, ln.stream>>>(d_iota[lane], (int32_t) s_lo, (int32_t) cn);
+      S_CUDA(cub::DeviceRadixSort::SortPairsDescending(d_sorttmp[lane], sort_tmp_bytes, d_len + s_lo, d_keys_out[lane],
+                                                       d_iota[lane], db->d_order + s_lo, (int) cn, 0, 32, ln.stream));
+      ctx->launches += 4;
+    }
+    DbView v; v.res = d_res; v.off = d_off; v.len = d_len; v.order = sorted ? db->d_order + s_lo : nullptr; v.first = s_lo; v.max_length = Lmax;
     unsigned int *d_nores_count = ln.counters + CTR_NORES_COUNT;
     S_CHECK(launch_ssv(ctx, lane, prof, v, nullptr, cn, d_sc, d_st, d_nores[lane], d_nores_count, d_pass, d_pass_count));
     S_CHECK(launch_msv_j(ctx, lane, prof, v, d_nores[lane], d_nores_count, cn, d_sc, d_st, d_pass, d_pass_count));
@@ -604,6 +619,11 @@ const float *p7gpu_result_bck_xmx(const p7gpu_pipeline_result *res) { return res
 const uint64_t *p7gpu_result_stage_residues(const p7gpu_pipeline_result *res) { return res ? res->stage_nres : nullptr; }
 int64_t p7gpu_result_nmsvpass(const p7gpu_pipeline_result *res) { return res ? (int64_t) res->msv_pass.size() : 0; }
 const p7gpu_msv_survivor *p7gpu_result_msvpass(const p7gpu_pipeline_result *res) { return res ? res->msv_pass.data() : nullptr; }
-void p7gpu_result_destroy(p7gpu_pipeline_result *res) { delete res; }
+void p7gpu_result_destroy(p7gpu_pipeline_result *res)
+{
+  if (!res) return;
+  if (res->ctx && res->msv_pass.capacity() > host_scratch(res->ctx).msv_cache.capacity()) host_scratch(res->ctx).msv_cache.swap(res->msv_pass);
+  delete res;
+}
 
 }

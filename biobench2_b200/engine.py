@@ -354,37 +354,66 @@ def msvfilter_stream(ctx, prof, packed, F1=0.02, sc=None, st=None, want_pass=Tru
     return sc, st, (pl[:npass.value] if want_pass else None), db
 
 
+class _ResultHandle:
+    """Owns one p7gpu_pipeline_result; the arrays viewing its buffers keep it alive."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def destroy(self):
+        if self.h:
+            lib().p7gpu_result_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class _Owned(np.ndarray):
+    """ndarray view of library memory that keeps its owner alive (also through derived views, via .base)."""
+    _owner = None
+
+
+def _view(ptr, nbytes, dtype, owner):
+    raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(nbytes,))
+    a = raw.view(dtype).view(_Owned)
+    a._owner = owner
+    return a
+
+
 class PipelineResult:
-    """Host copy of a p7gpu_pipeline_result."""
+    """A p7gpu_pipeline_result.  The record arrays are views of the library's own buffers (no copy).  They stay valid while
+    they (or this object) are referenced, or until close(); all of it must end before the Context is closed."""
 
     def __init__(self, h):
         L = lib()
+        self._own = own = _ResultHandle(h)
         c = L.p7gpu_result_counters(h).contents
         self.counters = np.array([c.nseqs, c.nres, c.n_past_msv, c.n_past_bias, c.n_past_vit, c.n_past_fwd], np.uint64)
         sr = L.p7gpu_result_stage_residues(h)
         self.stage_residues = {k: int(sr[i]) for i, k in enumerate(("msv", "bias", "vit", "fwd", "bwd"))}
-        n = L.p7gpu_result_nsurvivors(h)
-        sv = L.p7gpu_result_survivors(h)
-        if n:                                  # one structured array (a --max run returns millions of records)
-            raw = np.ctypeslib.as_array(C.cast(sv, C.POINTER(C.c_uint8)), shape=(n * C.sizeof(Survivor),))
-            self.survivors = raw.view(SURVIVOR_NP).copy()
-        else:
-            self.survivors = np.zeros(0, SURVIVOR_NP)
+        n = L.p7gpu_result_nsurvivors(h)      # one structured array (a --max run returns millions of records)
+        self.survivors = _view(L.p7gpu_result_survivors(h), n * C.sizeof(Survivor), SURVIVOR_NP, own) if n else np.zeros(0, SURVIVOR_NP)
         have = self.survivors["xmx_offset"] >= 0
         ext = int((self.survivors["xmx_offset"][have] + (self.survivors["L"][have].astype(np.int64) + 1) * 6).max()) if have.any() else 0
         if ext:
-            self.fwd_xmx = np.ctypeslib.as_array(L.p7gpu_result_fwd_xmx(h), shape=(ext,)).copy()
-            self.bck_xmx = np.ctypeslib.as_array(L.p7gpu_result_bck_xmx(h), shape=(ext,)).copy()
+            self.fwd_xmx = _view(L.p7gpu_result_fwd_xmx(h), ext * 4, np.float32, own)
+            self.bck_xmx = _view(L.p7gpu_result_bck_xmx(h), ext * 4, np.float32, own)
         else:
             self.fwd_xmx = self.bck_xmx = np.zeros(0, np.float32)
         m = L.p7gpu_result_nmsvpass(h)
-        if m:
-            raw = np.ctypeslib.as_array(C.cast(L.p7gpu_result_msvpass(h), C.POINTER(C.c_uint8)), shape=(m * C.sizeof(MsvSurvivor),))
-            rec = raw.view(np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")]))
-            self.msv_pass = rec.copy()
-        else:
-            self.msv_pass = np.zeros(0, np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")]))
-        L.p7gpu_result_destroy(h)
+        self.msv_pass = _view(L.p7gpu_result_msvpass(h), m * C.sizeof(MsvSurvivor), MSV_NP, own) if m else np.zeros(0, MSV_NP)
+
+    def close(self):
+        """Release the library buffers now (the arrays of this result must not be used afterwards)."""
+        self.survivors = self.fwd_xmx = self.bck_xmx = self.msv_pass = None
+        self._own.destroy()
+
+
+MSV_NP = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")])
 
 
 def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger=False):
