@@ -21,8 +21,12 @@ DiagGeom diag_geom(int M)
 {
   DiagGeom g; g.M = M;
   int Q = (M + 1 + 63) / 64;          // 64*Q >= M+1: at least one pad column
-  if ((Q & 1) == 0) Q++;              // odd lane stride -> conflict-free LDS.32
-  g.Q = Q; g.P = 64 * Q; g.rowWords = g.P + DIAG_CHUNK + Q;
+  // odd Q: lane stride Q words is conflict-free by itself.  Even Q <= MAX_EVEN_Q: lanes take consecutive words and the
+  // registers of a lane are 32 words apart (conflict-free for any Q, at the price of a longer wrap-free row).  Larger even
+  // Q are rounded up to odd (<= 6% of pad columns there).
+  if ((Q & 1) == 0 && Q > MAX_EVEN_Q) Q++;
+  g.Q = Q; g.P = 64 * Q;
+  g.rowWords = (Q & 1) ? g.P + DIAG_CHUNK + Q : g.P + DIAG_CHUNK + 32 * (Q - 1) + 1;
   return g;
 }
 

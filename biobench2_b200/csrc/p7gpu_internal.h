@@ -27,15 +27,17 @@ void set_error(const char *fmt, ...);
 // A warp holds 64*Q slots: lane l, register q, half h  <->  diagonal start column l*Q + q + h*32*Q.
 // At DP row i the slot sits on column (start + i) mod P, P = 64*Q >= M+1; columns >= M are pad columns
 // whose gain is PADGAIN, which resets the running diagonal to the floor before it re-enters at k=1.
-// Q is odd so that the 32 lanes of one LDS.32 (stride Q words) hit 32 distinct banks.
+// Q odd: lane stride Q words, so the 32 lanes of one LDS.32 hit 32 distinct banks.  Q even (<= MAX_EVEN_Q): start column
+// l + 32*q instead (lane stride 1, register stride 32): conflict-free for any Q; the wrap-free row is 32*(Q-1) words longer.
 constexpr int DIAG_CHUNK   = 16;      // DP rows per unrolled chunk = one 16-byte residue load
 constexpr int PADRES       = 29;      // table row used for masked (out-of-sequence) rows: all PADGAIN
 constexpr int NTABROWS     = 30;      // Kp + 1
 constexpr int SSV_PADGAIN  = -20000;  // int16; |v| stays < 2^15 (overflow argument)
 constexpr int MAX_Q        = 65;      // M <= 64*65-1 = 4159
+constexpr int MAX_EVEN_Q   = 14;      // even Q (consecutive-lane layout) up to here
 
 struct DiagGeom {
-  int M, Q, P, rowWords;              // rowWords = P + DIAG_CHUNK + Q  (wrap-free reads inside one chunk)
+  int M, Q, P, rowWords;              // rowWords = P + DIAG_CHUNK + Q (odd Q) or P + DIAG_CHUNK + 32*(Q-1) + 1 (even Q): wrap-free reads inside one chunk
   size_t tableBytes() const { return (size_t) NTABROWS * rowWords * 4; }
 };
 DiagGeom diag_geom(int M);

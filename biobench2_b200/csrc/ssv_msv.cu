@@ -18,8 +18,10 @@ namespace p7g {
 // canonical residues + the pad row in shared memory, the rare degenerate codes read from global (warp-uniform branch).
 constexpr int SSV_GLOBAL = 0, SSV_SMEM = 1, SSV_COMPACT = 2;
 constexpr int SSV_COMPACT_ROWS = 21;
-constexpr int ssv_mode_for(int Q)    { return Q <= 27 ? SSV_SMEM : (Q <= 41 ? SSV_COMPACT : SSV_GLOBAL); }
-constexpr int ssv_threads_for(int Q) { return Q <= 13 ? 256 : 512; }      // big tables leave room for one CTA per SM only
+__host__ __device__ constexpr int ssv_lane_stride(int Q)  { return (Q & 1) ? Q : 1; }          // words between the slots of neighbouring lanes
+__host__ __device__ constexpr int ssv_slot_stride(int Q)  { return (Q & 1) ? 1 : 32; }         // words between the registers of one lane
+constexpr int ssv_mode_for(int Q)    { return (Q & 1) ? (Q <= 27 ? SSV_SMEM : (Q <= 41 ? SSV_COMPACT : SSV_GLOBAL)) : (Q <= 8 ? SSV_SMEM : SSV_COMPACT); }
+constexpr int ssv_threads_for(int Q) { return (Q & 1) ? (Q <= 13 ? 256 : 512) : (Q <= 4 ? 256 : 512); }   // big tables leave room for few CTAs per SM
 constexpr int MSVJ_THREADS = 128;
 
 struct SsvParams {
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
 #pragma unroll
       for (int q = 0; q < Q; q++) v[q] = 0u;
       uint32_t xE = 0u;
-      int c = lane * Q;
+      int c = lane * ssv_lane_stride(Q);
       const long long end = o + L;
       long long pos = o & ~15LL;
       uint4 cur = ldg_res16(p.res + pos);
@@ -152,11 +154,11 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
             const uint32_t xr = (MODE == SSV_COMPACT) ? min(x, 20u) : x;
             const uint32_t a = xr * rowBytes + cbase;
 #pragma unroll
-            for (int q = 0; q < Q; q++) asm("ld.shared.u32 %0, [%1];" : "=r"(g[q]) : "r"(a + 4u * (uint32_t) (r + q)));
+            for (int q = 0; q < Q; q++) asm("ld.shared.u32 %0, [%1];" : "=r"(g[q]) : "r"(a + 4u * (uint32_t) (r + q * ssv_slot_stride(Q))));
           } else {
             const uint32_t *rowp = p.tab + x * rowWords + c + r;
 #pragma unroll
-            for (int q = 0; q < Q; q++) g[q] = __ldg(rowp + q);
+            for (int q = 0; q < Q; q++) g[q] = __ldg(rowp + q * ssv_slot_stride(Q));
           }
           // v >= 0 always, so max(v+g, g, 0) == max(v+g, 0): the .RELU form needs no zero operand register
 #pragma unroll
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(MSVJ_THREADS) msvj_kernel(const MsvjParams p)
     for (int q = 0; q < Q; q++) v[q] = 0u;
     int xJ = 0;
     int xB = p.s.base_b - tjbm; if (xB < 0) xB = 0;
-    int c = lane * Q;
+    int c = lane * ssv_lane_stride(Q);
     int status = P7GPU_OK;
     for (int i = 0; i < L; i++) {
       const uint32_t x = __ldg(p.res + o + i);
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(MSVJ_THREADS) msvj_kernel(const MsvjParams p)
       for (int q = 0; q < Q; q++) {
         uint32_t a = __vmaxs2(v[q], xB2);                      // max(M(i-1,k-1), xB)
         a = __viaddmin_s16x2(a, bias2, c255);                  // adds_epu8(., bias)
-        { const uint32_t g = __ldg(rowp + q); v[q] = __viaddmax_s16x2_relu(a, g, g); }   // subs_epu8(., rbv); a >= 0
+        { const uint32_t g = __ldg(rowp + q * ssv_slot_stride(Q)); v[q] = __viaddmax_s16x2_relu(a, g, g); }   // subs_epu8(., rbv); a >= 0
         xEv = __vmaxs2(xEv, v[q]);
       }
       c += 1; if (c >= P) c -= P;
@@ -303,6 +305,7 @@ static int launch_ssv_pick(p7gpu_ctx *ctx, cudaStream_t stream, const SsvParams 
 }
 
 #define P7G_ODD_Q_CASES(X) \
+  X(2) X(4) X(6) X(8) X(10) X(12) X(14) \
   X(1) X(3) X(5) X(7) X(9) X(11) X(13) X(15) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31) X(33) \
   X(35) X(37) X(39) X(41) X(43) X(45) X(47) X(49) X(51) X(53) X(55) X(57) X(59) X(61) X(63) X(65)
 
