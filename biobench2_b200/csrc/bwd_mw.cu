@@ -158,27 +158,32 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
       }
       float Yin = __shfl_down_sync(0xffffffffu, P, 1);                // Dz of the next lane's first node when nothing enters the warp
       if (lane == 31) Yin = 0.f;
-      const int par = i & 1;
-      if (lane == 0) {
-        float *pub = s_pub[par][w];
-        pub[0] = P; pub[1] = S;
-        pub[2] = mp[0] + rMD[0] * (dp[1] + s_pq[1][g].x * Yin);       // Ma: M of my first node without its xE and Yz_w terms
-      }
-      __syncthreads();                                                // ---- the row's only barrier ----
-      xB = 0.f;
+      float Ymine = 0.f, Ynext = 0.f;
+      if (W == 1) {                                                   // one warp: lane 0 holds the B sum, nothing enters
+        xB = __shfl_sync(0xffffffffu, S, 0);
+      } else {
+        const int par = i & 1;
+        if (lane == 0) {
+          float *pub = s_pub[par][w];
+          pub[0] = P; pub[1] = S;
+          pub[2] = mp[0] + rMD[0] * (dp[1] + s_pq[1][g].x * Yin);     // Ma: M of my first node without its xE and Yz_w terms
+        }
+        __syncthreads();                                              // ---- the row's only barrier ----
+        xB = 0.f;
 #pragma unroll
-      for (int v = 0; v < W; v++) xB += s_pub[par][v][1];
+        for (int v = 0; v < W; v++) xB += s_pub[par][v][1];
+        float Yz = 0.f;                                               // Yz_v = Dz entering warp v from above
+#pragma unroll
+        for (int v = W - 1; v >= 0; v--) {
+          if (v == w) Ymine = Yz;
+          if (v == w + 1) Ynext = Yz;
+          Yz = s_pub[par][v][0] + s_wB[v] * Yz;
+        }
+      }
       xC = xC * ploop;
       xJ = (xB * pmove) + (xJ * ploop);
       xN = (xB * pmove) + (xN * ploop);
       xE = (xC * p.s.xf_E_move) + (xJ * p.s.xf_E_loop);
-      float Yz = 0.f, Ymine = 0.f, Ynext = 0.f;                       // Yz_v = Dz entering warp v from above
-#pragma unroll
-      for (int v = W - 1; v >= 0; v--) {
-        if (v == w) Ymine = Yz;
-        if (v == w + 1) Ynext = Yz;
-        Yz = s_pub[par][v][0] + s_wB[v] * Yz;
-      }
       Yin = Yin + Bexc * Ymine;
       {
         float carry = Yin + xE * Qn;                                  // full D of the node behind this lane's last node
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
           carry = dp[j];
         }
       }
-      if (w + 1 < W) nm = (s_pub[par][w + 1][2] + xE * s_wMq[w + 1]) + s_wMk[w + 1] * Ynext;
+      if (w + 1 < W) nm = (s_pub[i & 1][w + 1][2] + xE * s_wMq[w + 1]) + s_wMk[w + 1] * Ynext;
       if (xB > 1.0e16f) own_scales = true;                            // :661
       float scale;
       if (own_scales) scale = (xB > 1.0e4f) ? xB : 1.0f;

@@ -108,25 +108,31 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
       }
       float Z = __shfl_up_sync(0xffffffffu, P, 1);                    // enters this lane when nothing enters the warp
       if (lane == 0) Z = 0.f;
-      const int par = i & 1;
-      if (lane == 31) {
-        float *pub = s_pub[par][w];
-        pub[0] = P; pub[1] = U; pub[2] = mp[C - 1]; pub[3] = ip[C - 1]; pub[4] = dp[C - 1] + Z * s_pp[C - 1][g];
-      }
-      __syncthreads();                                                // ---- the row's only barrier ----
-      float X = 0.f, Xmine = 0.f, Xprev = 0.f;
-      xE = 0.f;
+      if (W == 1) {                                                   // one warp: lane 31 holds the row sum, nothing enters
+        xE = __shfl_sync(0xffffffffu, U, 31);
 #pragma unroll
-      for (int v = 0; v < W; v++) {                                   // X_v = what enters warp v's first node
-        if (v == w) Xmine = X;
-        if (v + 1 == w) Xprev = X;
-        xE += s_pub[par][v][1] + s_wV[v] * X;
-        X = s_pub[par][v][0] + s_wB[v] * X;
-      }
-      Z = Z + Bexc * Xmine;
+        for (int j = 0; j < C; j++) dp[j] = dp[j] + Z * s_pp[j][g];
+      } else {
+        const int par = i & 1;
+        if (lane == 31) {
+          float *pub = s_pub[par][w];
+          pub[0] = P; pub[1] = U; pub[2] = mp[C - 1]; pub[3] = ip[C - 1]; pub[4] = dp[C - 1] + Z * s_pp[C - 1][g];
+        }
+        __syncthreads();                                              // ---- the row's only barrier ----
+        float X = 0.f, Xmine = 0.f, Xprev = 0.f;
+        xE = 0.f;
 #pragma unroll
-      for (int j = 0; j < C; j++) dp[j] = dp[j] + Z * s_pp[j][g];
-      if (w > 0) { const float *pub = s_pub[par][w - 1]; bm = pub[2]; bi = pub[3]; bd = pub[4] + s_wK[w - 1] * Xprev; }
+        for (int v = 0; v < W; v++) {                                 // X_v = what enters warp v's first node
+          if (v == w) Xmine = X;
+          if (v + 1 == w) Xprev = X;
+          xE += s_pub[par][v][1] + s_wV[v] * X;
+          X = s_pub[par][v][0] + s_wB[v] * X;
+        }
+        Z = Z + Bexc * Xmine;
+#pragma unroll
+        for (int j = 0; j < C; j++) dp[j] = dp[j] + Z * s_pp[j][g];
+        if (w > 0) { const float *pub = s_pub[par][w - 1]; bm = pub[2]; bi = pub[3]; bd = pub[4] + s_wK[w - 1] * Xprev; }
+      }
       xN = xN * ploop;                                                // :413-416
       xC = (xC * ploop) + (xE * p.s.xf_E_move);
       xJ = (xJ * ploop) + (xE * p.s.xf_E_loop);

@@ -1,5 +1,7 @@
-// fwdbwd_mw.cuh — one CTA per target for long models: p7_ForwardParser / p7_BackwardParser
-// (HMMER/src/impl_sse/fwdback.c:257-465 and :469-735, do_full = 0) with the model split over W warps.
+// fwdbwd_mw.cuh — one CTA of W warps per target: p7_ForwardParser / p7_BackwardParser
+// (HMMER/src/impl_sse/fwdback.c:257-465 and :469-735, do_full = 0) with the model split over W warps (W = 1 up to M = 512).
+// These are the production kernels for every model length; fwdbwd.cu keeps the first-generation one-warp kernels as a
+// cross-check (ctx option "fb_one_warp").
 //
 // The one-warp kernels of fwdbwd.cu keep C = ceil(M/32) cells per lane; beyond C = 16 (M > 512) their per-node
 // transition vectors no longer fit in registers and the tables no longer fit in shared memory, so every cell costs
@@ -60,6 +62,7 @@ __device__ __forceinline__ bool mw_next_target(const DpCommon &c, long long *sh,
 
 // (cells per lane C, warps per CTA W) instances; G = 32*W is a compile-time constant so that table loads have immediate offsets
 #define P7G_MW_CASES(X) \
+  X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(7, 1) X(8, 1) X(9, 1) X(10, 1) X(11, 1) X(12, 1) X(13, 1) X(14, 1) X(15, 1) X(16, 1) \
   X(5, 2) X(6, 2) X(7, 2) X(8, 2) X(9, 2) X(10, 2) X(11, 2) X(12, 2) X(13, 2) X(14, 2) X(15, 2) X(16, 2) \
   X(9, 4) X(10, 4) X(11, 4) X(12, 4) X(13, 4) X(14, 4) X(15, 4) X(16, 4) \
   X(9, 8) X(10, 8) X(11, 8) X(12, 8) X(13, 8) X(14, 8) \

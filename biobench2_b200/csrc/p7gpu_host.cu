@@ -162,15 +162,17 @@ int dp_cells_per_lane(int M)
 }
 
 // CTA-per-target geometry of the long-model Forward/Backward kernels (fwdbwd_mw.cuh): W warps x 32 lanes x C cells >= M.
-// Instances exist for W = 2 (5 <= C <= 16), W = 4 (9 <= C <= 16), W = 8 (9 <= C <= 14), W = 12 (10 <= C <= 11).  Environment (tuning and tests
-// only): P7GPU_MW_MINM = smallest M that uses these kernels (default 513), P7GPU_MW_CMAX = upper bound on C when choosing W.
+// Instances exist for W = 1 (2 <= C <= 16), W = 2 (5 <= C <= 16), W = 4 (9 <= C <= 16), W = 8 (9 <= C <= 14), W = 12 (10 <= C <= 11);
+// the smallest W that fits is used (W = 1 up to M = 512).  Environment (tuning and tests only): P7GPU_MW_MINM = smallest M that
+// uses these kernels (default 1: all models; below it the first-generation one-warp kernels of fwdbwd.cu run),
+// P7GPU_MW_CMAX = upper bound on C when choosing W.
 bool mw_geometry(int M, int *C, int *W)
 {
-  static const int ws[4] = {2, 4, 8, 12}, cmax[4] = {16, 16, 14, 11}, cmin[4] = {5, 9, 9, 10};
+  static const int ws[5] = {1, 2, 4, 8, 12}, cmax[5] = {16, 16, 16, 14, 11}, cmin[5] = {2, 5, 9, 9, 10};
   const char *e1 = getenv("P7GPU_MW_MINM"), *e2 = getenv("P7GPU_MW_CMAX");
-  const int minM = e1 ? atoi(e1) : 513, cap = e2 ? atoi(e2) : 0;
+  const int minM = e1 ? atoi(e1) : 1, cap = e2 ? atoi(e2) : 0;
   if (M < minM) return false;
-  for (int t = 0; t < 4; t++) {
+  for (int t = 0; t < 5; t++) {
     int cm = cmax[t]; if (cap > 0 && cap < cm) cm = cap;
     const int c = (M + 32 * ws[t] - 1) / (32 * ws[t]);
     if (c > cm) continue;
