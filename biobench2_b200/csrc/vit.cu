@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(DP_THREADS) vitp_kernel(const VitpParams p)
     uint32_t cur = __ldg(wp), nxt = __ldg(wp + 1);
     wp += 2;
     if (!redo)
+#pragma unroll (TREG ? 2 : 1)
     for (int i = 0; i < L; i++) {
       const uint32_t x = (cur >> sh) & 0xffu;
       sh += 8;
