@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
     if (w + 1 < W) nm = s_first[w + 1];
 
     // ---- rows L-1 .. 1 (:566-692) ----
-#pragma unroll (W == 1 && C >= 5 ? 2 : 1)
+#pragma unroll (C >= 5 ? 2 : 1)
     for (int i = L - 1; i >= 1; i--) {
       const float fscale = frow[(size_t) i * 6 + 5];
       // e[j] <- M(i+1,k) * e_k(x_{i+1})

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
       for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
     }
 
-#pragma unroll (W == 1 && C >= 5 ? 2 : 1)
+#pragma unroll (C >= 5 ? 2 : 1)
     for (int i = 1; i <= L; i++) {
       float pm = __shfl_up_sync(0xffffffffu, mp[C - 1], 1);
       float pi = __shfl_up_sync(0xffffffffu, ip[C - 1], 1);
