@@ -531,6 +531,25 @@ int p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_se
   return P7GPU_OK;
 }
 
+// Many profiles against one resident database: the outer loop over queries of hmmsearch.c:471-560 (for hmmscan, the roles of
+// query and target database swapped, the loop over profiles of hmmscan.c) with the per-query rewind and re-read of the
+// sequence file (hmmsearch.c:480-487) gone — the database stays in HBM, each profile costs its tables (<= 350 KB) and one
+// per-length constant table.
+int p7gpu_pipeline_run_many(p7gpu_ctx *ctx, const p7gpu_profile *const *profs, int64_t nprof, const p7gpu_seqdb *db,
+                            const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res)
+{
+  if (!ctx || !profs || nprof < 0 || !db || !opts || !ret_res) return P7GPU_EINVAL;
+  for (int64_t i = 0; i < nprof; i++) ret_res[i] = nullptr;
+  for (int64_t i = 0; i < nprof; i++) {
+    int st = profs[i] ? p7gpu_pipeline_run(ctx, profs[i], db, opts, &ret_res[i]) : P7GPU_EINVAL;
+    if (st != P7GPU_OK) {
+      for (int64_t j = 0; j < i; j++) { p7gpu_result_destroy(ret_res[j]); ret_res[j] = nullptr; }
+      return st;
+    }
+  }
+  return P7GPU_OK;
+}
+
 int p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
                             const int64_t *offsets, const int32_t *lengths, int64_t nseq,
                             const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res)

@@ -251,6 +251,10 @@ typedef struct p7gpu_pipeline_result p7gpu_pipeline_result;
 
 int  p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
                         const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+/* many profiles against one resident database (BASELINE config 5, hmmscan-style batch): the query loop of
+ * hmmsearch.c:471-560 without the per-query rewind and re-read of the sequence file (:480-487).  ret_res: nprof slots. */
+int  p7gpu_pipeline_run_many(p7gpu_ctx *ctx, const p7gpu_profile *const *profs, int64_t nprof, const p7gpu_seqdb *db,
+                             const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
 /* same for a HOST packed database: the upload is streamed under the MSV stage (p7gpu_msvfilter_stream) */
 int  p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
                              const int64_t *offsets, const int32_t *lengths, int64_t nseq,

@@ -187,6 +187,30 @@ def test_many_profiles_one_resident_database(ctx):
     db.close()
 
 
+def test_pipeline_run_many_equals_one_call_per_profile(ctx):
+    """p7gpu_pipeline_run_many (hmmscan-style batch, BASELINE config 5) against one p7gpu_pipeline_run per profile, on the
+    committed scan profiles (tests/golden/scan, M = 100..800)."""
+    import glob
+    from biobench2_b200.oprofile import OProfile
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "scan", "prof_scan_M*.npz")))
+    assert len(paths) >= 8
+    hdb = seqdb.synth_db(6000, mean=300, seed=77, degenerate_frac=0.003)
+    db = engine.SeqDB.upload(ctx, hdb)
+    profs = [engine.Profile(ctx, OProfile.load(p)) for p in paths]
+    many = engine.pipeline_run_many(ctx, profs, db, want_specials=False)
+    npast = 0
+    for prof, r in zip(profs, many):
+        one = engine.pipeline_run(ctx, prof, db, want_specials=False)
+        assert list(one.counters) == list(r.counters)
+        assert np.array_equal(one.survivors["seqidx"], r.survivors["seqidx"])
+        assert np.array_equal(bits(one.survivors["fwdsc"]), bits(r.survivors["fwdsc"]))
+        npast += int(r.counters[2])
+    assert npast > 0
+    for p in profs:
+        p.close()
+    db.close()
+
+
 def test_unsupported_model_length_is_rejected(ctx):
     """M beyond the slot geometry (64*65-1 = 4159 nodes) must fail loudly, not silently mis-score."""
     import ctypes
