@@ -276,6 +276,33 @@ void                           p7gpu_result_destroy  (p7gpu_pipeline_result *res
 float  p7gpu_nullsc(int L);
 double p7gpu_msv_pvalue(float usc, float nullsc_or_filtersc, float mmu, float mlambda);
 
+/* ------------------------------------------------------------------------------------------------
+ * 8. The packed on-disk target database.  Replaces, on the search path, esl_sqfile_OpenDigital +
+ *    esl_sqio_ReadBlock (easel/esl_sqio_ascii.c:1466-1500: one reader thread, text parsed again for every query);
+ *    the reference's own precedents for a pre-digitised database are src/cachedb.h and src/makehmmerdb.c.
+ *    p7gpu_dbfile_from_fasta digitises a FASTA file once, with `nthreads` host threads (0 = all), exactly as easel does
+ *    (amino alphabet esl_alphabet.c:269-296; FASTA input map and header rules esl_sqio_ascii.c:2952-3056; the same
+ *    error texts in p7gpu_last_error()), into: residues[nbytes] (dsq bytes back to back, one 255 sentinel before the
+ *    first and after every target), offsets[nseq] int64, lengths[nseq] int32, names and descriptions.  A search maps the
+ *    file and streams it: p7gpu_pipeline_run_file == p7gpu_pipeline_run_host on the mapped arrays.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct p7gpu_dbfile p7gpu_dbfile;
+int            p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nthreads, int64_t *ret_nseq, int64_t *ret_nres);
+int            p7gpu_dbfile_open      (const char *path, p7gpu_dbfile **ret_db);
+void           p7gpu_dbfile_close     (p7gpu_dbfile *db);
+int64_t        p7gpu_dbfile_nseq      (const p7gpu_dbfile *db);
+int64_t        p7gpu_dbfile_nres      (const p7gpu_dbfile *db);
+int64_t        p7gpu_dbfile_nbytes    (const p7gpu_dbfile *db);
+int32_t        p7gpu_dbfile_maxlength (const p7gpu_dbfile *db);
+const uint8_t *p7gpu_dbfile_residues  (const p7gpu_dbfile *db);
+const int64_t *p7gpu_dbfile_offsets   (const p7gpu_dbfile *db);
+const int32_t *p7gpu_dbfile_lengths   (const p7gpu_dbfile *db);
+const char    *p7gpu_dbfile_name      (const p7gpu_dbfile *db, int64_t s);     /* ESL_SQ.name */
+const char    *p7gpu_dbfile_desc      (const p7gpu_dbfile *db, int64_t s);     /* ESL_SQ.desc */
+int            p7gpu_dbfile_pin       (p7gpu_dbfile *db);                      /* page-lock the mapping (full-rate H2D) */
+int            p7gpu_pipeline_run_file(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_dbfile *db,
+                                       const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+
 #ifdef __cplusplus
 }
 #endif
