@@ -137,6 +137,7 @@ struct p7gpu_dbfile {
   void *map = nullptr; size_t map_bytes = 0; int fd = -1;
   const Header *h = nullptr;
   bool pinned = false;
+  uint8_t *p_res = nullptr; int64_t *p_off = nullptr; int32_t *p_len = nullptr;   // page-locked copies (p7gpu_dbfile_pin)
 };
 
 using namespace p7g;
@@ -252,7 +253,9 @@ int p7gpu_dbfile_open(const char *path, p7gpu_dbfile **ret)
 void p7gpu_dbfile_close(p7gpu_dbfile *d)
 {
   if (!d) return;
-  if (d->pinned) cudaHostUnregister(d->map);
+  if (d->p_res) cudaFreeHost(d->p_res);
+  if (d->p_off) cudaFreeHost(d->p_off);
+  if (d->p_len) cudaFreeHost(d->p_len);
   if (d->map) munmap(d->map, d->map_bytes);
   if (d->fd >= 0) close(d->fd);
   delete d;
@@ -262,9 +265,9 @@ int64_t        p7gpu_dbfile_nseq     (const p7gpu_dbfile *d) { return d ? (int64
 int64_t        p7gpu_dbfile_nres     (const p7gpu_dbfile *d) { return d ? (int64_t) d->h->nres : 0; }
 int64_t        p7gpu_dbfile_nbytes   (const p7gpu_dbfile *d) { return d ? (int64_t) d->h->nbytes : 0; }
 int32_t        p7gpu_dbfile_maxlength(const p7gpu_dbfile *d) { return d ? d->h->max_length : 0; }
-const uint8_t *p7gpu_dbfile_residues (const p7gpu_dbfile *d) { return d ? (const uint8_t *) d->map + d->h->off_residues : nullptr; }
-const int64_t *p7gpu_dbfile_offsets  (const p7gpu_dbfile *d) { return d ? (const int64_t *) ((const char *) d->map + d->h->off_offsets) : nullptr; }
-const int32_t *p7gpu_dbfile_lengths  (const p7gpu_dbfile *d) { return d ? (const int32_t *) ((const char *) d->map + d->h->off_lengths) : nullptr; }
+const uint8_t *p7gpu_dbfile_residues (const p7gpu_dbfile *d) { return !d ? nullptr : d->pinned ? d->p_res : (const uint8_t *) d->map + d->h->off_residues; }
+const int64_t *p7gpu_dbfile_offsets  (const p7gpu_dbfile *d) { return !d ? nullptr : d->pinned ? d->p_off : (const int64_t *) ((const char *) d->map + d->h->off_offsets); }
+const int32_t *p7gpu_dbfile_lengths  (const p7gpu_dbfile *d) { return !d ? nullptr : d->pinned ? d->p_len : (const int32_t *) ((const char *) d->map + d->h->off_lengths); }
 const char *p7gpu_dbfile_name(const p7gpu_dbfile *d, int64_t s)
 {
   if (!d || s < 0 || (uint64_t) s >= d->h->nseq) return nullptr;
@@ -277,13 +280,24 @@ const char *p7gpu_dbfile_desc(const p7gpu_dbfile *d, int64_t s)
   return nm ? nm + strlen(nm) + 1 : nullptr;
 }
 
-// page-lock the mapping so that the streamed upload runs at full PCIe rate (optional; costs a page walk once per open)
+// Load the database into page-locked host memory so that the streamed upload runs at full PCIe rate (optional, once per open;
+// a read-only file mapping cannot be registered with the driver, so this is a copy, made by all host threads).
 int p7gpu_dbfile_pin(p7gpu_dbfile *d)
 {
   if (!d) return P7GPU_EINVAL;
   if (d->pinned) return P7GPU_OK;
-  madvise(d->map, d->map_bytes, MADV_WILLNEED);
-  P7G_CUDA(cudaHostRegister(d->map, d->map_bytes, cudaHostRegisterReadOnly | cudaHostRegisterPortable));
+  const size_t nb = (size_t) d->h->nbytes, ns = (size_t) d->h->nseq;
+  P7G_CUDA(cudaHostAlloc((void **) &d->p_res, std::max<size_t>(nb, 1), cudaHostAllocPortable));
+  P7G_CUDA(cudaHostAlloc((void **) &d->p_off, std::max<size_t>(8 * ns, 8), cudaHostAllocPortable));
+  P7G_CUDA(cudaHostAlloc((void **) &d->p_len, std::max<size_t>(4 * ns, 4), cudaHostAllocPortable));
+  const uint8_t *src = (const uint8_t *) d->map + d->h->off_residues;
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t T = std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, 16));
+  std::vector<std::thread> th;
+  for (size_t k = 0; k < T; k++) th.emplace_back([=]() { const size_t lo = nb * k / T, hi = nb * (k + 1) / T; memcpy(d->p_res + lo, src + lo, hi - lo); });
+  for (auto &x : th) x.join();
+  memcpy(d->p_off, (const char *) d->map + d->h->off_offsets, 8 * ns);
+  memcpy(d->p_len, (const char *) d->map + d->h->off_lengths, 4 * ns);
   d->pinned = true;
   return P7GPU_OK;
 }

@@ -27,6 +27,9 @@ EXPORTS = [
     "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_pipeline_run_host", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
+    "p7gpu_dbfile_from_fasta", "p7gpu_dbfile_open", "p7gpu_dbfile_close", "p7gpu_dbfile_nseq", "p7gpu_dbfile_nres",
+    "p7gpu_dbfile_nbytes", "p7gpu_dbfile_maxlength", "p7gpu_dbfile_residues", "p7gpu_dbfile_offsets", "p7gpu_dbfile_lengths",
+    "p7gpu_dbfile_name", "p7gpu_dbfile_desc", "p7gpu_dbfile_pin", "p7gpu_pipeline_run_file",
 ]
 
 
@@ -122,6 +125,18 @@ def lib():
         L.p7gpu_ForwardParser.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.p7gpu_BackwardParser.argtypes = [vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.p7gpu_pipeline_run.argtypes = [vp, vp, vp, C.POINTER(PipelineOpts), C.POINTER(vp)]
+        L.p7gpu_dbfile_from_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(i64), C.POINTER(i64)]
+        L.p7gpu_dbfile_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.p7gpu_dbfile_close.argtypes = [vp]
+        for nm in ("nseq", "nres", "nbytes"):
+            getattr(L, "p7gpu_dbfile_" + nm).argtypes = [vp]; getattr(L, "p7gpu_dbfile_" + nm).restype = i64
+        L.p7gpu_dbfile_maxlength.argtypes = [vp]; L.p7gpu_dbfile_maxlength.restype = C.c_int32
+        for nm in ("residues", "offsets", "lengths"):
+            getattr(L, "p7gpu_dbfile_" + nm).argtypes = [vp]; getattr(L, "p7gpu_dbfile_" + nm).restype = vp
+        for nm in ("name", "desc"):
+            getattr(L, "p7gpu_dbfile_" + nm).argtypes = [vp, i64]; getattr(L, "p7gpu_dbfile_" + nm).restype = C.c_char_p
+        L.p7gpu_dbfile_pin.argtypes = [vp]
+        L.p7gpu_pipeline_run_file.argtypes = [vp, vp, vp, C.POINTER(PipelineOpts), C.POINTER(vp)]
         L.p7gpu_pipeline_run_many.argtypes = [vp, vp, i64, vp, C.POINTER(PipelineOpts), vp]
         L.p7gpu_result_counters.restype = C.POINTER(PipelineCounters)
         L.p7gpu_result_counters.argtypes = [vp]
@@ -448,6 +463,51 @@ def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilte
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
                                          _p(packed.lengths), packed.nseq, C.byref(o), C.byref(h)))
+    return PipelineResult(h)
+
+
+class DbFile:
+    """The packed on-disk target database (include/p7gpu.h section 8): built once from FASTA, mapped for every search."""
+
+    @staticmethod
+    def from_fasta(fasta_path, out_path, nthreads=0):
+        n = C.c_int64(0); r = C.c_int64(0)
+        _check(lib().p7gpu_dbfile_from_fasta(str(fasta_path).encode(), str(out_path).encode(), int(nthreads), C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def __init__(self, path):
+        h = C.c_void_p()
+        _check(lib().p7gpu_dbfile_open(str(path).encode(), C.byref(h)))
+        self.h = h
+        L = lib()
+        self.nseq, self.nres, self.nbytes = L.p7gpu_dbfile_nseq(h), L.p7gpu_dbfile_nres(h), L.p7gpu_dbfile_nbytes(h)
+        self.max_length = L.p7gpu_dbfile_maxlength(h)
+
+    def _arr(self, fn, ct, n):
+        return np.ctypeslib.as_array(C.cast(fn(self.h), C.POINTER(ct)), shape=(max(n, 0),)) if n else np.zeros(0, ct)
+
+    def packed(self):
+        """Views of the mapped arrays as a seqdb.PackedDB (valid until close())."""
+        from .seqdb import PackedDB
+        L = lib()
+        return PackedDB(self._arr(L.p7gpu_dbfile_residues, C.c_uint8, self.nbytes), self._arr(L.p7gpu_dbfile_offsets, C.c_int64, self.nseq),
+                        self._arr(L.p7gpu_dbfile_lengths, C.c_int32, self.nseq))
+
+    def name(self, s): return lib().p7gpu_dbfile_name(self.h, s).decode()
+    def desc(self, s): return lib().p7gpu_dbfile_desc(self.h, s).decode()
+    def pin(self): _check(lib().p7gpu_dbfile_pin(self.h))
+
+    def close(self):
+        if self.h:
+            lib().p7gpu_dbfile_close(self.h); self.h = None
+
+
+def pipeline_run_file(ctx, prof, dbfile, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
+                      stop_after_msv=False, region_trigger=False):
+    """The batched pipeline over a mapped packed database file (p7gpu_pipeline_run_file)."""
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
+    h = C.c_void_p()
+    _check(lib().p7gpu_pipeline_run_file(ctx.h, prof.h, dbfile.h, C.byref(o), C.byref(h)))
     return PipelineResult(h)
 
 

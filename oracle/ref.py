@@ -42,6 +42,21 @@ class RefHit(C.Structure):
 _lib = None
 
 
+def read_fasta(path, cap_bytes=1 << 26, cap_seqs=1 << 20, want_names=True):
+    """The reference's own digital FASTA reader -> (status, PackedDB-like dict, error text)."""
+    res = np.zeros(cap_bytes, np.uint8); off = np.zeros(cap_seqs, np.int64); ln = np.zeros(cap_seqs, np.int32)
+    names = C.create_string_buffer(1 << 22); err = C.create_string_buffer(512)
+    n = C.c_int64(0); nb = C.c_int64(0)
+    L = lib()
+    L.p7ref_read_fasta.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    st = L.p7ref_read_fasta(path.encode(), _p(res), cap_bytes, _p(off), _p(ln), cap_seqs, C.byref(n), C.byref(nb),
+                            names if want_names else None, 1 << 22, err, 512)
+    parts = names.raw.split(b"\0")
+    nm = [(parts[2 * i].decode(), parts[2 * i + 1].decode()) for i in range(n.value)] if (st == 0 and want_names) else []
+    return st, dict(residues=res[:nb.value].copy(), offsets=off[:n.value].copy(), lengths=ln[:n.value].copy(), names=nm), err.value.decode("latin-1")
+
+
 def lib():
     global _lib
     if _lib is None:

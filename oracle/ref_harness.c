@@ -252,6 +252,39 @@ int p7ref_domain_decoding(void *vh, int L, const float *fxmx, const float *bxmx,
   return st;
 }
 
+/* The reference's own FASTA reader in digital mode (esl_sqfile_OpenDigital + esl_sqio_Read, easel/esl_sqio.c,
+ * esl_sqio_ascii.c), packed the way include/p7gpu.h section 4 lays a database out.  Returns eslOK, or the reader's error
+ * code with its message copied to errbuf.  names: name\0desc\0 per record (may be NULL). */
+#include "esl_sqio.h"
+int p7ref_read_fasta(const char *path, uint8_t *residues, int64_t cap_bytes, int64_t *offsets, int32_t *lengths, int64_t cap_seqs,
+                     int64_t *ret_nseq, int64_t *ret_nbytes, char *names, int64_t cap_names, char *errbuf, int errbuf_len)
+{
+  ESL_ALPHABET *abc = esl_alphabet_Create(eslAMINO);
+  ESL_SQFILE *sqfp = NULL; ESL_SQ *sq = NULL; int status; int64_t n = 0, pos = 1, npos = 0;
+  ref_init_once();
+  if (errbuf && errbuf_len) errbuf[0] = 0;
+  status = esl_sqfile_OpenDigital(abc, path, eslSQFILE_FASTA, NULL, &sqfp);
+  if (status != eslOK) { esl_alphabet_Destroy(abc); return status; }
+  sq = esl_sq_CreateDigital(abc);
+  if (cap_bytes > 0) residues[0] = eslDSQ_SENTINEL;
+  while ((status = esl_sqio_Read(sqfp, sq)) == eslOK) {
+    if (n >= cap_seqs || pos + sq->n + 1 > cap_bytes) { status = eslEMEM; break; }
+    offsets[n] = pos; lengths[n] = (int32_t) sq->n;
+    memcpy(residues + pos, sq->dsq + 1, (size_t) sq->n); residues[pos + sq->n] = eslDSQ_SENTINEL;
+    pos += sq->n + 1;
+    if (names) {
+      int64_t ln = strlen(sq->name) + 1, ld = strlen(sq->desc) + 1;
+      if (npos + ln + ld <= cap_names) { memcpy(names + npos, sq->name, ln); memcpy(names + npos + ln, sq->desc, ld); npos += ln + ld; }
+    }
+    n++;
+    esl_sq_Reuse(sq);
+  }
+  if (status != eslEOF && errbuf && errbuf_len) snprintf(errbuf, errbuf_len, "%s", esl_sqfile_GetErrorBuf(sqfp));
+  *ret_nseq = n; *ret_nbytes = pos;
+  esl_sq_Destroy(sq); esl_sqfile_Close(sqfp); esl_alphabet_Destroy(abc);
+  return status == eslEOF ? eslOK : status;
+}
+
 float p7ref_nullsc(void *vh, int L)
 { P7REF *h = vh; float sc; p7_bg_SetLength(h->bg, L); p7_bg_NullOne(h->bg, NULL, L, &sc); return sc; }
 

@@ -1,0 +1,113 @@
+"""The packed on-disk database (csrc/dbfile.cu): the parallel FASTA digitiser against the reference's own
+reader (esl_sqfile_OpenDigital + esl_sqio_Read through oracle/_ref) — residues, lengths, names, descriptions and error
+behaviour — and the mapped file as a search input.  Host code only: runs without a GPU (the library loads; no kernel runs)."""
+import os
+import numpy as np
+import pytest
+
+from biobench2_b200 import engine, seqdb
+from oracle import ref
+
+SYMS = "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~"
+TRICKY = (
+    "\n  \n>sp|P1|ONE first protein  with  spaces \nACDEFGHIKLMNPQRSTVWY\nacdefghiklmnpqrstvwy\n"
+    ">two\tdesc after tab\r\nBJZOUX*~-_.\r\nAC DE\tFG\r\n\r\n"
+    ">empty_record\n>after_empty no residues before me\nMKV\n"
+    ">gt_inside desc with > sign\nMMM>inline_header starts mid-line\nKKK\n"
+    ">  spaced_name   trailing  \nWWW")                        # no newline at the end of the file
+
+
+def ref_or_skip():
+    if not ref.available():
+        pytest.skip("oracle/_ref/libp7ref.so not built")
+
+
+def roundtrip(tmp_path, text, threads=0, name="t.fa"):
+    fa = tmp_path / name; fa.write_text(text, newline="")
+    out = tmp_path / (name + ".p7db")
+    n, r = engine.DbFile.from_fasta(fa, out, threads)
+    return str(fa), engine.DbFile(out), n, r
+
+
+def assert_same_as_reference(fa, d):
+    st, rdb, err = ref.read_fasta(fa)
+    assert st == 0, err
+    p = d.packed()
+    assert d.nseq == len(rdb["lengths"]) and np.array_equal(p.lengths, rdb["lengths"])
+    assert np.array_equal(p.offsets, rdb["offsets"]) and np.array_equal(p.residues, rdb["residues"])
+    assert [(d.name(s), d.desc(s)) for s in range(d.nseq)] == rdb["names"]
+    assert d.nres == int(rdb["lengths"].sum()) and d.max_length == int(rdb["lengths"].max(initial=0))
+
+
+def test_tricky_fasta_same_as_reference_reader(tmp_path):
+    ref_or_skip()
+    fa, d, n, r = roundtrip(tmp_path, TRICKY)
+    assert n == 7
+    assert_same_as_reference(fa, d)
+    assert (d.name(0), d.desc(0)) == ("sp|P1|ONE", "first protein  with  spaces ")
+    assert d.packed().lengths[2] == 0                          # header directly followed by the next header
+    assert d.name(5) == "inline_header"                        # '>' in the middle of a sequence line starts a record
+    d.close()
+
+
+@pytest.mark.parametrize("threads", [1, 3, 16])
+def test_large_random_fasta_any_thread_count(tmp_path, threads):
+    ref_or_skip()
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(3000):
+        L = int(rng.integers(0, 700))
+        s = "".join(rng.choice(list(SYMS[:20] + "XBZ"), L))
+        w = int(rng.integers(20, 90))
+        body = "\n".join(s[k:k + w] for k in range(0, L, w))
+        recs.append(">seq%d some description %d > with a sign\n%s\n" % (i, i, body))
+    fa, d, n, r = roundtrip(tmp_path, "".join(recs), threads)
+    assert n == 3000
+    assert_same_as_reference(fa, d)
+    d.close()
+
+
+@pytest.mark.parametrize("text,needle", [
+    (">a\nACD1EF\n", "illegal character 1"),
+    (">a\nAC\xe9DE\n", "non-ASCII"),
+    ("ACDE\n>a\nAC\n", "expected FASTA to start with >"),
+    (">\nACDE\n", "no FASTA name found"),
+    (">a\nACDE\n>b desc only", "Premature EOF"),
+])
+def test_errors_like_the_reference(tmp_path, text, needle):
+    ref_or_skip()
+    fa = tmp_path / "bad.fa"; fa.write_bytes(text.encode("latin-1"))
+    with pytest.raises(engine.P7GpuError) as e:
+        engine.DbFile.from_fasta(fa, tmp_path / "bad.p7db")
+    assert needle in str(e.value)
+    st, _, err = ref.read_fasta(str(fa))
+    assert st != 0 and needle in err                            # the reference refuses the same file with the same words
+
+
+def test_empty_file_and_bad_magic(tmp_path):
+    fa, d, n, r = roundtrip(tmp_path, "")
+    assert n == 0 and d.nseq == 0 and d.nbytes == 1
+    d.close()
+    junk = tmp_path / "junk.p7db"; junk.write_bytes(b"x" * 4096)
+    with pytest.raises(engine.P7GpuError):
+        engine.DbFile(junk)
+
+
+@pytest.mark.gpu
+def test_search_from_mapped_file_equals_search_from_memory(tmp_path):
+    from conftest import golden_set
+    g = golden_set("globins4")
+    lines = []
+    for s in range(g.db.nseq):
+        o, L = int(g.db.offsets[s]), int(g.db.lengths[s])
+        lines.append(">t%d\n%s\n" % (s, "".join(SYMS[c] for c in g.db.residues[o:o + L])))
+    fa, d, n, r = roundtrip(tmp_path, "".join(lines))
+    assert n == g.db.nseq and np.array_equal(d.packed().residues, g.db.residues)
+    ctx = engine.Context(0); prof = engine.Profile(ctx, g.oprofile)
+    d.pin()
+    a = engine.pipeline_run_file(ctx, prof, d)
+    b = engine.pipeline_run_host(ctx, prof, g.db)
+    assert list(a.counters) == list(b.counters) == list(g.vec["pli_counters"])
+    assert np.array_equal(a.survivors["seqidx"], b.survivors["seqidx"])
+    assert np.array_equal(a.fwd_xmx.view(np.uint32), b.fwd_xmx.view(np.uint32))
+    a.close(); b.close(); prof.close(); d.close(); ctx.close()
