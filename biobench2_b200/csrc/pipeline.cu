@@ -11,6 +11,7 @@
 #include "p7gpu_internal.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -328,13 +329,40 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
 // Streamed MSV pass over a HOST database: the packed residues are copied in chunks on a copy stream while the SSV/MSV
 // kernels of earlier chunks run on alternating lanes.  The database stays resident in HBM (returned in *ret_db).
 // ------------------------------------------------------------------------------------------------------------------
+// 5-bit transfer format of the residues (p7gpu_pack5): eight codes (0..28, 31 = the 255 sentinel) in five bytes, little-endian
+// bit order.  One thread expands 40 packed bytes into 64 residue bytes (both sides 4-byte / 16-byte aligned).
+__global__ void __launch_bounds__(128) unpack5_kernel(const uint32_t *__restrict__ in, uint4 *__restrict__ out, long long nblocks64)
+{
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblocks64) return;
+  uint32_t w[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) w[k] = __ldg(in + t * 10 + k);
+  uint32_t o[16];
+#pragma unroll
+  for (int g = 0; g < 8; g++) {                                        // group g: packed bytes 5g..5g+4 = bits 40g..40g+39
+    const int bit = 40 * g, wi = bit >> 5, sh = bit & 31;
+    const unsigned long long v = ((unsigned long long) w[wi] >> sh) | ((unsigned long long) w[wi + 1] << (32 - sh));   // sh is 0, 8, 16 or 24: 40 bits fit
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      uint32_t a = (uint32_t) (v >> (5 * r)) & 31u, b = (uint32_t) (v >> (5 * (r + 4))) & 31u;
+      a = (a == 31u) ? 255u : a; b = (b == 31u) ? 255u : b;
+      lo |= a << (8 * r); hi |= b << (8 * r);
+    }
+    o[2 * g] = lo; o[2 * g + 1] = hi;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[t * 4 + k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+}
+
 __global__ void iota_from_kernel(int32_t *v, int32_t first, int32_t n)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = first + i;
 }
 
-static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
+static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, const uint8_t *packed5, int64_t nbytes,
                       const int64_t *offsets, const int32_t *lengths, int64_t nseq, double F1,
                       float *h_sc, int32_t *h_status, float *d_sc, int32_t *d_st, int32_t *d_pass, unsigned int *d_pass_count,
                       p7gpu_seqdb **ret_db)
@@ -363,8 +391,8 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
   cudaStream_t ms = ctx->stream, cs = ctx->copy_stream;
   p7gpu_seqdb *db = new p7gpu_seqdb();
   db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->owns = true; db->pooled = true;
-  const size_t padded = ((size_t) nbytes + 15) / 16 * 16 + 32;
-  uint8_t *d_res = nullptr; int64_t *d_off = nullptr; int32_t *d_len = nullptr;
+  const size_t padded = ((size_t) nbytes + 63) / 64 * 64 + 64;
+  uint8_t *d_res = nullptr, *d_pack = nullptr; int64_t *d_off = nullptr; int32_t *d_len = nullptr;
   int64_t *d_nores[3] = {nullptr, nullptr, nullptr}; void *d_sorttmp[3] = {nullptr, nullptr, nullptr};
   int32_t *d_keys_out[3] = {nullptr, nullptr, nullptr}, *d_iota[3] = {nullptr, nullptr, nullptr};
   size_t sort_tmp_bytes = 0;
@@ -373,6 +401,7 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
   auto cleanup = [&]() {
     for (auto e : events) cudaEventDestroy(e);
     if (ev_main) cudaEventDestroy(ev_main);
+    if (d_pack) cudaFreeAsync(d_pack, ms);
     for (int l = 1; l <= 2; l++) {
       if (d_nores[l]) cudaFreeAsync(d_nores[l], ms);
       if (d_sorttmp[l]) cudaFreeAsync(d_sorttmp[l], ms);
@@ -385,6 +414,7 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
 #define S_CHECK(call) do { int s__ = (call); if (s__ != P7GPU_OK) return fail(s__); } while (0)
   // stream-ordered allocations: after the first call they come back from the pool without touching the driver
   S_CUDA(cudaMallocAsync((void **) &d_res, padded, ms));                                       db->d_res = d_res;
+  if (packed5) S_CUDA(cudaMallocAsync((void **) &d_pack, padded / 64 * 40, ms));
   S_CUDA(cudaMallocAsync((void **) &d_off, 8 * (size_t) std::max<int64_t>(nseq, 1), ms));      db->d_off = d_off;
   S_CUDA(cudaMallocAsync((void **) &d_len, 4 * (size_t) std::max<int64_t>(nseq, 1), ms));      db->d_len = d_len;
   S_CUDA(cudaMallocAsync((void **) &db->d_order, 4 * (size_t) std::max<int64_t>(nseq, 1), ms));
@@ -396,7 +426,7 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
     S_CUDA(cudaMallocAsync((void **) &d_keys_out[l], 4 * (size_t) max_chunk_seqs, ms));
     S_CUDA(cudaMallocAsync((void **) &d_iota[l], 4 * (size_t) max_chunk_seqs, ms));
   }
-  S_CUDA(cudaMemsetAsync(d_res + (padded - 64), 0xff, 64, ms));
+  S_CUDA(cudaMemsetAsync(d_res + (padded - 128), 0xff, 128, ms));
   S_CUDA(cudaMemsetAsync(d_pass_count, 0, sizeof(unsigned int), ms));
   // everything queued on the copy stream and the lanes comes after what is already queued on the main stream
   S_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
@@ -424,9 +454,16 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
     }
     nres += cres; Lmax = std::max(Lmax, cLmax);
     S_CHECK(ensure_len_table(prof, Lmax, F1));
-    const int64_t b_lo = (offsets[s_lo] - 1) & ~15LL;
-    const int64_t b_hi = std::min<int64_t>(nbytes, (offsets[s_hi - 1] + lengths[s_hi - 1] + 1 + 15) & ~15LL);
-    S_CUDA(cudaMemcpyAsync(d_res + b_lo, residues + b_lo, (size_t) (b_hi - b_lo), cudaMemcpyHostToDevice, cs));
+    if (packed5) {                                                    // 5/8 of the bytes over PCIe, expanded on the copy stream
+      const int64_t g_lo = (offsets[s_lo] - 1) / 64, g_hi = (offsets[s_hi - 1] + lengths[s_hi - 1] + 1 + 63) / 64;
+      S_CUDA(cudaMemcpyAsync(d_pack + g_lo * 40, packed5 + g_lo * 40, (size_t) (g_hi - g_lo) * 40, cudaMemcpyHostToDevice, cs));
+      unpack5_kernel<<<(unsigned) ((g_hi - g_lo + 127) / 128), 128, 0, cs>>>((const uint32_t *) (d_pack + g_lo * 40), (uint4 *) (d_res + g_lo * 64), g_hi - g_lo);
+      ctx->launches++;
+    } else {
+      const int64_t b_lo = (offsets[s_lo] - 1) & ~15LL;
+      const int64_t b_hi = std::min<int64_t>(nbytes, (offsets[s_hi - 1] + lengths[s_hi - 1] + 1 + 15) & ~15LL);
+      S_CUDA(cudaMemcpyAsync(d_res + b_lo, residues + b_lo, (size_t) (b_hi - b_lo), cudaMemcpyHostToDevice, cs));
+    }
     S_CUDA(cudaMemcpyAsync(d_off + s_lo, offsets + s_lo, 8 * (size_t) cn, cudaMemcpyHostToDevice, cs));
     S_CUDA(cudaMemcpyAsync(d_len + s_lo, lengths + s_lo, 4 * (size_t) cn, cudaMemcpyHostToDevice, cs));
     cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
@@ -550,11 +587,11 @@ int p7gpu_pipeline_run_many(p7gpu_ctx *ctx, const p7gpu_profile *const *profs, i
   return P7GPU_OK;
 }
 
-int p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
-                            const int64_t *offsets, const int32_t *lengths, int64_t nseq,
-                            const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res)
+static int run_host_impl(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, const uint8_t *packed5, int64_t nbytes,
+                         const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                         const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res)
 {
-  if (!ctx || !prof || !opts || !ret_res || nseq < 0 || (nseq > 0 && (!residues || !offsets || !lengths))) return P7GPU_EINVAL;
+  if (!ctx || !prof || !opts || !ret_res || nseq < 0 || (nseq > 0 && ((!residues && !packed5) || !offsets || !lengths))) return P7GPU_EINVAL;
   *ret_res = nullptr;
   P7G_CHECK(check_opts(prof, opts));
   P7G_CUDA(cudaSetDevice(ctx->device));
@@ -573,7 +610,7 @@ int p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uin
     auto body = [&]() -> int {
       P7G_CHECK(d_sc.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_st.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_pass.alloc(4 * (size_t) nseq, st));
       tr.mark("alloc");
-      P7G_CHECK(stream_msv(ctx, prof, residues, nbytes, offsets, lengths, nseq, F1, nullptr, nullptr,
+      P7G_CHECK(stream_msv(ctx, prof, residues, packed5, nbytes, offsets, lengths, nseq, F1, nullptr, nullptr,
                            d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), d_pass_count, &db));
       tr.mark("stream_msv");
       P7G_CHECK(read_count(ctx, d_pass_count, &npass));
@@ -590,6 +627,52 @@ int p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uin
   p7gpu_seqdb_destroy(db);
   if (status != P7GPU_OK) { delete res; return status; }
   *ret_res = res;
+  return P7GPU_OK;
+}
+
+int p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
+                            const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                            const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res)
+{
+  if (nseq > 0 && !residues) return P7GPU_EINVAL;
+  return run_host_impl(ctx, prof, residues, nullptr, nbytes, offsets, lengths, nseq, opts, ret_res);
+}
+
+int p7gpu_pipeline_run_host5(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *packed5, int64_t nbytes,
+                             const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                             const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res)
+{
+  if (nseq > 0 && !packed5) return P7GPU_EINVAL;
+  return run_host_impl(ctx, prof, nullptr, packed5, nbytes, offsets, lengths, nseq, opts, ret_res);
+}
+
+int64_t p7gpu_pack5_bytes(int64_t nbytes) { return (nbytes + 63) / 64 * 40 + 40; }
+
+// residues (codes 0..28 and the 255 sentinel) -> the 5-bit transfer format; out must hold p7gpu_pack5_bytes(nbytes) bytes
+int p7gpu_pack5(const uint8_t *residues, int64_t nbytes, uint8_t *out, int nthreads)
+{
+  if (nbytes < 0 || (nbytes > 0 && (!residues || !out))) return P7GPU_EINVAL;
+  const int64_t ngroups = p7gpu_pack5_bytes(nbytes) / 5;
+  unsigned hw = std::thread::hardware_concurrency();
+  int64_t T = nthreads > 0 ? nthreads : (int64_t) std::min<unsigned>(hw ? hw : 1, 32);
+  if (T > ngroups / 65536 + 1) T = ngroups / 65536 + 1;
+  std::atomic<int> bad(0);
+  auto work = [&](int64_t g_lo, int64_t g_hi) {
+    for (int64_t g = g_lo; g < g_hi; g++) {
+      unsigned long long v = 0;
+      for (int r = 0; r < 8; r++) {
+        const int64_t i = g * 8 + r;
+        unsigned c = i < nbytes ? residues[i] : 255u;
+        if (c == 255u) c = 31u; else if (c > 28u) { bad = 1; c = 31u; }
+        v |= (unsigned long long) c << (5 * r);
+      }
+      for (int b = 0; b < 5; b++) out[g * 5 + b] = (uint8_t) (v >> (8 * b));
+    }
+  };
+  std::vector<std::thread> th;
+  for (int64_t k = 0; k < T; k++) th.emplace_back(work, ngroups * k / T, ngroups * (k + 1) / T);
+  for (auto &x : th) x.join();
+  if (bad) { set_error("pack5: a residue code outside 0..28 / 255"); return P7GPU_EINVAL; }
   return P7GPU_OK;
 }
 
@@ -610,7 +693,7 @@ int p7gpu_msvfilter_stream(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint
     unsigned int *d_pass_count = ctx->lanes[0].counters + CTR_PASS_COUNT;
     auto body = [&]() -> int {
       P7G_CHECK(d_sc.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_st.alloc(4 * (size_t) nseq, st)); P7G_CHECK(d_pass.alloc(4 * (size_t) nseq, st));
-      P7G_CHECK(stream_msv(ctx, prof, residues, nbytes, offsets, lengths, nseq, F1, sc, status,
+      P7G_CHECK(stream_msv(ctx, prof, residues, nullptr, nbytes, offsets, lengths, nseq, F1, sc, status,
                            d_sc.as<float>(), d_st.as<int32_t>(), d_pass.as<int32_t>(), d_pass_count, &db));
       unsigned npass = 0;
       P7G_CHECK(read_count(ctx, d_pass_count, &npass));

@@ -24,7 +24,7 @@ EXPORTS = [
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
     "p7gpu_backward_batch", "p7gpu_region_trigger_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
     "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser",
-    "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_pipeline_run_host", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
+    "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
     "p7gpu_dbfile_from_fasta", "p7gpu_dbfile_open", "p7gpu_dbfile_close", "p7gpu_dbfile_nseq", "p7gpu_dbfile_nres",
@@ -137,6 +137,9 @@ def lib():
             getattr(L, "p7gpu_dbfile_" + nm).argtypes = [vp, i64]; getattr(L, "p7gpu_dbfile_" + nm).restype = C.c_char_p
         L.p7gpu_dbfile_pin.argtypes = [vp]
         L.p7gpu_pipeline_run_file.argtypes = [vp, vp, vp, C.POINTER(PipelineOpts), C.POINTER(vp)]
+        L.p7gpu_pack5_bytes.argtypes = [i64]; L.p7gpu_pack5_bytes.restype = i64
+        L.p7gpu_pack5.argtypes = [vp, i64, vp, C.c_int]
+        L.p7gpu_pipeline_run_host5.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.POINTER(PipelineOpts), C.POINTER(vp)]
         L.p7gpu_pipeline_run_many.argtypes = [vp, vp, i64, vp, C.POINTER(PipelineOpts), vp]
         L.p7gpu_result_counters.restype = C.POINTER(PipelineCounters)
         L.p7gpu_result_counters.argtypes = [vp]
@@ -463,6 +466,27 @@ def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilte
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
                                          _p(packed.lengths), packed.nseq, C.byref(o), C.byref(h)))
+    return PipelineResult(h)
+
+
+def pack5(residues, out=None, nthreads=0):
+    """Residue bytes -> the 5-bit transfer format (p7gpu_pack5).  `out`: optional preallocated uint8 array (e.g. pinned)."""
+    residues = np.ascontiguousarray(residues, np.uint8)
+    nb = lib().p7gpu_pack5_bytes(residues.shape[0])
+    if out is None:
+        out = np.empty(nb, np.uint8)
+    assert out.dtype == np.uint8 and out.shape[0] >= nb
+    _check(lib().p7gpu_pack5(_p(residues), residues.shape[0], _p(out), int(nthreads)))
+    return out
+
+
+def pipeline_run_host5(ctx, prof, packed5, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
+                       stop_after_msv=False, region_trigger=False):
+    """pipeline_run_host with the residues in the 5-bit transfer format; `packed` supplies offsets, lengths and the unpacked size."""
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
+    h = C.c_void_p()
+    _check(lib().p7gpu_pipeline_run_host5(ctx.h, prof.h, _p(packed5), packed.residues.shape[0], _p(packed.offsets), _p(packed.lengths),
+                                          packed.nseq, C.byref(o), C.byref(h)))
     return PipelineResult(h)
 
 

@@ -259,6 +259,15 @@ int  p7gpu_pipeline_run_many(p7gpu_ctx *ctx, const p7gpu_profile *const *profs, 
 int  p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
                              const int64_t *offsets, const int32_t *lengths, int64_t nseq,
                              const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+/* same with the residues in the 5-bit transfer format (eight codes in five bytes; 31 = sentinel): 5/8 of the bytes cross
+ * PCIe and a small kernel on the copy stream expands them in HBM.  Where several GPUs share one PCIe uplink (HGX boards)
+ * the streamed search is transfer-bound, and this is what brings it back to the kernels' rate.  p7gpu_pack5 builds the
+ * format once per database (nthreads = 0: all host threads); `nbytes` is always the size of the UNPACKED residue array. */
+int64_t p7gpu_pack5_bytes(int64_t nbytes);
+int  p7gpu_pack5(const uint8_t *residues, int64_t nbytes, uint8_t *out, int nthreads);
+int  p7gpu_pipeline_run_host5(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *packed5, int64_t nbytes,
+                              const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                              const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
 /* residues seen by each stage {MSV, bias, Viterbi, Forward, Backward}: the denominators of per-stage cells/s
  * (the reference reports one Mc/s figure for the whole pipeline, p7_pipeline.c:1789-1793) */
 const uint64_t                *p7gpu_result_stage_residues(const p7gpu_pipeline_result *res);

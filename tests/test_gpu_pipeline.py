@@ -211,6 +211,30 @@ def test_pipeline_run_many_equals_one_call_per_profile(ctx):
     db.close()
 
 
+@pytest.mark.parametrize("name", ["globins4", "Pkinase", "tufa420_sprot"])
+def test_five_bit_transfer_format_gives_identical_results(ctx, name):
+    """p7gpu_pipeline_run_host5: residues cross PCIe as eight 5-bit codes in five bytes and are expanded on the device;
+    counters, survivors and specials must be those of the byte path, bit for bit."""
+    g = golden_set(name)
+    prof = engine.Profile(ctx, g.oprofile)
+    hdb = seqdb.concat([g.db, seqdb.synth_db(5000, mean=200, seed=3, degenerate_frac=0.02)])
+    p5 = engine.pack5(hdb.residues)
+    assert p5.shape[0] == (hdb.residues.shape[0] + 63) // 64 * 40 + 40
+    a = engine.pipeline_run_host5(ctx, prof, p5, hdb)
+    b = engine.pipeline_run_host(ctx, prof, hdb)
+    assert list(a.counters) == list(b.counters)
+    assert np.array_equal(a.survivors["seqidx"], b.survivors["seqidx"]) and len(b.survivors) > 0
+    for k in ("usc", "vfsc", "fwdsc", "bcksc", "filtersc"):
+        assert np.array_equal(bits(a.survivors[k]), bits(b.survivors[k])), k
+    assert np.array_equal(bits(a.fwd_xmx), bits(b.fwd_xmx)) and np.array_equal(bits(a.bck_xmx), bits(b.bck_xmx))
+    c = engine.pipeline_run_host5(ctx, prof, p5, hdb, stop_after_msv=True)
+    d = engine.pipeline_run_host(ctx, prof, hdb, stop_after_msv=True)
+    assert np.array_equal(c.msv_pass["seqidx"], d.msv_pass["seqidx"]) and np.array_equal(bits(c.msv_pass["usc"]), bits(d.msv_pass["usc"]))
+    with pytest.raises(engine.P7GpuError):
+        engine.pack5(np.array([255, 3, 29, 255], np.uint8))
+    prof.close()
+
+
 def test_unsupported_model_length_is_rejected(ctx):
     """M beyond the slot geometry (64*65-1 = 4159 nodes) must fail loudly, not silently mis-score."""
     import ctypes
