@@ -2,6 +2,7 @@
 // the batched stage entry points of include/p7gpu.h.  No CPU compute fallback lives here: every stage
 // entry launches a CUDA kernel or fails with P7GPU_ESYS.
 #include "p7gpu_internal.h"
+#include <thread>
 #include <cub/device/device_radix_sort.cuh>
 #include <cstdarg>
 #include <cstdio>
@@ -143,7 +144,15 @@ int ensure_len_table(const p7gpu_profile *prof, int Lmax, double F1)
   if (Lmax < prof->len_cap) return P7GPU_OK;
   int cap = std::max(Lmax + 1, std::max(4096, prof->len_cap * 2));
   prof->h_len.resize(cap);
-  for (int L = prof->len_cap; L < cap; L++) prof->h_len[L] = len_const(prof, L, F1);
+  {                                                                     // ~0.7 us per length (bisection over exp()): all host threads
+    const int L0 = prof->len_cap, nL = cap - L0;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int T = nL < 2048 ? 1 : (int) std::min<unsigned>(hw ? hw : 1, 16);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++)
+      th.emplace_back([=]() { for (int L = L0 + (int) ((long long) nL * t / T); L < L0 + (int) ((long long) nL * (t + 1) / T); L++) prof->h_len[L] = len_const(prof, L, F1); });
+    for (auto &x : th) x.join();
+  }
   LenConst *d_new = nullptr;
   P7G_CUDA(cudaMalloc(&d_new, sizeof(LenConst) * cap));
   P7G_CUDA(cudaMemcpyAsync(d_new, prof->h_len.data(), sizeof(LenConst) * cap, cudaMemcpyHostToDevice, prof->ctx->stream));
