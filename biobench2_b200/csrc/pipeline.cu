@@ -10,6 +10,9 @@
 // on the <= 2% of targets that get that far: pass/fail decisions therefore never depend on device libm.
 #include "p7gpu_internal.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <math_constants.h>
+#include <iterator>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -96,17 +99,17 @@ static HostScratch &host_scratch(p7gpu_ctx *ctx)
 }
 
 // sorted survivors of the MSV stage on the host (arrays live in the context's HostScratch)
-struct MsvPass { std::vector<int64_t> &idx; std::vector<float> &usc; std::vector<int32_t> &st, &len; DevBuf d_idx64;
+struct MsvPass { std::vector<int64_t> &idx; std::vector<float> &usc; std::vector<int32_t> &st, &len; DevBuf d_idx64, g_usc, g_st, g_len;
                  explicit MsvPass(HostScratch &h) : idx(h.idx), usc(h.usc), st(h.st), len(h.len) {} };
 
 static int fetch_msv_pass(p7gpu_ctx *ctx, const p7gpu_seqdb *db, const float *d_usc, const int32_t *d_st,
-                          int32_t *d_pass, unsigned npass, MsvPass *out)
+                          int32_t *d_pass, unsigned npass, MsvPass *out, bool to_host)
 {
   cudaStream_t st = ctx->stream;
-  out->idx.resize(npass); out->usc.resize(npass); out->st.resize(npass); out->len.resize(npass);
+  if (to_host) { out->idx.resize(npass); out->usc.resize(npass); out->st.resize(npass); out->len.resize(npass); }
   P7G_CHECK(out->d_idx64.alloc(sizeof(int64_t) * npass, st));
   if (npass == 0) return P7GPU_OK;
-  DevBuf sorted, tmp, g_usc, g_st, g_len;
+  DevBuf sorted, tmp; DevBuf &g_usc = out->g_usc, &g_st = out->g_st, &g_len = out->g_len;
   P7G_CHECK(sorted.alloc(sizeof(int32_t) * npass, st));
   size_t tmp_bytes = 0;
   P7G_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_pass, sorted.as<int32_t>(), (int) npass, 0, 32, st));
@@ -117,6 +120,7 @@ static int fetch_msv_pass(p7gpu_ctx *ctx, const p7gpu_seqdb *db, const float *d_
                                                            out->d_idx64.as<int64_t>(), g_usc.as<float>(), g_st.as<int32_t>(), g_len.as<int32_t>());
   P7G_CUDA(cudaGetLastError());
   ctx->launches += 3;
+  if (!to_host) return P7GPU_OK;
   P7G_CUDA(cudaMemcpyAsync(out->idx.data(), out->d_idx64.p, 8 * (size_t) npass, cudaMemcpyDeviceToHost, st));
   P7G_CUDA(cudaMemcpyAsync(out->usc.data(), g_usc.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
   P7G_CUDA(cudaMemcpyAsync(out->st.data(), g_st.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
@@ -130,6 +134,179 @@ static int upload_idx(p7gpu_ctx *ctx, const std::vector<int64_t> &idx, DevBuf *d
 {
   P7G_CHECK(d_idx->alloc(8 * idx.size(), ctx->stream));
   if (!idx.empty()) P7G_CUDA(cudaMemcpyAsync(d_idx->p, idx.data(), 8 * idx.size(), cudaMemcpyHostToDevice, ctx->stream));
+  return P7GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stage decisions on the device.  Every P-value test of p7_Pipeline has the form "P(seq_score) > F" with
+// seq_score = (float)((sc - filtersc) / ln 2) and P a non-increasing function of seq_score (esl_gumbel_surv, esl_exp_surv).
+// The host finds, with its own libm and the reference's expressions, the smallest float T whose P passes, and checks that
+// the 64 floats on either side of T are ordered the way monotonicity says; the device then only compares floats: its
+// seq_score is formed with the same IEEE operations (float subtract, double divide, round to float) as the host's, so the
+// decisions are the host's, bit for bit, with no transcendental evaluated on the device.
+// ------------------------------------------------------------------------------------------------------------------
+static inline float float_step(float x, int n)                     // n-th representable float after (before) x
+{
+  int32_t i; memcpy(&i, &x, 4);
+  i = (i < 0) ? (int32_t) 0x80000000 - i : i;                      // to a monotone integer line
+  i += n;
+  i = (i < 0) ? (int32_t) 0x80000000 - i : i;
+  memcpy(&x, &i, 4);
+  return x;
+}
+template <class F> static bool pvalue_threshold(F passes, float guess, float *T)
+{
+  float lo = guess - 4.0f, hi = guess + 4.0f;
+  if (passes(lo) || !passes(hi)) return false;
+  while (float_step(lo, 1) < hi) {                                  // invariant: lo fails, hi passes
+    const float mid = lo + 0.5f * (hi - lo);
+    if (mid <= lo || mid >= hi) break;
+    if (passes(mid)) hi = mid; else lo = mid;
+  }
+  while (float_step(lo, 1) < hi) { const float nx = float_step(lo, 1); if (passes(nx)) { hi = nx; break; } lo = nx; }
+  for (int k = 1; k <= 64; k++) if (passes(float_step(hi, -k)) || !passes(float_step(hi, k))) return false;
+  *T = hi;
+  return true;
+}
+
+struct CandRec { int64_t idx; int32_t L, msv_st, vit_st; float usc, filtersc, vfsc; };
+
+__device__ __forceinline__ float seq_score_of(float sc, float filtersc)
+{
+  return (float) ((double) __fsub_rn(sc, filtersc) / 0.69314718055994529);
+}
+
+__global__ void bias_decide_kernel(unsigned n, const float *usc, const float *fsc, const int32_t *len, float T1, float T2,
+                                   uint8_t *keep, uint8_t *need, unsigned long long *sums)
+{
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long l = 0;
+  if (j < n) {
+    const float x = seq_score_of(usc[j], fsc[j]);
+    const bool k = (x >= T1);                                        // !(P > F1), p7_pipeline.c:700-703
+    keep[j] = k; need[j] = k && !(x >= T2);                          // P > F2: the Viterbi filter runs, :716
+    l = (unsigned long long) len[j];
+  }
+  for (int d = 16; d >= 1; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d);
+  if ((threadIdx.x & 31) == 0 && l) atomicAdd(sums, l);
+}
+
+__global__ void gather_vit_kernel(unsigned n, const int32_t *pos, const int64_t *idx64, const int32_t *len, int64_t *out_idx, unsigned long long *sums)
+{
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long l = 0;
+  if (k < n) { const int32_t j = pos[k]; out_idx[k] = idx64[j]; l = (unsigned long long) len[j]; }
+  for (int d = 16; d >= 1; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d);
+  if ((threadIdx.x & 31) == 0 && l) atomicAdd(sums + 1, l);
+}
+
+__global__ void vit_decide_kernel(unsigned n, const int32_t *pos, const float *vsc, const int32_t *vst, const float *fsc, float Tv,
+                                  uint8_t *keep, float *vf_full, int32_t *vs_full)
+{
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int32_t j = pos[k];
+  vf_full[j] = vsc[k]; vs_full[j] = vst[k];
+  if (!(seq_score_of(vsc[k], fsc[j]) >= Tv)) keep[j] = 0;            // P > F2 after the Viterbi filter, :720-722
+}
+
+__global__ void gather_cand_kernel(unsigned n, const int32_t *pos, const int64_t *idx64, const int32_t *len, const int32_t *mst, const float *usc,
+                                   const float *fsc, const float *vf_full, const int32_t *vs_full, const uint8_t *need, CandRec *out)
+{
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int32_t j = pos[k];
+  CandRec r; r.idx = idx64[j]; r.L = len[j]; r.msv_st = mst[j]; r.usc = usc[j]; r.filtersc = fsc[j];
+  r.vit_st = need[j] ? vs_full[j] : -1; r.vfsc = need[j] ? vf_full[j] : __int_as_float(0x7fc00000);   // the host path's NAN
+  out[k] = r;
+}
+
+struct IotaIt {                                                      // minimal counting iterator for cub::DeviceSelect
+  using iterator_category = std::random_access_iterator_tag; using value_type = int32_t; using difference_type = ptrdiff_t;
+  using pointer = const int32_t *; using reference = int32_t;
+  int32_t v;
+  __host__ __device__ int32_t operator*() const { return v; }
+  __host__ __device__ int32_t operator[](ptrdiff_t i) const { return v + (int32_t) i; }
+  __host__ __device__ IotaIt operator+(ptrdiff_t i) const { return IotaIt{v + (int32_t) i}; }
+  __host__ __device__ IotaIt &operator+=(ptrdiff_t i) { v += (int32_t) i; return *this; }
+  __host__ __device__ IotaIt &operator++() { ++v; return *this; }
+};
+
+static int select_positions(p7gpu_ctx *ctx, const uint8_t *d_flags, unsigned n, int32_t *d_out, unsigned *d_count)
+{
+  size_t bytes = 0;
+  P7G_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, IotaIt{0}, d_flags, d_out, d_count, (int) n, ctx->stream));
+  DevBuf tmp; P7G_CHECK(tmp.alloc(bytes, ctx->stream));
+  P7G_CUDA(cub::DeviceSelect::Flagged(tmp.p, bytes, IotaIt{0}, d_flags, d_out, d_count, (int) n, ctx->stream));
+  ctx->launches += 2;
+  return P7GPU_OK;
+}
+
+// Stages B + C with the decisions on the device: fills `cand` (the targets alive after the Viterbi stage) and the counters.
+static int bias_vit_on_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const DbView &dbv, MsvPass &mp, unsigned npass,
+                              float T1, float T2, float Tv, std::vector<Cand> &cand, p7gpu_pipeline_result *res)
+{
+  cudaStream_t st = ctx->stream;
+  cand.clear();
+  if (npass == 0) return P7GPU_OK;
+  DevBuf d_f, d_keep, d_need, d_sums, d_pos, d_vpos, d_cnt, d_vf, d_vs;
+  P7G_CHECK(d_f.alloc(4 * (size_t) npass, st)); P7G_CHECK(d_keep.alloc(npass, st)); P7G_CHECK(d_need.alloc(npass, st));
+  P7G_CHECK(d_sums.alloc(16, st)); P7G_CHECK(d_pos.alloc(4 * (size_t) npass, st)); P7G_CHECK(d_vpos.alloc(4 * (size_t) npass, st));
+  P7G_CHECK(d_cnt.alloc(16, st)); P7G_CHECK(d_vf.alloc(4 * (size_t) npass, st)); P7G_CHECK(d_vs.alloc(4 * (size_t) npass, st));
+  P7G_CUDA(cudaMemsetAsync(d_sums.p, 0, 16, st)); P7G_CUDA(cudaMemsetAsync(d_cnt.p, 0, 16, st));
+  P7G_CHECK(launch_bias(ctx, 0, prof, dbv, mp.d_idx64.as<int64_t>(), npass, d_f.as<float>()));
+  const unsigned nb = (npass + 255) / 256;
+  bias_decide_kernel<<<nb, 256, 0, st>>>(npass, mp.g_usc.as<float>(), d_f.as<float>(), mp.g_len.as<int32_t>(), T1, T2,
+                                         d_keep.as<uint8_t>(), d_need.as<uint8_t>(), d_sums.as<unsigned long long>());
+  P7G_CUDA(cudaGetLastError());
+  unsigned *cnt = d_cnt.as<unsigned>();
+  P7G_CHECK(select_positions(ctx, d_keep.as<uint8_t>(), npass, d_pos.as<int32_t>(), cnt + 0));
+  P7G_CHECK(select_positions(ctx, d_need.as<uint8_t>(), npass, d_vpos.as<int32_t>(), cnt + 1));
+  unsigned h_cnt[4] = {0, 0, 0, 0};
+  P7G_CUDA(cudaMemcpyAsync(h_cnt, cnt, 8, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaStreamSynchronize(st));
+  const unsigned nc = h_cnt[0], nv = h_cnt[1];
+  res->counters.n_past_bias = nc;
+  ctx->launches += 1;
+  if (nv) {                                                          // Viterbi filter on the candidates that still need it
+    DevBuf d_vidx, d_vsc, d_vst;
+    P7G_CHECK(d_vidx.alloc(8 * (size_t) nv, st)); P7G_CHECK(d_vsc.alloc(4 * (size_t) nv, st)); P7G_CHECK(d_vst.alloc(4 * (size_t) nv, st));
+    gather_vit_kernel<<<(nv + 255) / 256, 256, 0, st>>>(nv, d_vpos.as<int32_t>(), mp.d_idx64.as<int64_t>(), mp.g_len.as<int32_t>(),
+                                                        d_vidx.as<int64_t>(), d_sums.as<unsigned long long>());
+    P7G_CUDA(cudaGetLastError());
+    P7G_CHECK(launch_vit(ctx, 0, prof, dbv, d_vidx.as<int64_t>(), (int64_t) nv, d_vsc.as<float>(), d_vst.as<int32_t>()));
+    vit_decide_kernel<<<(nv + 255) / 256, 256, 0, st>>>(nv, d_vpos.as<int32_t>(), d_vsc.as<float>(), d_vst.as<int32_t>(), d_f.as<float>(), Tv,
+                                                        d_keep.as<uint8_t>(), d_vf.as<float>(), d_vs.as<int32_t>());
+    P7G_CUDA(cudaGetLastError());
+    P7G_CHECK(select_positions(ctx, d_keep.as<uint8_t>(), npass, d_pos.as<int32_t>(), cnt + 2));
+    ctx->launches += 2;
+  } else {
+    P7G_CUDA(cudaMemcpyAsync(cnt + 2, cnt + 0, 4, cudaMemcpyDeviceToDevice, st));
+  }
+  unsigned long long h_sums[2] = {0, 0};
+  P7G_CUDA(cudaMemcpyAsync(h_cnt + 2, cnt + 2, 4, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaMemcpyAsync(h_sums, d_sums.p, 16, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaStreamSynchronize(st));
+  const unsigned nf = h_cnt[2];
+  res->stage_nres[1] += h_sums[0]; res->stage_nres[2] += h_sums[1];
+  if (nf) {
+    DevBuf d_rec; P7G_CHECK(d_rec.alloc(sizeof(CandRec) * (size_t) nf, st));
+    gather_cand_kernel<<<(nf + 255) / 256, 256, 0, st>>>(nf, d_pos.as<int32_t>(), mp.d_idx64.as<int64_t>(), mp.g_len.as<int32_t>(), mp.g_st.as<int32_t>(),
+                                                         mp.g_usc.as<float>(), d_f.as<float>(), d_vf.as<float>(), d_vs.as<int32_t>(), d_need.as<uint8_t>(),
+                                                         d_rec.as<CandRec>());
+    P7G_CUDA(cudaGetLastError());
+    std::vector<CandRec> rec(nf);
+    P7G_CUDA(cudaMemcpyAsync(rec.data(), d_rec.p, sizeof(CandRec) * (size_t) nf, cudaMemcpyDeviceToHost, st));
+    P7G_CUDA(cudaStreamSynchronize(st));
+    ctx->launches += 1;
+    cand.resize(nf);
+    const LenConst *hl = prof->h_len.data();
+    for (unsigned k = 0; k < nf; k++) {
+      Cand &c = cand[k]; const CandRec &r = rec[k];
+      c.idx = r.idx; c.L = r.L; c.msv_st = r.msv_st; c.vit_st = r.vit_st; c.usc = r.usc; c.nullsc = hl[r.L].nullsc; c.filtersc = r.filtersc;
+      c.vfsc = r.vfsc; c.fwdsc = NAN; c.bcksc = NAN; c.ftot = 0.f; c.btot = 0.f; c.P = 0.0;
+    }
+  }
   return P7GPU_OK;
 }
 
@@ -149,7 +326,16 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   Trace tr;
   HostScratch &hs = host_scratch(ctx);
   MsvPass mp(hs);
-  P7G_CHECK(fetch_msv_pass(ctx, db, d_usc, d_st, d_pass, npass, &mp));
+  // default thresholds: the bias and Viterbi stages decide on the device (float thresholds found and verified on the host)
+  float T1 = 0.f, T2 = 0.f, Tv = 0.f;
+  bool dev_decide = do_bias && !o->stop_after_msv && F1 > 0 && F1 < 1 && F2 > 0 && F2 < 1 && !getenv("P7GPU_HOST_DECISIONS");
+  if (dev_decide) {
+    auto gum = [&](double F, float mu, float lam) { return (float) (mu - log(-log1p(-F)) / lam); };
+    dev_decide = pvalue_threshold([&](float x) { return !(host_gumbel_surv((double) x, ev[0], ev[1]) > F1); }, gum(F1, ev[0], ev[1]), &T1)
+              && pvalue_threshold([&](float x) { return !(host_gumbel_surv((double) x, ev[0], ev[1]) > F2); }, gum(F2, ev[0], ev[1]), &T2)
+              && pvalue_threshold([&](float x) { return !(host_gumbel_surv((double) x, ev[2], ev[3]) > F2); }, gum(F2, ev[2], ev[3]), &Tv);
+  }
+  P7G_CHECK(fetch_msv_pass(ctx, db, d_usc, d_st, d_pass, npass, &mp, !dev_decide));
   tr.mark("after_msv: fetch msv pass");
   if (o->stop_after_msv) {
     res->ctx = ctx;
@@ -161,6 +347,11 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     return P7GPU_OK;
   }
 
+  std::vector<Cand> &cand = hs.cand; cand.clear();
+  if (dev_decide) {
+    P7G_CHECK(bias_vit_on_device(ctx, prof, dbv, mp, npass, T1, T2, Tv, cand, res));
+    tr.mark("after_msv: bias + viterbi (device decisions)");
+  } else {
   // ---- B. bias filter (p7_pipeline.c:697-705) ----
   std::vector<float> &filtersc = hs.filtersc; filtersc.resize(npass);
   if (do_bias && npass) {
@@ -177,7 +368,6 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     for (size_t j = lo; j < hi; j++)
       Pv[j] = host_filter_pvalue_gumbel(mp.usc[j], do_bias ? filtersc[j] : hl[mp.len[j]].nullsc, ev[0], ev[1]);
   });
-  std::vector<Cand> &cand = hs.cand; cand.clear();
   for (unsigned j = 0; j < npass; j++) {
     if (do_bias && Pv[j] > F1) continue;
     Cand c;
@@ -213,6 +403,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       cand.resize(w);
     }
   }
+  }   // host decisions
   res->counters.n_past_vit = cand.size();
   tr.mark("after_msv: viterbi stage");
 

@@ -235,6 +235,31 @@ def test_five_bit_transfer_format_gives_identical_results(ctx, name):
     prof.close()
 
 
+@pytest.mark.parametrize("name", ["synth_M400", "globins4", "Pkinase", "tufa420_sprot", "synth_M100"])
+def test_device_stage_decisions_equal_host_decisions(ctx, name):
+    """Default path: the bias and Viterbi P-value tests are float-threshold compares on the device (thresholds found and
+    verified with the host libm).  P7GPU_HOST_DECISIONS=1 evaluates every P-value on the host in the reference's own
+    expressions.  Both must give the same counters, the same survivors and bit-identical scores."""
+    g = golden_set(name)
+    prof = engine.Profile(ctx, g.oprofile)
+    hdb = seqdb.concat([g.db, seqdb.synth_db(60000, mean=300, seed=13, degenerate_frac=0.002)])
+    db = engine.SeqDB.upload(ctx, hdb)
+    dev = engine.pipeline_run(ctx, prof, db, F3=1e-2)            # a looser F3 so that some survivors carry Viterbi scores
+    os.environ["P7GPU_HOST_DECISIONS"] = "1"
+    try:
+        host = engine.pipeline_run(ctx, prof, db, F3=1e-2)
+    finally:
+        del os.environ["P7GPU_HOST_DECISIONS"]
+    assert list(dev.counters) == list(host.counters)
+    assert dev.stage_residues == host.stage_residues
+    assert np.array_equal(dev.survivors["seqidx"], host.survivors["seqidx"])
+    for k in ("usc", "vfsc", "fwdsc", "bcksc", "filtersc", "nullsc"):
+        assert np.array_equal(bits(dev.survivors[k]), bits(host.survivors[k])), k
+    assert np.array_equal(dev.survivors["vit_status"], host.survivors["vit_status"])
+    assert int(dev.counters[3]) <= int(dev.counters[2]) and int(dev.counters[4]) < int(dev.counters[3])   # the filters removed something
+    db.close(); prof.close()
+
+
 def test_unsupported_model_length_is_rejected(ctx):
     """M beyond the slot geometry (64*65-1 = 4159 nodes) must fail loudly, not silently mis-score."""
     import ctypes
