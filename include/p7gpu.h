@@ -278,7 +278,8 @@ int64_t                        p7gpu_result_nsurvivors(const p7gpu_pipeline_resu
 const p7gpu_survivor          *p7gpu_result_survivors (const p7gpu_pipeline_result *res);
 const float                   *p7gpu_result_fwd_xmx  (const p7gpu_pipeline_result *res);
 const float                   *p7gpu_result_bck_xmx  (const p7gpu_pipeline_result *res);
-void                           p7gpu_result_destroy  (p7gpu_pipeline_result *res);
+void                           p7gpu_result_destroy  (p7gpu_pipeline_result *res);   /* before p7gpu_ctx_destroy of its context:
+                                                                                      a result hands its largest buffer back to the context */
 
 /* host-side helpers restating the reference's per-target scalar arithmetic (host libm, bit-exact):
  * p7_bg_NullOne (p7_bg.c:358-363) and the MSV P-value test of p7_pipeline.c:691-693. */
