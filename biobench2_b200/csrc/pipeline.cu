@@ -21,12 +21,36 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <sys/mman.h>
+
+// Host array that grows without zero-filling, on 2 MB-aligned storage advised for transparent huge pages: a --max result
+// holds GBs of specials, and first-touch page faults on 4 KB pages (not PCIe) bounded the copy at 2 GB/s.  A result hands
+// its arrays back to the context when it is destroyed, so a second search faults nothing.
+struct RawFloats {
+  float *p = nullptr; size_t n = 0, cap = 0;
+  bool resize(size_t m) {
+    if (m > cap) {
+      const size_t c = (std::max(m, cap + cap / 2) * sizeof(float) + ((size_t) 2 << 20) - 1) & ~(((size_t) 2 << 20) - 1);
+      void *q = nullptr;
+      if (posix_memalign(&q, (size_t) 2 << 20, c) != 0) return false;
+      madvise(q, c, MADV_HUGEPAGE);
+      if (n) memcpy(q, p, n * sizeof(float));
+      free(p); p = (float *) q; cap = c / sizeof(float);
+    }
+    n = m; return true;
+  }
+  float *data() const { return p; }
+  void swap(RawFloats &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
+  RawFloats() = default;
+  RawFloats(const RawFloats &) = delete; RawFloats &operator=(const RawFloats &) = delete;
+  ~RawFloats() { free(p); }
+};
 
 struct p7gpu_pipeline_result {
   p7gpu_ctx *ctx = nullptr;                       // the MSV-survivor buffer goes back to this context's cache on destroy
   p7gpu_pipeline_counters counters;
   std::vector<p7gpu_survivor> survivors;
-  std::vector<float> fwd_xmx, bck_xmx;
+  RawFloats fwd_xmx, bck_xmx;
   std::vector<p7gpu_msv_survivor> msv_pass;       // only when opts->stop_after_msv
   uint64_t stage_nres[5] = {0, 0, 0, 0, 0};       // residues seen by the MSV, bias, Viterbi, Forward, Backward stages
   uint64_t n_region_flagged = 0;                  // survivors whose specials were returned
@@ -91,6 +115,7 @@ struct HostScratch {
   std::vector<int64_t> idx, vidx; std::vector<float> usc, filtersc, vsc; std::vector<int32_t> st, len, vst;
   std::vector<double> P; std::vector<size_t> where; std::vector<Cand> cand;
   std::vector<p7gpu_msv_survivor> msv_cache;
+  RawFloats xmx_cache[2];
 };
 static HostScratch &host_scratch(p7gpu_ctx *ctx)
 {
@@ -127,6 +152,43 @@ static int fetch_msv_pass(p7gpu_ctx *ctx, const p7gpu_seqdb *db, const float *d_
   P7G_CUDA(cudaMemcpyAsync(out->len.data(), g_len.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
   P7G_CUDA(cudaStreamSynchronize(st));
   return P7GPU_OK;
+}
+
+// Large device -> pageable host copy: DMA into two page-locked bounce buffers, host threads move each piece to its
+// destination while the next piece is in flight (a plain cudaMemcpy into pageable memory ran at 2.5 GB/s).
+static int d2h_large(p7gpu_ctx *ctx, void *dst, const void *d_src, size_t bytes)
+{
+  cudaStream_t st = ctx->stream;
+  const size_t piece = (size_t) 32 << 20;
+  if (bytes <= piece) {
+    if (bytes) { P7G_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, st)); P7G_CUDA(cudaStreamSynchronize(st)); }
+    return P7GPU_OK;
+  }
+  P7G_CHECK(ensure_pinned(ctx, 2 * piece));
+  char *buf[2] = {(char *) ctx->h_pinned, (char *) ctx->h_pinned + piece};
+  cudaEvent_t ev[2];
+  P7G_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming)); P7G_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  const size_t np = (bytes + piece - 1) / piece;
+  auto len_of = [&](size_t k) { return std::min(piece, bytes - k * piece); };
+  int rc = P7GPU_OK;
+  cudaError_t e = cudaMemcpyAsync(buf[0], d_src, len_of(0), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaEventRecord(ev[0], st);
+  for (size_t k = 0; k < np && e == cudaSuccess; k++) {
+    if (k + 1 < np) {
+      e = cudaMemcpyAsync(buf[(k + 1) & 1], (const char *) d_src + (k + 1) * piece, len_of(k + 1), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[(k + 1) & 1], st);
+      if (e != cudaSuccess) break;
+    }
+    e = cudaEventSynchronize(ev[k & 1]);
+    if (e != cudaSuccess) break;
+    char *d = (char *) dst + k * piece; const char *sbuf = buf[k & 1]; const size_t n = len_of(k);
+    parallel_for(n >> 12, [&](size_t lo, size_t hi) { memcpy(d + (lo << 12), sbuf + (lo << 12), (hi - lo) << 12); });
+    if (n & 4095) memcpy(d + (n & ~(size_t) 4095), sbuf + (n & ~(size_t) 4095), n & 4095);
+    // the buffer just drained is refilled two pieces later: that copy is queued only after this memcpy returned
+  }
+  if (e != cudaSuccess) { set_error("d2h_large: %s", cudaGetErrorString(e)); rc = P7GPU_ESYS; cudaStreamSynchronize(st); }
+  cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+  return rc;
 }
 
 // upload a host idx list, run `fn`, fetch float scores (+ statuses)
@@ -429,6 +491,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     P7G_CUDA(cudaMemcpyAsync(fsc.data(), d_sc.p, 4 * n, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaMemcpyAsync(ftot.data(), d_tot.p, 4 * n, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaStreamSynchronize(st));
+    tr.mark("  slice: forward done");
     std::vector<int64_t> bidx, boff; std::vector<size_t> bwhere;
     for (size_t k = 0; k < n; k++) {
       Cand &c = cand[lo + k];
@@ -461,6 +524,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
         P7G_CUDA(cudaMemcpyAsync(flag.data(), d_flag.p, 4 * nb, cudaMemcpyDeviceToHost, st));
       }
       P7G_CUDA(cudaStreamSynchronize(st));
+      tr.mark("  slice: backward + trigger done");
       // which survivors' specials go to the host: all of them, or those whose region trigger fired
       std::vector<int64_t> src, dst; std::vector<int32_t> nfl; std::vector<int64_t> host_off(nb, -1);
       size_t need = 0;
@@ -478,10 +542,13 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
                     "(specials only for targets that can have a domain) or want_specials=0");
           return P7GPU_EMEM;
         }
-        res->fwd_xmx.resize(host_floats + need); res->bck_xmx.resize(host_floats + need);
+        if (!res->ctx) { res->ctx = ctx; res->fwd_xmx.swap(hs.xmx_cache[0]); res->bck_xmx.swap(hs.xmx_cache[1]); res->fwd_xmx.n = res->bck_xmx.n = 0; }
+        if (!res->fwd_xmx.resize(host_floats + need) || !res->bck_xmx.resize(host_floats + need)) {
+          set_error("pipeline: out of host memory for %zu floats of specials", 2 * (host_floats + need)); return P7GPU_EMEM;
+        }
         if (src.size() == n) {                                       // every target of the slice: one bulk copy each
-          P7G_CUDA(cudaMemcpyAsync(res->fwd_xmx.data() + host_floats, d_fx.p, 4 * need, cudaMemcpyDeviceToHost, st));
-          P7G_CUDA(cudaMemcpyAsync(res->bck_xmx.data() + host_floats, d_bx.p, 4 * need, cudaMemcpyDeviceToHost, st));
+          P7G_CHECK(d2h_large(ctx, res->fwd_xmx.data() + host_floats, d_fx.p, 4 * need));
+          P7G_CHECK(d2h_large(ctx, res->bck_xmx.data() + host_floats, d_bx.p, 4 * need));
         } else {                                                     // dense copy on the device first, then one bulk copy each
           DevBuf d_src, d_dst, d_nfl, d_ofx, d_obx;
           P7G_CHECK(upload_idx(ctx, src, &d_src)); P7G_CHECK(upload_idx(ctx, dst, &d_dst));
@@ -490,12 +557,13 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
           P7G_CHECK(d_ofx.alloc(4 * need, st)); P7G_CHECK(d_obx.alloc(4 * need, st));
           P7G_CHECK(launch_gather_xmx(ctx, 0, d_fx.as<float>(), d_bx.as<float>(), d_src.as<int64_t>(), d_dst.as<int64_t>(),
                                       d_nfl.as<int32_t>(), (int64_t) src.size(), d_ofx.as<float>(), d_obx.as<float>()));
-          P7G_CUDA(cudaMemcpyAsync(res->fwd_xmx.data() + host_floats, d_ofx.p, 4 * need, cudaMemcpyDeviceToHost, st));
-          P7G_CUDA(cudaMemcpyAsync(res->bck_xmx.data() + host_floats, d_obx.p, 4 * need, cudaMemcpyDeviceToHost, st));
+          P7G_CHECK(d2h_large(ctx, res->fwd_xmx.data() + host_floats, d_ofx.p, 4 * need));
+          P7G_CHECK(d2h_large(ctx, res->bck_xmx.data() + host_floats, d_obx.p, 4 * need));
           P7G_CUDA(cudaStreamSynchronize(st));                       // the staging vectors and buffers die with this scope
         }
         P7G_CUDA(cudaStreamSynchronize(st));
       }
+      tr.mark("  slice: specials on the host");
       for (size_t k = 0; k < nb; k++) {
         const Cand &c = cand[bwhere[k]];
         p7gpu_survivor s;
@@ -509,6 +577,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       }
       host_floats += need;
       res->n_region_flagged += (uint64_t) src.size();
+      tr.mark("  slice: survivor records");
     }
     lo = hi;
   }
@@ -915,7 +984,12 @@ const p7gpu_msv_survivor *p7gpu_result_msvpass(const p7gpu_pipeline_result *res)
 void p7gpu_result_destroy(p7gpu_pipeline_result *res)
 {
   if (!res) return;
-  if (res->ctx && res->msv_pass.capacity() > host_scratch(res->ctx).msv_cache.capacity()) host_scratch(res->ctx).msv_cache.swap(res->msv_pass);
+  if (res->ctx) {
+    HostScratch &hs = host_scratch(res->ctx);
+    if (res->msv_pass.capacity() > hs.msv_cache.capacity()) hs.msv_cache.swap(res->msv_pass);
+    if (res->fwd_xmx.cap > hs.xmx_cache[0].cap) hs.xmx_cache[0].swap(res->fwd_xmx);
+    if (res->bck_xmx.cap > hs.xmx_cache[1].cap) hs.xmx_cache[1].swap(res->bck_xmx);
+  }
   delete res;
 }
 

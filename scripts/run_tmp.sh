@@ -1,1 +1,1 @@
-timeout 1200 python -m pytest tests/test_gpu_pipeline.py -x -q -k "device_stage and tufa" 2>&1 | grep -E "^E|assert" | head -20
+timeout 1200 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_region_trigger.py tests/test_dbfile.py -x -q 2>&1 | tail -3
