@@ -117,3 +117,38 @@ def test_permutation_invariance_checksum(full):
     assert torch.equal(torch.flip(sc, [0]).view(torch.int32), f["sc"][:n].view(torch.int32))
     assert torch.equal(torch.flip(st, [0]), f["st"][:n])
     db2.close()
+
+
+def test_max_mode_over_many_slices_with_device_trigger():
+    """--max on 6e5 targets (Forward + Backward on every target: 5 GB of specials per direction, three 2-GiB slices) with the
+    region trigger on the device: counters say everything passed, the flagged set and every score agree with per-stage
+    batch calls on a random sample, and the returned specials are the sample's own."""
+    g = golden_set("synth_M400")
+    ctx = engine.Context(0)
+    prof = engine.Profile(ctx, g.oprofile)
+    n = int(os.environ.get("P7_MAXMODE_NSEQ", "600000"))
+    hdb = seqdb.synth_db(n, mean=350, seed=21)
+    db = engine.SeqDB.upload(ctx, hdb)
+    r = engine.pipeline_run(ctx, prof, db, do_max=True, want_specials=True, region_trigger=True)
+    assert list(r.counters) == [n, hdb.nres, n, n, n, n]
+    sv = r.survivors
+    assert np.array_equal(sv["seqidx"], np.arange(n)) and set(np.unique(sv["region_flag"])) <= {0, 1}
+    frac = float((sv["region_flag"] == 1).mean())
+    assert 0.0 < frac < 1.0, frac
+    assert ((sv["xmx_offset"] >= 0) == (sv["region_flag"] == 1)).all()
+    rng = np.random.default_rng(3)
+    flagged = np.nonzero(sv["region_flag"] == 1)[0]
+    idx = np.sort(np.concatenate([rng.choice(n, 300, replace=False), rng.choice(flagged, 100, replace=False)])).astype(np.int64)
+    idx = np.unique(idx)
+    fsc, fst, xmx, xoff, tot = engine.forward_batch(ctx, prof, db, hdb.lengths[idx], idx=idx)
+    bsc, bst, bx, btot = engine.backward_batch(ctx, prof, db, xmx, xoff, idx=idx)
+    mocc, flag = engine.region_trigger_batch(ctx, prof, db, xmx, bx, xoff, idx=idx)
+    assert np.array_equal(bits(fsc), bits(sv["fwdsc"][idx])) and np.array_equal(bits(bsc), bits(sv["bcksc"][idx]))
+    assert np.array_equal(flag, sv["region_flag"][idx]) and np.array_equal(bits(mocc), bits(sv["mocc_max"][idx]))
+    for j, s in enumerate(idx):
+        if sv["region_flag"][s] == 1:
+            m = (int(hdb.lengths[s]) + 1) * 6
+            o = int(sv["xmx_offset"][s])
+            assert np.array_equal(bits(r.fwd_xmx[o:o + m]), bits(xmx[xoff[j]:xoff[j] + m]))
+            assert np.array_equal(bits(r.bck_xmx[o:o + m]), bits(bx[xoff[j]:xoff[j] + m]))
+    r.close(); db.close(); prof.close(); ctx.close()
