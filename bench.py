@@ -57,13 +57,18 @@ def synth_lengths_np(n, mean, seed):
     return seqdb.synth_lengths(n, mean, np.random.default_rng(seed))
 
 
-def synth_db_device(torch, dev, nseq, mean, seed):
-    """Packed layout of include/p7gpu.h §4 built in HBM: (residues u8 [nbytes+32], offsets i64, lengths i32)."""
+def synth_db_device(torch, dev, nseq, mean, seed, align=16):
+    """Packed layout of include/p7gpu.h §4 built in HBM: (residues u8 [nbytes+32], offsets i64, lengths i32).
+    align=16 (default): every target starts on a 16-byte boundary, the gap filled with sentinels (the layout the header
+    recommends: the kernels read residues as aligned 16-byte vectors, so an aligned target has no masked leading rows);
+    align=1: exactly one sentinel between targets."""
     from biobench2_b200 import seqdb
     lengths = synth_lengths_np(nseq, mean, seed)
     l64 = lengths.astype(np.int64)
-    offsets = np.concatenate([[0], np.cumsum(l64 + 1)[:-1]]) + 1
-    nbytes = int(l64.sum()) + nseq + 1
+    span = (l64 + 1 + align - 1) // align * align                       # residues + at least one sentinel, rounded up
+    first = align if align > 1 else 1
+    offsets = np.concatenate([[0], np.cumsum(span)[:-1]]) + first
+    nbytes = int(offsets[-1] + span[-1]) if nseq else first
     g = torch.Generator(device=dev); g.manual_seed(seed)
     cdf = torch.tensor(np.cumsum(seqdb.AMINO_FREQ / seqdb.AMINO_FREQ.sum()), dtype=torch.float32, device=dev)
     res = torch.empty(nbytes + 32, dtype=torch.uint8, device=dev)
@@ -74,10 +79,14 @@ def synth_db_device(torch, dev, nseq, mean, seed):
         res[lo:hi] = torch.searchsorted(cdf, u, right=True).clamp_(max=19).to(torch.uint8)
         del u
     res[nbytes:] = 255
+    res[:first] = 255
     d_off = torch.from_numpy(offsets).to(dev)
     d_len = torch.from_numpy(lengths).to(dev)
-    res[d_off - 1] = 255
-    res[nbytes - 1] = 255
+    end = d_off + d_len                                                  # first byte after each target
+    nxt = torch.from_numpy(offsets + span).to(dev)                       # start of the next target
+    for k in range(align if align > 1 else 1):                          # 1..align sentinels after every target
+        idx = end + k
+        res[idx[idx < nxt]] = 255
     return res, d_off, d_len, lengths, offsets, nbytes
 
 

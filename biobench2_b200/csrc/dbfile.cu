@@ -82,7 +82,7 @@ int64_t next_record(const char *t, int64_t n, int64_t p)
   return n;
 }
 
-void parse_range(const char *t, int64_t n, int64_t lo, int64_t hi, Chunk *out)
+void parse_range(const char *t, int64_t n, int64_t lo, int64_t hi, int align, Chunk *out)
 {
   int64_t p = next_record(t, n, lo);
   while (p < hi && p < n) {
@@ -111,6 +111,7 @@ void parse_range(const char *t, int64_t n, int64_t lo, int64_t hi, Chunk *out)
     }
     out->len.push_back((int32_t) (out->res.size() - r0));
     out->res.push_back(C_SENT);
+    while (out->res.size() % (size_t) align) out->res.push_back(C_SENT);      // the next target starts on an `align` boundary
     p = q;
   }
 }
@@ -144,9 +145,9 @@ using namespace p7g;
 
 extern "C" {
 
-int p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nthreads, int64_t *ret_nseq, int64_t *ret_nres)
+int p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nthreads, int align, int64_t *ret_nseq, int64_t *ret_nres)
 {
-  if (!fasta_path || !out_path) return P7GPU_EINVAL;
+  if (!fasta_path || !out_path || align < 1 || align > 4096 || (align & (align - 1))) return P7GPU_EINVAL;
   int fd = open(fasta_path, O_RDONLY);
   if (fd < 0) { set_error("dbfile_from_fasta: cannot open %s: %s", fasta_path, strerror(errno)); return P7GPU_EINVAL; }
   struct stat sb;
@@ -173,7 +174,7 @@ int p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nt
   std::vector<Chunk> chunks((size_t) T);
   {
     std::vector<std::thread> th;
-    for (int k = 0; k < T; k++) th.emplace_back([&, k]() { parse_range(t, n, n * k / T, n * (k + 1) / T, &chunks[(size_t) k]); });
+    for (int k = 0; k < T; k++) th.emplace_back([&, k]() { parse_range(t, n, n * k / T, n * (k + 1) / T, align, &chunks[(size_t) k]); });
     for (auto &x : th) x.join();
   }
   for (auto &c : chunks)
@@ -186,15 +187,16 @@ int p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nt
       return done(P7GPU_EINVAL);
     }
   // ---- assemble: residues (one leading sentinel), offsets, lengths, names ----
-  uint64_t nseq = 0, resbytes = 1, namebytes = 0; int64_t nres = 0; int32_t Lmax = 0;
+  const uint64_t lead = (uint64_t) align;                              // leading sentinels: the first target starts at `align` (1: one sentinel)
+  uint64_t nseq = 0, resbytes = lead, namebytes = 0; int64_t nres = 0; int32_t Lmax = 0;
   for (auto &c : chunks) { nseq += c.len.size(); resbytes += c.res.size(); namebytes += c.names.size(); }
   std::vector<int64_t> offsets((size_t) nseq); std::vector<int32_t> lengths((size_t) nseq); std::vector<uint64_t> nameidx((size_t) nseq);
   {
-    uint64_t s = 0, pos = 1, npos = 0;
+    uint64_t s = 0, pos = lead, npos = 0;
     for (auto &c : chunks) {
       uint64_t q = pos;
       for (size_t j = 0; j < c.len.size(); j++, s++) {
-        offsets[s] = (int64_t) q; lengths[s] = c.len[j]; q += (uint64_t) c.len[j] + 1;
+        offsets[s] = (int64_t) q; lengths[s] = c.len[j]; q += ((uint64_t) c.len[j] + 1 + (uint64_t) align - 1) / (uint64_t) align * (uint64_t) align;
         nameidx[s] = npos + c.nameoff[j]; nres += c.len[j]; Lmax = std::max(Lmax, c.len[j]);
       }
       pos += c.res.size(); npos += c.names.size();
@@ -213,7 +215,7 @@ int p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nt
   bool bad = false;
   uint64_t w = 0;
   bad |= write_all(ofd, &h, sizeof(h)) != 0; w += sizeof(h); bad |= pad_to(ofd, &w, 4096) != 0;
-  { const uint8_t s0 = C_SENT; bad |= write_all(ofd, &s0, 1) != 0; w += 1; }
+  { std::vector<uint8_t> s0((size_t) lead, C_SENT); bad |= write_all(ofd, s0.data(), s0.size()) != 0; w += lead; }
   for (auto &c : chunks) { bad |= write_all(ofd, c.res.data(), c.res.size()) != 0; w += c.res.size(); }
   bad |= pad_to(ofd, &w, 4096) != 0;
   bad |= write_all(ofd, offsets.data(), 8 * (size_t) nseq) != 0; w += 8 * nseq; bad |= pad_to(ofd, &w, 4096) != 0;

@@ -40,14 +40,15 @@ struct SsvParams {
   unsigned long long *work_counter;
 };
 
-__device__ __forceinline__ uint32_t patch_word(uint32_t w, long long wpos, long long o, long long end)
+// Word b (bytes 4b..4b+3) of a 16-byte chunk whose first `head` and last `tail` bytes lie outside the target: those bytes
+// become the pad residue (an all-PADGAIN table row), so that the chunk body needs no per-row bounds test.
+__device__ __forceinline__ uint32_t patch_word(uint32_t w, int b, int head, int tail)
 {
-#pragma unroll
-  for (int b = 0; b < 4; b++) {
-    long long pos = wpos + b;
-    if (pos < o || pos >= end) w = (w & ~(0xffu << (8 * b))) | ((uint32_t) PADRES << (8 * b));
-  }
-  return w;
+  const int nh = min(max(head - 4 * b, 0), 4), nt = min(max(tail - 4 * (3 - b), 0), 4);
+  const uint32_t mh = nh >= 4 ? 0xffffffffu : ((1u << (8 * nh)) - 1u);
+  const uint32_t mt = nt >= 4 ? 0xffffffffu : ~(0xffffffffu >> (8 * nt));
+  const uint32_t m = mh | mt;
+  return (w & ~m) | ((uint32_t) PADRES * 0x01010101u & m);
 }
 
 // 16 residues per load; the L2::128B hint makes the L2 fetch the whole 128-byte line from HBM once, so that the
@@ -139,8 +140,9 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
         if (pos + DIAG_CHUNK < end) nxt = ldg_res16(p.res + pos + DIAG_CHUNK);
         uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         if (pos < o || pos + DIAG_CHUNK > end) {
+          const int head = (int) (o - pos), tail = (int) (pos + DIAG_CHUNK - end);
 #pragma unroll
-          for (int b = 0; b < 4; b++) w[b] = patch_word(w[b], pos + 4 * b, o, end);
+          for (int b = 0; b < 4; b++) w[b] = patch_word(w[b], b, head, tail);
         }
         // byte address of this lane's first slot in table row 0 for this chunk; row x adds x*rowBytes (one IMAD),
         // the in-chunk row r and the slot q are immediate offsets of the LDS

@@ -125,7 +125,7 @@ def lib():
         L.p7gpu_ForwardParser.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.p7gpu_BackwardParser.argtypes = [vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.p7gpu_pipeline_run.argtypes = [vp, vp, vp, C.POINTER(PipelineOpts), C.POINTER(vp)]
-        L.p7gpu_dbfile_from_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(i64), C.POINTER(i64)]
+        L.p7gpu_dbfile_from_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]
         L.p7gpu_dbfile_open.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.p7gpu_dbfile_close.argtypes = [vp]
         for nm in ("nseq", "nres", "nbytes"):
@@ -494,9 +494,10 @@ class DbFile:
     """The packed on-disk target database (include/p7gpu.h section 8): built once from FASTA, mapped for every search."""
 
     @staticmethod
-    def from_fasta(fasta_path, out_path, nthreads=0):
+    def from_fasta(fasta_path, out_path, nthreads=0, align=16):
+        """align=16: every target starts on a 16-byte boundary (recommended); align=1: exactly one sentinel between targets."""
         n = C.c_int64(0); r = C.c_int64(0)
-        _check(lib().p7gpu_dbfile_from_fasta(str(fasta_path).encode(), str(out_path).encode(), int(nthreads), C.byref(n), C.byref(r)))
+        _check(lib().p7gpu_dbfile_from_fasta(str(fasta_path).encode(), str(out_path).encode(), int(nthreads), int(align), C.byref(n), C.byref(r)))
         return n.value, r.value
 
     def __init__(self, path):

@@ -68,17 +68,19 @@ class PackedDB:
         return min(lo, self.nseq), min(hi, self.nseq)
 
 
-def pack(seqs, names=None):
-    """List of uint8 residue arrays -> PackedDB."""
+def pack(seqs, names=None, align=1):
+    """List of uint8 residue arrays -> PackedDB.  align=16 starts every target on a 16-byte boundary (include/p7gpu.h §4)."""
     lengths = np.array([len(s) for s in seqs], dtype=np.int32)
     offsets = np.zeros(len(seqs), dtype=np.int64)
-    total = int(lengths.astype(np.int64).sum()) + len(seqs) + 1
+    span = (lengths.astype(np.int64) + 1 + align - 1) // align * align
+    first = align if align > 1 else 1
+    total = int(span.sum()) + first
     residues = np.full(total, SENTINEL, dtype=np.uint8)
-    pos = 1
+    pos = first
     for j, s in enumerate(seqs):
         offsets[j] = pos
         residues[pos:pos + len(s)] = s
-        pos += len(s) + 1
+        pos += int(span[j])
     return PackedDB(residues, offsets, lengths, names)
 
 

@@ -123,9 +123,12 @@ int  p7gpu_profile_set_biasfilter(p7gpu_profile *prof, const float *t6, const fl
 
 /* ------------------------------------------------------------------------------------------------
  * 4. Target database: replaces ESL_SQ_BLOCK hand-off (easel/esl_sqio.c:1041; hmmsearch.c:1317-1361).
- *    Packed form: `residues` holds every target's dsq[1..L] back to back with ONE 255 sentinel byte
- *    before the first target and after every target, so residues + offsets[s] - 1 is a valid
- *    sentinel-framed ESL_DSQ of length lengths[s] (offsets[s] = index of the target's first residue).
+ *    Packed form: `residues` holds every target's dsq[1..L] one after the other, in target order, with AT LEAST ONE
+ *    255 sentinel byte before the first target and after every target (any further gap bytes must be 255 too), so
+ *    residues + offsets[s] - 1 is a valid sentinel-framed ESL_DSQ of length lengths[s] (offsets[s] = index of the
+ *    target's first residue).  Recommended: start every target on a 16-byte boundary — the kernels read residues as
+ *    aligned 16-byte vectors, and a target that starts mid-vector pays for up to 15 masked DP rows (4% of the MSV pass
+ *    at mean length 350).  `nbytes` counts everything up to and including the last sentinel.
  * ---------------------------------------------------------------------------------------------- */
 int  p7gpu_seqdb_upload (p7gpu_ctx *ctx, const uint8_t *residues, int64_t nbytes,
                          const int64_t *offsets, const int32_t *lengths, int64_t nseq,
@@ -293,11 +296,13 @@ double p7gpu_msv_pvalue(float usc, float nullsc_or_filtersc, float mmu, float ml
  *    p7gpu_dbfile_from_fasta digitises a FASTA file once, with `nthreads` host threads (0 = all), exactly as easel does
  *    (amino alphabet esl_alphabet.c:269-296; FASTA input map and header rules esl_sqio_ascii.c:2952-3056; the same
  *    error texts in p7gpu_last_error()), into: residues[nbytes] (dsq bytes back to back, one 255 sentinel before the
- *    first and after every target), offsets[nseq] int64, lengths[nseq] int32, names and descriptions.  A search maps the
+ *    first and after every target; with align = 16 — recommended — every target starts on a 16-byte boundary, the gap
+ *    filled with sentinels, so that the kernels' aligned 16-byte residue loads carry no masked leading rows; align = 1:
+ *    exactly one sentinel), offsets[nseq] int64, lengths[nseq] int32, names and descriptions.  A search maps the
  *    file and streams it: p7gpu_pipeline_run_file == p7gpu_pipeline_run_host on the mapped arrays.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct p7gpu_dbfile p7gpu_dbfile;
-int            p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nthreads, int64_t *ret_nseq, int64_t *ret_nres);
+int            p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nthreads, int align, int64_t *ret_nseq, int64_t *ret_nres);
 int            p7gpu_dbfile_open      (const char *path, p7gpu_dbfile **ret_db);
 void           p7gpu_dbfile_close     (p7gpu_dbfile *db);
 int64_t        p7gpu_dbfile_nseq      (const p7gpu_dbfile *db);

@@ -32,7 +32,7 @@ def main():
     except Exception as e:                                     # noqa: BLE001
         res["reference_reader_error"] = str(e)
     d = engine.DbFile(out)
-    assert np.array_equal(d.packed().residues, hdb.residues)
+    assert np.array_equal(d.packed().lengths, hdb.lengths) and (d.packed().offsets % 16 == 0).all()
     if engine.lib().p7gpu_device_count() > 0:
         ctx = engine.Context(0)
         prof = engine.Profile(ctx, OProfile.load(os.path.join(ROOT, "tests", "golden", "prof_synth_M400.npz")))

@@ -1,15 +1,4 @@
-timeout 1200 python -m pytest tests/test_gpu_fullsize.py -x -q -k "max_mode" 2>&1 | tail -3
-timeout 600 python - <<'PY' 2>&1 | tail -12
-import os, sys
-sys.path.insert(0, os.getcwd()); sys.path.insert(0, "tests")
-from conftest import golden_set
-from biobench2_b200 import engine, seqdb
-ctx = engine.Context(0)
-hdb = seqdb.synth_db(50000, mean=350, seed=5)
-db = engine.SeqDB.upload(ctx, hdb)
-for name in ("globins4", "fn3", "Pkinase", "tufa420_sprot", "synth_M100", "synth_M400", "synth_M800", "synth_M2000"):
-    g = golden_set(name); prof = engine.Profile(ctx, g.oprofile)
-    r = engine.pipeline_run(ctx, prof, db, do_max=True, want_specials=False, region_trigger=True)
-    print(name, g.oprofile.M, "flagged fraction on random targets: %.4f" % float((r.survivors["region_flag"] == 1).mean()), flush=True)
-    r.close(); prof.close()
-PY
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -3
+timeout 900 python bench.py --no-cpu-baseline --no-stages --e2e-steps 3 > gpurun_out/bench_al.log 2>&1; tail -1 gpurun_out/bench_al.log | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline_alu']['kernel_gcups'], d['roofline_alu']['frac'], d['detail']['residues_per_gpu'])"

@@ -22,10 +22,10 @@ def ref_or_skip():
         pytest.skip("oracle/_ref/libp7ref.so not built")
 
 
-def roundtrip(tmp_path, text, threads=0, name="t.fa"):
+def roundtrip(tmp_path, text, threads=0, name="t.fa", align=1):
     fa = tmp_path / name; fa.write_text(text, newline="")
-    out = tmp_path / (name + ".p7db")
-    n, r = engine.DbFile.from_fasta(fa, out, threads)
+    out = tmp_path / (name + ".a%d.p7db" % align)
+    n, r = engine.DbFile.from_fasta(fa, out, threads, align)
     return str(fa), engine.DbFile(out), n, r
 
 
@@ -84,6 +84,25 @@ def test_errors_like_the_reference(tmp_path, text, needle):
     assert st != 0 and needle in err                            # the reference refuses the same file with the same words
 
 
+def test_aligned_layout_holds_the_same_targets(tmp_path):
+    """align=16 (the default): every target starts on a 16-byte boundary, gaps are sentinels, content unchanged."""
+    ref_or_skip()
+    fa, d1, n1, r1 = roundtrip(tmp_path, TRICKY, align=1)
+    _, d16, n16, r16 = roundtrip(tmp_path, TRICKY, align=16)
+    p1, p16 = d1.packed(), d16.packed()
+    assert n1 == n16 and r1 == r16 and np.array_equal(p1.lengths, p16.lengths)
+    assert (p16.offsets % 16 == 0).all() and p16.residues.shape[0] % 16 == 0
+    covered = np.zeros(p16.residues.shape[0], bool)
+    for s in range(n1):
+        a = p1.residues[p1.offsets[s]: p1.offsets[s] + p1.lengths[s]]
+        b = p16.residues[p16.offsets[s]: p16.offsets[s] + p16.lengths[s]]
+        assert np.array_equal(a, b) and p16.residues[p16.offsets[s] - 1] == 255 and p16.residues[p16.offsets[s] + p16.lengths[s]] == 255
+        covered[p16.offsets[s]: p16.offsets[s] + p16.lengths[s]] = True
+        assert (d1.name(s), d1.desc(s)) == (d16.name(s), d16.desc(s))
+    assert (p16.residues[~covered] == 255).all()
+    d1.close(); d16.close()
+
+
 def test_empty_file_and_bad_magic(tmp_path):
     fa, d, n, r = roundtrip(tmp_path, "")
     assert n == 0 and d.nseq == 0 and d.nbytes == 1
@@ -101,8 +120,8 @@ def test_search_from_mapped_file_equals_search_from_memory(tmp_path):
     for s in range(g.db.nseq):
         o, L = int(g.db.offsets[s]), int(g.db.lengths[s])
         lines.append(">t%d\n%s\n" % (s, "".join(SYMS[c] for c in g.db.residues[o:o + L])))
-    fa, d, n, r = roundtrip(tmp_path, "".join(lines))
-    assert n == g.db.nseq and np.array_equal(d.packed().residues, g.db.residues)
+    fa, d, n, r = roundtrip(tmp_path, "".join(lines), align=16)
+    assert n == g.db.nseq and np.array_equal(d.packed().lengths, g.db.lengths)
     ctx = engine.Context(0); prof = engine.Profile(ctx, g.oprofile)
     d.pin()
     a = engine.pipeline_run_file(ctx, prof, d)
