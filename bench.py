@@ -214,6 +214,21 @@ def hmmsearch_cli_baseline(cpu, mean, nseq=200_000):
         m = re.search(r"# Mc/sec:\s+([0-9.]+)", r.stdout)
         out[label] = {"elapsed_s": dt, "gcups": cpu.M * hdb.nres / dt / 1e9, "rc": r.returncode,
                       "own_mc_per_sec_line": float(m.group(1)) if m else None}
+    # the input side of the same comparison: the reference's own digital FASTA reader (esl_sqio, the one
+    # reader thread of hmmsearch) against this repo's parallel digitiser into the packed on-disk database, same file
+    try:
+        from biobench2_b200 import engine
+        t0 = time.perf_counter()
+        st, rdb, err = ref.read_fasta(fa, cap_bytes=hdb.residues.shape[0] + 64, cap_seqs=nseq + 1, want_names=False)
+        dtr = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        n2, r2 = engine.DbFile.from_fasta(fa, os.path.join(tmp, "db.p7db"), 0)
+        dtd = time.perf_counter() - t0
+        if st == 0 and n2 == nseq and r2 == hdb.nres and int(rdb["lengths"].astype(np.int64).sum()) == hdb.nres:
+            out["fasta_reader"] = {"reference_esl_sqio_Mres_per_s": hdb.nres / dtr / 1e6, "p7gpu_dbfile_from_fasta_Mres_per_s": hdb.nres / dtd / 1e6,
+                                   "threads": cpu.cores}
+    except Exception as e:                                                # noqa: BLE001 — a baseline extra, never fatal
+        out["fasta_reader"] = {"error": str(e)}
     for f in os.listdir(tmp):
         os.remove(os.path.join(tmp, f))
     os.rmdir(tmp)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Measurement for the packed on-disk database: FASTA digitiser (all host cores) against the reference's own
-reader (esl_sqio through oracle/_ref, one thread — the reader thread of hmmsearch), then a search from the mapped file.
+"""Measurement for the packed on-disk database: FASTA digitiser on all host cores and on one, then a search
+from the mapped file.  (The comparison with the reference's own reader is part of bench.py's cpu_baseline leg.)
 Usage: dbfile_bench.py [nseq]"""
 import os, sys, json, time, tempfile
 import numpy as np
@@ -23,14 +23,6 @@ def main():
     res["digitise_s"] = dt; res["digitise_Mres_per_s"] = hdb.nres / dt / 1e6; res["digitise_MB_per_s"] = fbytes / dt / 1e6
     t0 = time.perf_counter(); n1, r1 = engine.DbFile.from_fasta(fa, out + "1", 1); dt1 = time.perf_counter() - t0
     res["digitise_1thread_Mres_per_s"] = hdb.nres / dt1 / 1e6
-    try:
-        from oracle import ref
-        if ref.available():
-            t0 = time.perf_counter(); st, rdb, err = ref.read_fasta(fa, cap_bytes=hdb.residues.shape[0] + 16, cap_seqs=nseq + 1, want_names=False); dtr = time.perf_counter() - t0
-            assert st == 0 and np.array_equal(rdb["lengths"], hdb.lengths)
-            res["reference_reader_s"] = dtr; res["reference_reader_Mres_per_s"] = hdb.nres / dtr / 1e6
-    except Exception as e:                                     # noqa: BLE001
-        res["reference_reader_error"] = str(e)
     d = engine.DbFile(out)
     assert np.array_equal(d.packed().lengths, hdb.lengths) and (d.packed().offsets % 16 == 0).all()
     if engine.lib().p7gpu_device_count() > 0:
