@@ -131,16 +131,20 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
       for (int q = 0; q < Q; q++) v[q] = 0u;
       uint32_t xE = 0u;
       int c = lane * ssv_lane_stride(Q);
-      const long long end = o + L;
-      long long pos = o & ~15LL;
-      uint4 cur = ldg_res16(p.res + pos);
+      // rows are counted relative to the target's first residue (32-bit): chunk k covers rows r0 .. r0+15, r0 = 16k - head,
+      // where head = bytes between the 16-byte boundary below the target and its first residue (0 in the aligned layout)
+      const int head0 = (int) (o & 15LL);
+      const uint8_t *ptr = p.res + (o - head0);
+      uint4 cur = ldg_res16(ptr);
       int since_check = 0;
-      for (; pos < end; pos += DIAG_CHUNK) {
+#pragma unroll (Q <= 14 ? 2 : 1)
+      for (int r0 = -head0; r0 < L; r0 += DIAG_CHUNK) {
+        ptr += DIAG_CHUNK;
         uint4 nxt = cur;
-        if (pos + DIAG_CHUNK < end) nxt = ldg_res16(p.res + pos + DIAG_CHUNK);
+        if (r0 + DIAG_CHUNK < L) nxt = ldg_res16(ptr);
         uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-        if (pos < o || pos + DIAG_CHUNK > end) {
-          const int head = (int) (o - pos), tail = (int) (pos + DIAG_CHUNK - end);
+        if (r0 < 0 || r0 + DIAG_CHUNK > L) {
+          const int head = -r0, tail = r0 + DIAG_CHUNK - L;
 #pragma unroll
           for (int b = 0; b < 4; b++) w[b] = patch_word(w[b], b, head, tail);
         }

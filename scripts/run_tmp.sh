@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python scripts/sanitize_small.py > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|ERROR SUMMARY|hazard|ok " gpurun_out/racecheck.log | head -20
-timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python scripts/sanitize_small.py > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|Invalid|ok " gpurun_out/memcheck.log | head -20
+for p in synth_M400 synth_M800 synth_M2000; do timeout 300 python scripts/stage_bench.py $p 200000 2>&1 | tail -1 | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['profile'], round(d['ssv_gcups'],1))"; done
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "integer or geometry or seeded" 2>&1 | tail -2
