@@ -76,3 +76,22 @@ def test_digitize_matches_easel_alphabet():
     assert list(seqdb.digitize("ACDEFGHIKLMNPQRSTVWY-BJZOUX*~")) == list(range(29))
     with pytest.raises(ValueError):
         seqdb.digitize("AC1")
+
+
+def test_pack5_transfer_format_round_trip_on_the_host():
+    """p7gpu_pack5 is host code: eight residue codes (0..28; the 255 sentinel as 31) in five bytes, little-endian bit order,
+    padded with sentinels to a multiple of 64 residues.  Decoding it with numpy must give the input back."""
+    import numpy as np
+    from biobench2_b200 import engine, seqdb
+    hdb = seqdb.synth_db(300, mean=90, seed=8, degenerate_frac=0.05)
+    res = hdb.residues
+    p5 = engine.pack5(res, nthreads=3)
+    assert p5.shape[0] == (res.shape[0] + 63) // 64 * 40 + 40
+    ngroups = p5.shape[0] // 5
+    b = p5.reshape(ngroups, 5).astype(np.uint64)
+    v = b[:, 0] | (b[:, 1] << np.uint64(8)) | (b[:, 2] << np.uint64(16)) | (b[:, 3] << np.uint64(24)) | (b[:, 4] << np.uint64(32))
+    codes = np.stack([(v >> np.uint64(5 * r)) & np.uint64(31) for r in range(8)], axis=1).reshape(-1).astype(np.uint8)
+    codes[codes == 31] = 255
+    assert np.array_equal(codes[:res.shape[0]], res)
+    assert (codes[res.shape[0]:] == 255).all()
+    assert np.array_equal(engine.pack5(res, nthreads=1), p5)
