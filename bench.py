@@ -235,6 +235,21 @@ def hmmsearch_cli_baseline(cpu, mean, nseq=200_000):
     return out
 
 
+def cpu_stage_rates(cpu, mean, nseq=24_000):
+    """p7_ViterbiFilter and p7_ForwardParser of the unmodified reference on every host core (one om clone per thread), on a
+    small sample: the CPU side of the per-stage kernel rates in `pipeline.stage_kernel_rates`."""
+    if cpu.kind != "reference":
+        return None
+    hdb = cpu_sample(nseq, mean, seed=777)
+    out = {"sample": "%d iid targets (%d residues), %d threads" % (nseq, hdb.nres, cpu.cores)}
+    for stage in ("vit", "fwd"):
+        cpu.p.stage_batch(stage, hdb.residues[:1 << 16], hdb.offsets[:64], hdb.lengths[:64], threads=1)     # warm
+        t0 = time.perf_counter()
+        cpu.p.stage_batch(stage, hdb.residues, hdb.offsets, hdb.lengths, threads=cpu.cores)
+        out[stage + "_gcups"] = cpu.M * hdb.nres / (time.perf_counter() - t0) / 1e9
+    return out
+
+
 def cpu_sample(nseq, mean, seed=4242):
     from biobench2_b200 import seqdb
     return seqdb.synth_db(nseq, mean=mean, seed=seed)
@@ -522,6 +537,10 @@ def main():
         cpu_baseline = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": cpu.cores, "kind": cpu.kind,
                         "sample": "%d passes over %d iid targets (mean L=%d, %d residues), p7_MSVFilter on %d threads, %.1f s"
                                   % (reps, n, args.mean_len, sample_db.nres, cpu.cores, dt)}
+        try:                                                          # the other stages of the path on the same host cores
+            cpu_baseline["stages"] = cpu_stage_rates(cpu, args.mean_len)
+        except Exception as e:                                       # informative only
+            cpu_baseline["stages"] = {"error": repr(e)}
         try:
             cpu_baseline["hmmsearch_cli"] = hmmsearch_cli_baseline(cpu, args.mean_len)
         except Exception as e:                                       # the CLI leg is informative only
