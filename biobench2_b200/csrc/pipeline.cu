@@ -906,6 +906,18 @@ int p7gpu_pipeline_run_host5(p7gpu_ctx *ctx, const p7gpu_profile *prof, const ui
   return run_host_impl(ctx, prof, nullptr, packed5, nbytes, offsets, lengths, nseq, opts, ret_res);
 }
 
+// Diagnostic: the float threshold the device-side stage decisions use for "P(seq_score) > F" (kind 0: esl_gumbel_surv with
+// (mu, lambda); kind 1: esl_exp_surv).  Returns P7GPU_OK and *T = the smallest seq_score that passes, or P7GPU_ERANGE when no
+// verified threshold exists (the pipeline then evaluates that test on the host).  Host code; needs no device.
+int p7gpu_stage_threshold(int kind, double F, float mu, float lambda, float *T)
+{
+  if (!T || !(F > 0.0 && F < 1.0) || !(lambda > 0.0f)) return P7GPU_EINVAL;
+  bool ok;
+  if (kind == 0) ok = pvalue_threshold([&](float x) { return !(host_gumbel_surv((double) x, mu, lambda) > F); }, (float) (mu - log(-log1p(-F)) / lambda), T);
+  else           ok = pvalue_threshold([&](float x) { return !(host_exp_surv((double) x, mu, lambda) > F); }, (float) (mu - log(F) / lambda), T);
+  return ok ? P7GPU_OK : P7GPU_ERANGE;
+}
+
 int64_t p7gpu_pack5_bytes(int64_t nbytes) { return (nbytes + 63) / 64 * 40 + 40; }
 
 // residues (codes 0..28 and the 255 sentinel) -> the 5-bit transfer format; out must hold p7gpu_pack5_bytes(nbytes) bytes

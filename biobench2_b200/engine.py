@@ -24,7 +24,7 @@ EXPORTS = [
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
     "p7gpu_backward_batch", "p7gpu_region_trigger_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
     "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser",
-    "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
+    "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_stage_threshold", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
     "p7gpu_dbfile_from_fasta", "p7gpu_dbfile_open", "p7gpu_dbfile_close", "p7gpu_dbfile_nseq", "p7gpu_dbfile_nres",
@@ -137,6 +137,7 @@ def lib():
             getattr(L, "p7gpu_dbfile_" + nm).argtypes = [vp, i64]; getattr(L, "p7gpu_dbfile_" + nm).restype = C.c_char_p
         L.p7gpu_dbfile_pin.argtypes = [vp]
         L.p7gpu_pipeline_run_file.argtypes = [vp, vp, vp, C.POINTER(PipelineOpts), C.POINTER(vp)]
+        L.p7gpu_stage_threshold.argtypes = [C.c_int, C.c_double, C.c_float, C.c_float, C.POINTER(C.c_float)]
         L.p7gpu_pack5_bytes.argtypes = [i64]; L.p7gpu_pack5_bytes.restype = i64
         L.p7gpu_pack5.argtypes = [vp, i64, vp, C.c_int]
         L.p7gpu_pipeline_run_host5.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.POINTER(PipelineOpts), C.POINTER(vp)]
@@ -467,6 +468,16 @@ def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilte
     _check(lib().p7gpu_pipeline_run_host(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
                                          _p(packed.lengths), packed.nseq, C.byref(o), C.byref(h)))
     return PipelineResult(h)
+
+
+def stage_threshold(kind, F, mu, lam):
+    """Smallest float seq_score whose P-value passes F (p7gpu_stage_threshold); None when no verified threshold exists."""
+    T = C.c_float(0)
+    st = lib().p7gpu_stage_threshold({"gumbel": 0, "exp": 1}[kind], float(F), float(mu), float(lam), C.byref(T))
+    if st == ERANGE:
+        return None
+    _check(st)
+    return np.float32(T.value)
 
 
 def pack5(residues, out=None, nthreads=0):

@@ -262,6 +262,11 @@ int  p7gpu_pipeline_run_many(p7gpu_ctx *ctx, const p7gpu_profile *const *profs, 
 int  p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
                              const int64_t *offsets, const int32_t *lengths, int64_t nseq,
                              const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+/* diagnostic (host code, no device needed): the float threshold behind the device-side stage decisions.  Every P-value test
+ * of p7_Pipeline reads "P(seq_score) > F" with P non-increasing; *T is the smallest float seq_score that passes, found and
+ * verified with the host libm in the reference's expressions (kind 0: esl_gumbel_surv(x, mu, lambda), easel/esl_gumbel.c:
+ * 129-138; kind 1: esl_exp_surv, easel/esl_exponential.c:127-132).  P7GPU_ERANGE: no verified threshold (host evaluation). */
+int  p7gpu_stage_threshold(int kind, double F, float mu, float lambda, float *T);
 /* same with the residues in the 5-bit transfer format (eight codes in five bytes; 31 = sentinel): 5/8 of the bytes cross
  * PCIe and a small kernel on the copy stream expands them in HBM.  Where several GPUs share one PCIe uplink (HGX boards)
  * the streamed search is transfer-bound, and this is what brings it back to the kernels' rate.  p7gpu_pack5 builds the

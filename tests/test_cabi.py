@@ -95,3 +95,29 @@ def test_pack5_transfer_format_round_trip_on_the_host():
     assert np.array_equal(codes[:res.shape[0]], res)
     assert (codes[res.shape[0]:] == 255).all()
     assert np.array_equal(engine.pack5(res, nthreads=1), p5)
+
+
+def test_stage_thresholds_reproduce_the_p_value_tests():
+    """The device-side stage decisions compare seq_score with a float threshold (p7gpu_stage_threshold, host code).  For
+    calibrated parameter ranges and the pipeline's F values, `x >= T` must equal `not (P(x) > F)` with P evaluated by the
+    oracle's restatement of esl_gumbel_surv / esl_exp_surv (pinned to the reference), at T, around T and far from it."""
+    import numpy as np
+    from biobench2_b200 import engine
+    from oracle import port
+    rng = np.random.default_rng(11)
+    surv = {"gumbel": port.gumbel_surv, "exp": port.exp_surv}
+    n = 0
+    for kind in ("gumbel", "exp"):
+        for F in (0.02, 1e-3, 1e-5, 0.3, 1e-9):
+            for _ in range(12):
+                mu = np.float32(rng.uniform(-25.0, 5.0)); lam = np.float32(rng.uniform(0.55, 0.85))
+                T = engine.stage_threshold(kind, F, mu, lam)
+                assert T is not None
+                near = [np.nextafter(T, np.float32(-np.inf), dtype=np.float32), T, np.nextafter(T, np.float32(np.inf), dtype=np.float32)]
+                xs = near + [np.float32(T + d) for d in rng.uniform(-3, 3, 40)] + [np.float32(T * (1 + e)) for e in rng.uniform(-1e-5, 1e-5, 40)]
+                for x in xs:
+                    passes = not (surv[kind](float(np.float32(x)), float(mu), float(lam)) > F)
+                    assert (np.float32(x) >= T) == passes, (kind, F, mu, lam, x, T)
+                    n += 1
+    assert n > 9000
+    assert engine.stage_threshold("gumbel", 0.02, -10.0, 0.7) is not None
