@@ -130,3 +130,45 @@ def test_search_from_mapped_file_equals_search_from_memory(tmp_path):
     assert np.array_equal(a.survivors["seqidx"], b.survivors["seqidx"])
     assert np.array_equal(a.fwd_xmx.view(np.uint32), b.fwd_xmx.view(np.uint32))
     a.close(); b.close(); prof.close(); d.close(); ctx.close()
+
+
+def test_random_well_formed_fasta_property(tmp_path):
+    """Property test (hypothesis): any well-formed FASTA text — mixed case, every alphabet symbol, '_' and '.' gaps, blank
+    lines, CRLF, ragged line widths, spaces and tabs inside sequence lines, '>' inside descriptions — is digitised exactly
+    as the reference's reader digitises it, at any thread count."""
+    ref_or_skip()
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    sym = st.sampled_from(list(SYMS + SYMS.lower()[:20] + "_."))
+    name = st.text(alphabet=st.characters(min_codepoint=33, max_codepoint=126), min_size=1, max_size=12)
+    desc = st.text(alphabet=st.characters(min_codepoint=32, max_codepoint=126), min_size=0, max_size=30)
+    eol = st.sampled_from(["\n", "\r\n"])
+    filler = st.sampled_from(["", " ", "\t", "  "])
+
+    @st.composite
+    def record(draw):
+        seq = "".join(draw(st.lists(sym, min_size=0, max_size=120)))
+        width = draw(st.integers(5, 70))
+        lines = [seq[k:k + width] for k in range(0, len(seq), width)]
+        body = "".join(draw(filler) + ln + draw(filler) + draw(eol) + ("\n" if draw(st.integers(0, 9)) == 0 else "") for ln in lines)
+        return ">" + draw(st.sampled_from(["", " "])) + draw(name) + draw(st.sampled_from([" ", "\t", "  "])) + draw(desc) + draw(eol) + body
+
+    counter = [0]
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(st.lists(record(), min_size=1, max_size=12), st.integers(1, 5))
+    def check(recs, threads):
+        text = "".join(recs)
+        if not text.endswith("\n") or text.rstrip("\r\n").rsplit("\n", 1)[-1].startswith(">"):
+            text += "A\n"                                    # a header at the very end of the file is an error for both readers
+        counter[0] += 1
+        fa = tmp_path / ("h%d.fa" % counter[0]); fa.write_bytes(text.encode("ascii"))
+        out = tmp_path / ("h%d.p7db" % counter[0])
+        n, r = engine.DbFile.from_fasta(fa, out, threads, 1)
+        d = engine.DbFile(out)
+        try:
+            assert_same_as_reference(str(fa), d)
+        finally:
+            d.close()
+
+    check()
