@@ -109,6 +109,7 @@ void parse_range(const char *t, int64_t n, int64_t lo, int64_t hi, int align, Ch
       else if (x == C_EOD) break;
       else if (x == C_ILLEGAL) { out->err_pos = q; out->err_char = c; out->err_kind = (c >= 128) ? 3 : 1; return; }
     }
+    if (out->res.size() - r0 > (size_t) 0x7fffffff) { out->err_pos = p; out->err_kind = 5; return; }   // ESL_SQ.n is 64-bit; the GPU path is not
     out->len.push_back((int32_t) (out->res.size() - r0));
     out->res.push_back(C_SENT);
     while (out->res.size() % (size_t) align) out->res.push_back(C_SENT);      // the next target starts on an `align` boundary
@@ -183,6 +184,7 @@ int p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nt
       if (c.err_kind == 1) set_error("Line %lld: illegal character %c", line, c.err_char);                 // seebuf, esl_sqio_ascii.c:2294
       else if (c.err_kind == 3) set_error("Line %lld: non-ASCII character in sequence", line);             // :2268
       else if (c.err_kind == 4) set_error("Premature EOF in parsing FASTA name/description line");         // :3047
+      else if (c.err_kind == 5) set_error("Line %lld: target longer than 2^31-1 residues (unsupported)", line);
       else set_error("Line %lld: no FASTA name found", line);                                              // :3029
       return done(P7GPU_EINVAL);
     }
