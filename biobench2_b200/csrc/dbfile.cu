@@ -140,6 +140,7 @@ struct p7gpu_dbfile {
   const Header *h = nullptr;
   bool pinned = false;
   uint8_t *p_res = nullptr; int64_t *p_off = nullptr; int32_t *p_len = nullptr;   // page-locked copies (p7gpu_dbfile_pin)
+  uint8_t *p_res5 = nullptr;                                                      // ... and the residues in the 5-bit transfer format
 };
 
 using namespace p7g;
@@ -258,6 +259,7 @@ void p7gpu_dbfile_close(p7gpu_dbfile *d)
 {
   if (!d) return;
   if (d->p_res) cudaFreeHost(d->p_res);
+  if (d->p_res5) cudaFreeHost(d->p_res5);
   if (d->p_off) cudaFreeHost(d->p_off);
   if (d->p_len) cudaFreeHost(d->p_len);
   if (d->map) munmap(d->map, d->map_bytes);
@@ -302,6 +304,9 @@ int p7gpu_dbfile_pin(p7gpu_dbfile *d)
   for (auto &x : th) x.join();
   memcpy(d->p_off, (const char *) d->map + d->h->off_offsets, 8 * ns);
   memcpy(d->p_len, (const char *) d->map + d->h->off_lengths, 4 * ns);
+  // the streamed search sends 5/8 of the bytes when it has the 5-bit form (p7gpu_pipeline_run_host5)
+  P7G_CUDA(cudaHostAlloc((void **) &d->p_res5, (size_t) p7gpu_pack5_bytes((int64_t) nb), cudaHostAllocPortable));
+  P7G_CHECK(p7gpu_pack5(d->p_res, (int64_t) nb, d->p_res5, 0));
   d->pinned = true;
   return P7GPU_OK;
 }
@@ -310,6 +315,8 @@ int p7gpu_pipeline_run_file(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7g
                             p7gpu_pipeline_result **ret_res)
 {
   if (!d) return P7GPU_EINVAL;
+  if (d->pinned && d->p_res5)
+    return p7gpu_pipeline_run_host5(ctx, prof, d->p_res5, (int64_t) d->h->nbytes, d->p_off, d->p_len, (int64_t) d->h->nseq, opts, ret_res);
   return p7gpu_pipeline_run_host(ctx, prof, p7gpu_dbfile_residues(d), (int64_t) d->h->nbytes, p7gpu_dbfile_offsets(d),
                                  p7gpu_dbfile_lengths(d), (int64_t) d->h->nseq, opts, ret_res);
 }

@@ -319,8 +319,10 @@ const int64_t *p7gpu_dbfile_offsets   (const p7gpu_dbfile *db);
 const int32_t *p7gpu_dbfile_lengths   (const p7gpu_dbfile *db);
 const char    *p7gpu_dbfile_name      (const p7gpu_dbfile *db, int64_t s);     /* ESL_SQ.name */
 const char    *p7gpu_dbfile_desc      (const p7gpu_dbfile *db, int64_t s);     /* ESL_SQ.desc */
-int            p7gpu_dbfile_pin       (p7gpu_dbfile *db);                      /* load into page-locked memory (full-rate H2D);
-                                                                                  the array accessors then return that copy */
+int            p7gpu_dbfile_pin       (p7gpu_dbfile *db);                      /* load into page-locked memory (full-rate H2D),
+                                                                                  also in the 5-bit transfer format, which
+                                                                                  p7gpu_pipeline_run_file then streams; the
+                                                                                  array accessors return the pinned copy */
 int            p7gpu_pipeline_run_file(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_dbfile *db,
                                        const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
 
