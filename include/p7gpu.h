@@ -304,7 +304,8 @@ double p7gpu_msv_pvalue(float usc, float nullsc_or_filtersc, float mmu, float ml
  *    first and after every target; with align = 16 — recommended — every target starts on a 16-byte boundary, the gap
  *    filled with sentinels, so that the kernels' aligned 16-byte residue loads carry no masked leading rows; align = 1:
  *    exactly one sentinel), offsets[nseq] int64, lengths[nseq] int32, names and descriptions.  A search maps the
- *    file and streams it: p7gpu_pipeline_run_file == p7gpu_pipeline_run_host on the mapped arrays.
+ *    file and streams it: p7gpu_pipeline_run_file == p7gpu_pipeline_run_host on the mapped arrays (after
+ *    p7gpu_dbfile_pin: == p7gpu_pipeline_run_host5 on the pinned 5-bit copy).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct p7gpu_dbfile p7gpu_dbfile;
 int            p7gpu_dbfile_from_fasta(const char *fasta_path, const char *out_path, int nthreads, int align, int64_t *ret_nseq, int64_t *ret_nres);
