@@ -205,6 +205,11 @@ int p7gpu_ForwardParser (p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_
 int p7gpu_BackwardParser(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
                          const float *fwd_xmx, float *bck_xmx /* (L+1)*6 or NULL */,
                          float *bck_totscale, float *opt_sc);
+/* same, also reporting P7_OMX.has_own_scales of the Backward matrix (fwdback.c:661-663) */
+int p7gpu_BackwardParser2(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
+                          const float *fwd_xmx, float *bck_xmx, float *bck_totscale, float *opt_sc, int *opt_own_scales);
+/* The one-target wrappers of the two parsers run the exact-order kernels (bit-identical to the reference) unless the ctx
+ * option "fb_fast" is set; the batched p7gpu_forward_batch/p7gpu_backward_batch run the fast kernels unless "fb_exact" is set. */
 
 /* ------------------------------------------------------------------------------------------------
  * 7. The batched pipeline: what the loop body at hmmsearch.c:1399-1411 does per target
@@ -225,7 +230,11 @@ typedef struct p7gpu_pipeline_opts {   /* the fields of P7_PIPELINE the path rea
                                         *    on the device and return specials only for survivors on which it fires: the
                                         *    others have nregions = 0 and p7_Pipeline drops them (p7_pipeline.c:739).
                                         *    Meant for --max, where every target reaches this point.   */
-  int32_t reserved;
+  int32_t fb_exact;                    /* 1: every Forward/Backward result that reaches the host — fwdsc, bcksc, the specials, the F3
+                                        *    decision — is computed in the reference's own order of float operations (the striped
+                                        *    SSE order of impl_sse/fwdback.c:257-465, :469-735; csrc/fbx.cu) and is therefore
+                                        *    bit-identical to p7_ForwardParser/p7_BackwardParser; the fast kernels (1e-4 relative)
+                                        *    then only pre-filter for the F3 test.  0: fast kernels only.                    */
 } p7gpu_pipeline_opts;
 
 typedef struct p7gpu_pipeline_counters { /* P7_PIPELINE accounting (hmmer.h:1224-1231), merged like p7_pipeline_Merge */
@@ -326,6 +335,24 @@ int            p7gpu_dbfile_pin       (p7gpu_dbfile *db);                      /
                                                                                   array accessors return the pinned copy */
 int            p7gpu_pipeline_run_file(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_dbfile *db,
                                        const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+
+/* ------------------------------------------------------------------------------------------------
+ * 9. Several GPUs from one C host (replaces hmmsearch's worker threads hmmsearch.c:505-516 and --mpi, :806-1283).
+ *    The database shards by sequence with no data-path exchange: contiguous ranges balanced by residue count, one
+ *    context (device) and one host thread per shard.  first[nshards+1] receives the shard boundaries; ret_res[k] is
+ *    shard k's result with seqidx already in DATABASE numbering.  The caller merges exactly as the reference merges
+ *    its workers: counters by sum (p7gpu_counters_merge == p7_pipeline_Merge, p7_pipeline.c:597-636), hits through
+ *    p7_tophits_Merge (integration/impl_b200/p7_b200_search.c).  profs[k] must have been uploaded through ctxs[k].
+ * ---------------------------------------------------------------------------------------------- */
+int  p7gpu_shard_plan(const int64_t *offsets, const int32_t *lengths, int64_t nseq, int nshards, int64_t *first);
+int  p7gpu_pipeline_run_sharded(p7gpu_ctx *const *ctxs, const p7gpu_profile *const *profs, int nshards,
+                                const uint8_t *residues, const uint8_t *packed5, int64_t nbytes,
+                                const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                                const p7gpu_pipeline_opts *opts, int64_t *first, p7gpu_pipeline_result **ret_res);
+int  p7gpu_pipeline_run_file_sharded(p7gpu_ctx *const *ctxs, const p7gpu_profile *const *profs, int nshards,
+                                     const p7gpu_dbfile *db, const p7gpu_pipeline_opts *opts, int64_t *first,
+                                     p7gpu_pipeline_result **ret_res);
+void p7gpu_counters_merge(p7gpu_pipeline_counters *into, const p7gpu_pipeline_counters *from);
 
 #ifdef __cplusplus
 }

@@ -19,8 +19,8 @@ def build():
 def lib():
     global _lib
     if _lib is None:
-        src = os.path.join(_HERE, "p7_oracle.c")
-        if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        srcs = [os.path.join(_HERE, f) for f in ("p7_oracle.c", "p7_fbx_oracle.c", "p7_oracle.h")]
+        if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
             build()
         L = C.CDLL(LIB_PATH)
         L.p7o_profile_from_view.restype = C.c_void_p
@@ -38,6 +38,9 @@ def lib():
         L.p7o_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.p7o_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
                                    C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.p7o_forward_striped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.p7o_backward_striped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
+                                           C.POINTER(C.c_int), C.POINTER(C.c_float)]
         L.p7o_filtersc.restype = C.c_float
         L.p7o_domain_decoding.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -96,6 +99,20 @@ class OracleProfile:
         xmx = np.zeros((L + 1, 6), np.float32)
         fwd_xmx = np.ascontiguousarray(fwd_xmx, np.float32)
         st = lib().p7o_backward(self.h, _p(dsq), L, _p(fwd_xmx), _p(xmx), C.byref(tot), C.byref(own), C.byref(sc))
+        return st, np.float32(sc.value), xmx, np.float32(tot.value), own.value
+
+    # the two parsers in the reference's own (striped) order of float operations: bit-exact (oracle/p7_fbx_oracle.c)
+    def fwd_striped(self, dsq, L):
+        sc = C.c_float(0); tot = C.c_float(0)
+        xmx = np.zeros((L + 1, 6), np.float32)
+        st = lib().p7o_forward_striped(C.byref(self._keep[0]), _p(dsq), L, _p(xmx), C.byref(tot), C.byref(sc))
+        return st, np.float32(sc.value), xmx, np.float32(tot.value)
+
+    def bwd_striped(self, dsq, L, fwd_xmx):
+        sc = C.c_float(0); tot = C.c_float(0); own = C.c_int(0)
+        xmx = np.zeros((L + 1, 6), np.float32)
+        fwd_xmx = np.ascontiguousarray(fwd_xmx, np.float32)
+        st = lib().p7o_backward_striped(C.byref(self._keep[0]), _p(dsq), L, _p(fwd_xmx), _p(xmx), C.byref(tot), C.byref(own), C.byref(sc))
         return st, np.float32(sc.value), xmx, np.float32(tot.value), own.value
 
     def domain_decoding(self, L, fwd_xmx, bck_xmx, own_scales=0):
