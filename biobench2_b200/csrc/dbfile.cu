@@ -321,4 +321,14 @@ int p7gpu_pipeline_run_file(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7g
                                  p7gpu_dbfile_lengths(d), (int64_t) d->h->nseq, opts, ret_res);
 }
 
+int p7gpu_pipeline_run_file_sharded(p7gpu_ctx *const *ctxs, const p7gpu_profile *const *profs, int nshards, const p7gpu_dbfile *d,
+                                    const p7gpu_pipeline_opts *opts, int64_t *first, p7gpu_pipeline_result **ret_res)
+{
+  if (!d) return P7GPU_EINVAL;
+  const bool five = d->pinned && d->p_res5;
+  return p7gpu_pipeline_run_sharded(ctxs, profs, nshards, five ? nullptr : p7gpu_dbfile_residues(d), five ? d->p_res5 : nullptr,
+                                    (int64_t) d->h->nbytes, p7gpu_dbfile_offsets(d), p7gpu_dbfile_lengths(d), (int64_t) d->h->nseq,
+                                    opts, first, ret_res);
+}
+
 }  // extern "C"

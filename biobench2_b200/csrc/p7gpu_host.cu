@@ -4,6 +4,8 @@
 #include "p7gpu_internal.h"
 #include <thread>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <iterator>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -49,6 +51,14 @@ int ensure_scratch2(p7gpu_ctx *ctx, size_t bytes)
   ctx->d_scratch2_bytes = want;
   return P7GPU_OK;
 }
+int ensure_fbx_state(p7gpu_ctx *ctx, size_t bytes)
+{
+  if (bytes <= ctx->d_fbx_state_bytes) return P7GPU_OK;
+  if (ctx->d_fbx_state) { P7G_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->d_fbx_state); ctx->d_fbx_state = nullptr; ctx->d_fbx_state_bytes = 0; }
+  P7G_CUDA(cudaMalloc(&ctx->d_fbx_state, bytes));
+  ctx->d_fbx_state_bytes = bytes;
+  return P7GPU_OK;
+}
 int ensure_pinned(p7gpu_ctx *ctx, size_t bytes)
 {
   if (bytes <= ctx->h_pinned_bytes) return P7GPU_OK;
@@ -72,6 +82,28 @@ static int16_t wordify(float scale_w, float sc)
   else if (sc <= -32768.0) return -32768;
   else return (int16_t) sc;
 }
+// totscale and score of a Forward matrix from its specials, exactly as forward_engine accumulates them (fwdback.c:434, :463):
+// float += double log of every scale factor > 1 in row order; score = totscale + log(xC * xf[C][MOVE]) in double, stored to float
+void fbx_host_fwd_score(const float *xmx, int L, float pmove, float *totscale, float *sc, int *status)
+{
+  float tot = 0.0f;
+  for (int i = 1; i <= L; i++) { const float s = xmx[(size_t) i * 6 + 5]; if (s != 1.0f) tot = (float) ((double) tot + log((double) s)); }
+  const float xC = xmx[(size_t) L * 6 + 4];
+  *totscale = tot;
+  if (std::isnan(xC) || (L > 0 && xC == 0.0f) || std::isinf(xC)) { *status = P7GPU_ERANGE; *sc = xC; }   // :456-458
+  else { *status = P7GPU_OK; *sc = (float) ((double) tot + log((double) (xC * pmove))); }
+}
+// same for backward_engine (:553, :689, :735): row L first, then rows L-1 .. 1
+void fbx_host_bwd_score(const float *xmx, int L, float *totscale, float *sc, int *status)
+{
+  float tot = (float) log((double) xmx[(size_t) L * 6 + 5]);
+  for (int i = L - 1; i >= 1; i--) { const float s = xmx[(size_t) i * 6 + 5]; if (s > 1.0f) tot = (float) ((double) tot + log((double) s)); }
+  const float xN = xmx[1];
+  *totscale = tot;
+  if (std::isnan(xN) || (L > 0 && xN == 0.0f) || std::isinf(xN)) { *status = P7GPU_ERANGE; *sc = xN; }   // :731-733
+  else { *status = P7GPU_OK; *sc = (float) ((double) tot + log((double) xN)); }
+}
+
 float host_nullsc(int L)                                   // p7_bg_NullOne, p7_bg.c:358-363 (double math, float result)
 {
   float p1 = (float) L / (float) (L + 1);
@@ -326,6 +358,7 @@ void p7gpu_ctx_destroy(p7gpu_ctx *ctx)
   for (auto &t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
+  if (ctx->d_fbx_state) cudaFree(ctx->d_fbx_state);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
 }
@@ -348,6 +381,10 @@ int p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value)
   if (!ctx || !name) return P7GPU_EINVAL;
   if (!strcmp(name, "vit_exact_only")) { ctx->vit_exact_only = value; return P7GPU_OK; }
   if (!strcmp(name, "fb_one_warp"))    { ctx->fb_one_warp = value; return P7GPU_OK; }
+  if (!strcmp(name, "fb_exact"))       { ctx->fb_exact = value; return P7GPU_OK; }
+  if (!strcmp(name, "fb_fast"))        { ctx->fb_fast = value; return P7GPU_OK; }
+  if (!strcmp(name, "fbx_global"))     { ctx->fbx_global = value; return P7GPU_OK; }
+  if (!strcmp(name, "fbx_warps"))      { ctx->fbx_warps = value; return P7GPU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return P7GPU_EINVAL;
 }
@@ -445,6 +482,19 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
     P7G_CUDA(cudaMalloc(&prof->d_tw, tw.size() * 2)); P7G_CUDA(cudaMemcpy(prof->d_tw, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
     P7G_CUDA(cudaMalloc(&prof->d_rf, rf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rf, rf.data(), rf.size() * 4, cudaMemcpyHostToDevice));
     P7G_CUDA(cudaMalloc(&prof->d_tf, tf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
+    {                                                                 // exact-order kernels (fbx.cu): striped values, wider loads
+      const int Q = Q4, Qp = (Q4 + 3) / 4 * 4;
+      std::vector<float> tfx((size_t) Q * 32, 0.0f), rfx((size_t) NTABROWS * 4 * Qp, 0.0f);
+      for (int q = 0; q < Q; q++)
+        for (int z = 0; z < 4; z++) {
+          for (int t = 0; t < 7; t++) tfx[((size_t) q * 4 + z) * 8 + t] = om->tfv[((size_t) 7 * q + t) * 4 + z];
+          tfx[((size_t) q * 4 + z) * 8 + 7] = om->tfv[((size_t) 7 * Q + q) * 4 + z];
+          for (int x = 0; x < Kp; x++) rfx[((size_t) x * 4 + z) * Qp + q] = om->rfv[((size_t) x * Q + q) * 4 + z];
+        }
+      P7G_CUDA(cudaMalloc(&prof->d_tfx, tfx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tfx, tfx.data(), tfx.size() * 4, cudaMemcpyHostToDevice));
+      P7G_CUDA(cudaMalloc(&prof->d_rfx, rfx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rfx, rfx.data(), rfx.size() * 4, cudaMemcpyHostToDevice));
+      prof->fbxQ = Q; prof->fbxQp = Qp;
+    }
     int mc = 0, mw = 0;
     if (mw_geometry(M, &mc, &mw)) {                                   // long models: [row][j][g], node k = g*mc + j + 1
       const int G = 32 * mw;
@@ -477,6 +527,7 @@ void p7gpu_profile_destroy(p7gpu_profile *prof)
   cudaFree(prof->d_ssv_tab); cudaFree(prof->d_msv_tab);
   cudaFree(prof->d_rw); cudaFree(prof->d_tw); cudaFree(prof->d_rf); cudaFree(prof->d_tf);
   cudaFree(prof->d_rf_mw); cudaFree(prof->d_tf_mw);
+  cudaFree(prof->d_tfx); cudaFree(prof->d_rfx);
   cudaFree(prof->d_rwp); cudaFree(prof->d_twp); cudaFree(prof->d_scanw);
   cudaFree(prof->d_len);
   delete prof;
@@ -557,6 +608,17 @@ int p7gpu_seqdb_upload(p7gpu_ctx *ctx, const uint8_t *residues, int64_t nbytes, 
   return P7GPU_OK;
 }
 
+struct WidenIt {                                                       // int32 lengths read as int64 (input iterator for cub::DeviceReduce)
+  using iterator_category = std::random_access_iterator_tag; using value_type = int64_t; using difference_type = ptrdiff_t;
+  using pointer = const int64_t *; using reference = int64_t;
+  const int32_t *p;
+  __host__ __device__ int64_t operator*() const { return (int64_t) *p; }
+  __host__ __device__ int64_t operator[](ptrdiff_t i) const { return (int64_t) p[i]; }
+  __host__ __device__ WidenIt operator+(ptrdiff_t i) const { return WidenIt{p + i}; }
+  __host__ __device__ WidenIt &operator+=(ptrdiff_t i) { p += i; return *this; }
+  __host__ __device__ WidenIt &operator++() { ++p; return *this; }
+};
+
 int p7gpu_seqdb_adopt_device(p7gpu_ctx *ctx, const void *d_residues, int64_t nbytes, const void *d_offsets,
                              const void *d_lengths, int64_t nseq, int32_t max_length, p7gpu_seqdb **ret_db)
 {
@@ -565,8 +627,21 @@ int p7gpu_seqdb_adopt_device(p7gpu_ctx *ctx, const void *d_residues, int64_t nby
   *ret_db = nullptr;
   P7G_CUDA(cudaSetDevice(ctx->device));
   p7gpu_seqdb *db = new p7gpu_seqdb();
-  db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->nres = nbytes - nseq - 1; db->max_length = max_length; db->owns = false;
+  db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->nres = 0; db->max_length = max_length; db->owns = false;
   db->d_res = (const uint8_t *) d_residues; db->d_off = (const int64_t *) d_offsets; db->d_len = (const int32_t *) d_lengths;
+  if (nseq) {                                                          // pli->nres = sum of the lengths (p7_pli_NewSeq); gaps between targets are layout
+    size_t tmp_bytes = 0; int64_t *d_sum = nullptr; void *d_tmp = nullptr;
+    WidenIt it{db->d_len};
+    P7G_CUDA(cub::DeviceReduce::Sum(nullptr, tmp_bytes, it, (int64_t *) nullptr, (int) nseq, ctx->stream));
+    P7G_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 16));
+    d_sum = (int64_t *) ((char *) d_tmp + (tmp_bytes + 7) / 8 * 8);
+    cudaError_t e = cub::DeviceReduce::Sum(d_tmp, tmp_bytes, it, d_sum, (int) nseq, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&db->nres, d_sum, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) { set_error("seqdb_adopt_device: length sum failed: %s", cudaGetErrorString(e)); delete db; return P7GPU_ESYS; }
+    ctx->launches += 1;
+  }
   int st = build_order(ctx, db);
   if (st != P7GPU_OK) { p7gpu_seqdb_destroy(db); return st; }
   *ret_db = db;
@@ -722,6 +797,14 @@ static int lengths_of(p7gpu_ctx *ctx, const p7gpu_seqdb *db, const int64_t *idx,
   return P7GPU_OK;
 }
 
+// dense offsets for callers that pass no specials buffer but run the exact-order kernels (which always write specials)
+static void dense_xmx_offsets(const std::vector<int32_t> &lens, std::vector<int64_t> &off, int64_t *ext)
+{
+  off.resize(lens.size()); int64_t e = 0;
+  for (size_t j = 0; j < lens.size(); j++) { off[j] = e; e += (int64_t) (lens[j] + 1) * P7GPU_NXCELLS; }
+  *ext = e;
+}
+
 int p7gpu_forward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
                         const int64_t *idx, int64_t n, float *sc, int32_t *status,
                         float *xmx, const int64_t *xmx_offsets, float *totscale)
@@ -732,26 +815,38 @@ int p7gpu_forward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_s
   P7G_CUDA(cudaSetDevice(ctx->device));
   BatchBufs b;
   P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
+  const bool exact = ctx->fb_exact != 0;
   float *d_xmx = nullptr; int64_t *d_xoff = nullptr; float *d_tot = nullptr; int64_t ext = 0;
-  std::vector<int32_t> lens;
+  std::vector<int32_t> lens; std::vector<int64_t> own_off;
   const size_t nb = (size_t) std::max<int64_t>(b.n, 1);
-  if (xmx) { P7G_CHECK(lengths_of(ctx, db, idx, b.n, lens)); ext = xmx_extent(db, xmx_offsets, b.n, lens.data()); }
+  if (xmx || exact) P7G_CHECK(lengths_of(ctx, db, idx, b.n, lens));
+  if (xmx) ext = xmx_extent(db, xmx_offsets, b.n, lens.data());
+  else if (exact) { dense_xmx_offsets(lens, own_off, &ext); xmx_offsets = own_off.data(); }
+  const bool dev_x = xmx || exact;
   const size_t off_bytes = (nb * 8 + 255) / 256 * 256, tot_bytes = (nb * 4 + 255) / 256 * 256;
   P7G_CHECK(ensure_scratch2(ctx, off_bytes + tot_bytes + (size_t) ext * 4 + 256));
   d_xoff = (int64_t *) ctx->d_scratch2; d_tot = (float *) ((char *) ctx->d_scratch2 + off_bytes);
-  if (xmx) {
+  if (dev_x) {
     d_xmx = (float *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes);
     P7G_CUDA(cudaMemcpyAsync(d_xoff, xmx_offsets, sizeof(int64_t) * b.n, cudaMemcpyHostToDevice, ctx->stream));
   }
-  P7G_CHECK(launch_fwd(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc, b.d_st, d_xmx, xmx ? d_xoff : nullptr, d_tot));
+  if (exact) P7G_CHECK(launch_fbx_fwd(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc, b.d_st, d_xmx, d_xoff, d_tot));
+  else       P7G_CHECK(launch_fwd(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc, b.d_st, d_xmx, xmx ? d_xoff : nullptr, d_tot));
   if (xmx && ext) P7G_CUDA(cudaMemcpyAsync(xmx, d_xmx, sizeof(float) * ext, cudaMemcpyDeviceToHost, ctx->stream));
   if (totscale && b.n) P7G_CUDA(cudaMemcpyAsync(totscale, d_tot, sizeof(float) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
-  return fetch_batch(ctx, b, sc, status);
+  P7G_CHECK(fetch_batch(ctx, b, sc, status));
+  if (exact && xmx)                                                   // scores from the specials with the host libm (fwdback.c:434,:463)
+    for (int64_t j = 0; j < b.n; j++) {
+      float t, s; int st;
+      fbx_host_fwd_score(xmx + xmx_offsets[j], lens[j], prof->h_len[lens[j]].pmove, &t, &s, &st);
+      if (sc) sc[j] = s; if (status) status[j] = st; if (totscale) totscale[j] = t;
+    }
+  return P7GPU_OK;
 }
 
-int p7gpu_backward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
-                         const int64_t *idx, int64_t n, const float *fwd_xmx, const int64_t *xmx_offsets,
-                         float *sc, int32_t *status, float *bck_xmx, float *bck_totscale)
+static int backward_batch_impl(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                               const int64_t *idx, int64_t n, const float *fwd_xmx, const int64_t *xmx_offsets,
+                               float *sc, int32_t *status, float *bck_xmx, float *bck_totscale, int32_t *own_scales)
 {
   if (!ctx || !prof || !db || !fwd_xmx || !xmx_offsets) return P7GPU_EINVAL;
   if (!prof->d_rf) { set_error("backward: profile was uploaded without the Forward part"); return P7GPU_EINVAL; }
@@ -764,17 +859,34 @@ int p7gpu_backward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_
   const size_t nb = (size_t) std::max<int64_t>(b.n, 1);
   const size_t off_bytes = (nb * 8 + 255) / 256 * 256, tot_bytes = (nb * 4 + 255) / 256 * 256;
   const size_t x_bytes = ((size_t) ext * 4 + 255) / 256 * 256;
-  P7G_CHECK(ensure_scratch2(ctx, off_bytes + tot_bytes + 2 * x_bytes + 256));
+  P7G_CHECK(ensure_scratch2(ctx, off_bytes + 2 * tot_bytes + 2 * x_bytes + 256));
   int64_t *d_xoff = (int64_t *) ctx->d_scratch2;
   float *d_tot = (float *) ((char *) ctx->d_scratch2 + off_bytes);
-  float *d_fx  = (float *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes);
-  float *d_bx  = (float *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes + x_bytes);
+  int32_t *d_own = (int32_t *) ((char *) ctx->d_scratch2 + off_bytes + tot_bytes);
+  float *d_fx  = (float *) ((char *) ctx->d_scratch2 + off_bytes + 2 * tot_bytes);
+  float *d_bx  = (float *) ((char *) ctx->d_scratch2 + off_bytes + 2 * tot_bytes + x_bytes);
   P7G_CUDA(cudaMemcpyAsync(d_xoff, xmx_offsets, sizeof(int64_t) * b.n, cudaMemcpyHostToDevice, ctx->stream));
   if (ext) P7G_CUDA(cudaMemcpyAsync(d_fx, fwd_xmx, sizeof(float) * ext, cudaMemcpyHostToDevice, ctx->stream));
-  P7G_CHECK(launch_bwd(ctx, 0, prof, db->view(), b.d_idx, b.n, d_fx, d_xoff, b.d_sc, b.d_st, d_bx, d_tot));
+  if (ctx->fb_exact) P7G_CHECK(launch_fbx_bwd(ctx, 0, prof, db->view(), b.d_idx, b.n, d_fx, d_xoff, b.d_sc, b.d_st, d_bx, d_tot, d_own));
+  else               P7G_CHECK(launch_bwd(ctx, 0, prof, db->view(), b.d_idx, b.n, d_fx, d_xoff, b.d_sc, b.d_st, d_bx, d_tot, d_own));
   if (bck_xmx && ext) P7G_CUDA(cudaMemcpyAsync(bck_xmx, d_bx, sizeof(float) * ext, cudaMemcpyDeviceToHost, ctx->stream));
   if (bck_totscale && b.n) P7G_CUDA(cudaMemcpyAsync(bck_totscale, d_tot, sizeof(float) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
-  return fetch_batch(ctx, b, sc, status);
+  if (own_scales && b.n) P7G_CUDA(cudaMemcpyAsync(own_scales, d_own, sizeof(int32_t) * b.n, cudaMemcpyDeviceToHost, ctx->stream));
+  P7G_CHECK(fetch_batch(ctx, b, sc, status));
+  if (ctx->fb_exact && bck_xmx)                                        // fwdback.c:553,:689,:735 with the host libm
+    for (int64_t j = 0; j < b.n; j++) {
+      float t, s; int st;
+      fbx_host_bwd_score(bck_xmx + xmx_offsets[j], lens[j], &t, &s, &st);
+      if (sc) sc[j] = s; if (status) status[j] = st; if (bck_totscale) bck_totscale[j] = t;
+    }
+  return P7GPU_OK;
+}
+
+int p7gpu_backward_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_seqdb *db,
+                         const int64_t *idx, int64_t n, const float *fwd_xmx, const int64_t *xmx_offsets,
+                         float *sc, int32_t *status, float *bck_xmx, float *bck_totscale)
+{
+  return backward_batch_impl(ctx, prof, db, idx, n, fwd_xmx, xmx_offsets, sc, status, bck_xmx, bck_totscale, nullptr);
 }
 
 // The region trigger of p7_domaindef_ByPosteriorHeuristics for targets whose specials are on the host (decode.cu).
@@ -846,23 +958,40 @@ int p7gpu_ViterbiFilter(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_p
   P7G_CHECK(p7gpu_vitfilter_batch(ctx, om, one.db, nullptr, 1, ret_sc, &st));
   return st;
 }
+// the one-target parsers answer in the reference's own order of operations (bit-identical) unless option "fb_fast" is set
+struct ExactScope { p7gpu_ctx *c; int saved; explicit ExactScope(p7gpu_ctx *ctx) : c(ctx), saved(ctx->fb_exact) { if (!ctx->fb_fast) ctx->fb_exact = 1; } ~ExactScope() { c->fb_exact = saved; } };
+
 int p7gpu_ForwardParser(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
                         float *fwd_xmx, float *fwd_totscale, float *opt_sc)
 {
   OneSeq one; int32_t st = 0; float sc = 0; int64_t xoff = 0;
+  if (!ctx) return P7GPU_EINVAL;
   P7G_CHECK(one_seq_db(ctx, dsq, L, &one));
+  ExactScope ex(ctx);
+  std::vector<float> tmp;
+  if (!fwd_xmx && ctx->fb_exact) { tmp.resize((size_t) (L + 1) * P7GPU_NXCELLS); fwd_xmx = tmp.data(); }   // scores come from the specials
   P7G_CHECK(p7gpu_forward_batch(ctx, om, one.db, nullptr, 1, &sc, &st, fwd_xmx, fwd_xmx ? &xoff : nullptr, fwd_totscale));
   if (opt_sc) *opt_sc = sc;
+  return st;
+}
+int p7gpu_BackwardParser2(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
+                          const float *fwd_xmx, float *bck_xmx, float *bck_totscale, float *opt_sc, int *opt_own_scales)
+{
+  OneSeq one; int32_t st = 0, own = 0; float sc = 0; int64_t xoff = 0;
+  if (!ctx) return P7GPU_EINVAL;
+  P7G_CHECK(one_seq_db(ctx, dsq, L, &one));
+  ExactScope ex(ctx);
+  std::vector<float> tmp;
+  if (!bck_xmx && ctx->fb_exact) { tmp.resize((size_t) (L + 1) * P7GPU_NXCELLS); bck_xmx = tmp.data(); }
+  P7G_CHECK(backward_batch_impl(ctx, om, one.db, nullptr, 1, fwd_xmx, &xoff, &sc, &st, bck_xmx, bck_totscale, &own));
+  if (opt_sc) *opt_sc = sc;
+  if (opt_own_scales) *opt_own_scales = own;
   return st;
 }
 int p7gpu_BackwardParser(p7gpu_ctx *ctx, const uint8_t *dsq, int L, const p7gpu_profile *om,
                          const float *fwd_xmx, float *bck_xmx, float *bck_totscale, float *opt_sc)
 {
-  OneSeq one; int32_t st = 0; float sc = 0; int64_t xoff = 0;
-  P7G_CHECK(one_seq_db(ctx, dsq, L, &one));
-  P7G_CHECK(p7gpu_backward_batch(ctx, om, one.db, nullptr, 1, fwd_xmx, &xoff, &sc, &st, bck_xmx, bck_totscale));
-  if (opt_sc) *opt_sc = sc;
-  return st;
+  return p7gpu_BackwardParser2(ctx, dsq, L, om, fwd_xmx, bck_xmx, bck_totscale, opt_sc, nullptr);
 }
 
 float p7gpu_nullsc(int L) { return host_nullsc(L); }

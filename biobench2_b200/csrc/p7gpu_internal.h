@@ -107,6 +107,11 @@ struct p7gpu_ctx {
   int64_t      launches = 0;
   int          vit_exact_only = 0;      // option "vit_exact_only": skip the packed Viterbi fast path (tests)
   int          fb_one_warp = 0;         // option "fb_one_warp": Forward/Backward with the one-warp kernels even for long models (tests)
+  int          fb_exact = 0;            // option "fb_exact": p7gpu_forward_batch/p7gpu_backward_batch run the exact-order kernels (fbx.cu)
+  int          fb_fast = 0;             // option "fb_fast": the one-target wrappers p7gpu_ForwardParser/BackwardParser run the fast kernels
+  int          fbx_global = 0;          // option "fbx_global": exact-order kernels keep their DP row in global memory (diagnostic)
+  int          fbx_warps = 0;           // option "fbx_warps": resident warps per SM of the global-state variant (0 = auto)
+  void  *d_fbx_state = nullptr; size_t d_fbx_state_bytes = 0;   // fbx.cu: DP rows of the exact-order kernels for long models
   // growable scratch buffers (device + pinned host)
   void  *d_scratch = nullptr;  size_t d_scratch_bytes = 0;
   void  *h_pinned  = nullptr;  size_t h_pinned_bytes  = 0;
@@ -140,6 +145,10 @@ struct p7gpu_profile {
   int       mwC = 0, mwW = 0;            // cells per lane, warps per CTA
   float    *d_rf_mw = nullptr;         // [NTABROWS][mwC][32*mwW]  node k = g*mwC + j + 1
   float    *d_tf_mw = nullptr;         // [8][mwC][32*mwW]
+  // exact-order Forward/Backward (fbx.cu): the reference's striped values, re-laid out for load width only
+  int       fbxQ = 0, fbxQp = 0;       // Q = p7O_NQF(M); Qp = Q rounded up to a multiple of 4
+  float    *d_tfx = nullptr;           // [Q][4][8]: BM,MM,IM,DM,MD,MI,II,DD of vector q, element z
+  float    *d_rfx = nullptr;           // [NTABROWS][4][Qp]
   // bias-filter HMM (p7_bg_SetFilter), optional
   bool        have_bias = false;
   p7g::BiasHmm bias;
@@ -182,6 +191,7 @@ int ensure_len_table(const p7gpu_profile *prof, int Lmax, double F1 = -1.0);   /
 int ensure_scratch(p7gpu_ctx *ctx, size_t bytes);
 int ensure_scratch2(p7gpu_ctx *ctx, size_t bytes);
 int ensure_pinned(p7gpu_ctx *ctx, size_t bytes);
+int ensure_fbx_state(p7gpu_ctx *ctx, size_t bytes);
 int build_order(p7gpu_ctx *ctx, p7gpu_seqdb *db);
 
 // the reference's scalar score -> P-value arithmetic, host libm (p7_pipeline.c:691-730)
@@ -207,6 +217,16 @@ int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
 int launch_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                const float *d_fwd_xmx, const int64_t *d_xmx_off, float *d_sc, int32_t *d_status,
                float *d_bck_xmx, float *d_totscale, int32_t *d_own = nullptr);
+// fbx.cu: the two parsers in the reference's own order of float operations (bit-identical specials); same arguments
+int launch_fbx_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+                   float *d_sc, int32_t *d_status, float *d_xmx, const int64_t *d_xmx_off, float *d_totscale);
+int launch_fbx_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+                   const float *d_fwd_xmx, const int64_t *d_xmx_off, float *d_sc, int32_t *d_status,
+                   float *d_bck_xmx, float *d_totscale, int32_t *d_own);
+// host libm restatement of the two scores from the specials (fwdback.c:434,:463 / :553,:689,:735): totscale and score exactly as the
+// reference accumulates them; used whenever exact-order specials reach the host
+void fbx_host_fwd_score(const float *xmx, int L, float pmove, float *totscale, float *sc, int *status);
+void fbx_host_bwd_score(const float *xmx, int L, float *totscale, float *sc, int *status);
 // decode.cu: the region trigger of p7_domaindef_ByPosteriorHeuristics (max_i mocc[i] >= rt1) and the gather of selected specials
 int launch_region_trigger(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                           const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int32_t *d_own,

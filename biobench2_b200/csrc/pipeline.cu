@@ -52,7 +52,7 @@ struct p7gpu_pipeline_result {
   std::vector<p7gpu_survivor> survivors;
   RawFloats fwd_xmx, bck_xmx;
   std::vector<p7gpu_msv_survivor> msv_pass;       // only when opts->stop_after_msv
-  uint64_t stage_nres[5] = {0, 0, 0, 0, 0};       // residues seen by the MSV, bias, Viterbi, Forward, Backward stages
+  uint64_t stage_nres[6] = {0, 0, 0, 0, 0, 0};    // residues seen by the MSV, bias, Viterbi, Forward, Backward stages and the exact-order Forward recomputation
   uint64_t n_region_flagged = 0;                  // survivors whose specials were returned
 };
 
@@ -471,26 +471,63 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
 
   // ---- D + E. Forward parser, F3 test, Backward parser for the survivors (:727-735), in slices bounded by the
   //      size of the specials ((L+1)*6 floats per target and direction) ----
+  // opts->fb_exact: whatever reaches the host is computed by the exact-order kernels (fbx.cu), bit-identical to the reference.
+  // Under the default thresholds the fast Forward kernel first discards every candidate whose P-value cannot reach F3 even if
+  // its score were 2e-4 relative higher (the fast kernels are tested to 1e-4, measured 4e-6); what is left — the survivors and
+  // the few candidates next to the threshold — is recomputed exactly and decided on the exact score.
+  const bool exact = o->fb_exact != 0;
+  if (exact && F3 < 1.0 && !cand.empty()) {
+    const size_t n = cand.size();
+    std::vector<int64_t> idx(n);
+    for (size_t k = 0; k < n; k++) { idx[k] = cand[k].idx; res->stage_nres[3] += (uint64_t) cand[k].L; }
+    DevBuf d_idx, d_sc, d_stt;
+    P7G_CHECK(upload_idx(ctx, idx, &d_idx));
+    P7G_CHECK(d_sc.alloc(4 * n, st)); P7G_CHECK(d_stt.alloc(4 * n, st));
+    P7G_CHECK(launch_fwd(ctx, 0, prof, dbv, d_idx.as<int64_t>(), (int64_t) n, d_sc.as<float>(), d_stt.as<int32_t>(), nullptr, nullptr, nullptr));
+    std::vector<float> fsc(n);
+    P7G_CUDA(cudaMemcpyAsync(fsc.data(), d_sc.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    P7G_CUDA(cudaStreamSynchronize(st));
+    size_t w = 0;
+    for (size_t k = 0; k < n; k++) {
+      const float f = fsc[k];
+      const float hi = std::isfinite(f) ? f + 2e-4f * std::max(1.0f, std::fabs(f)) : f;
+      if (std::isfinite(f) && host_filter_pvalue_exp(hi, cand[k].filtersc, ev[4], ev[5]) > F3) continue;   // cannot pass
+      cand[w++] = cand[k];
+    }
+    cand.resize(w);
+    tr.mark("after_msv: forward prefilter (fast kernel)");
+  }
   const size_t slice_floats = (size_t) 1 << 29;                 // 2 GiB of forward specials per slice
   size_t host_floats = 0;
+  RawFloats exact_fx;                                           // exact mode, F3 < 1: the slice's forward specials on the host (scores)
   for (size_t lo = 0; lo < cand.size();) {
     size_t hi = lo, ext = 0;
     std::vector<int64_t> idx, xoff;
     while (hi < cand.size() && (hi == lo || ext + (size_t) (cand[hi].L + 1) * 6 <= slice_floats)) {
       idx.push_back(cand[hi].idx); xoff.push_back((int64_t) ext); ext += (size_t) (cand[hi].L + 1) * 6;
-      res->stage_nres[3] += (uint64_t) cand[hi].L; hi++;
+      res->stage_nres[exact && F3 < 1.0 ? 5 : 3] += (uint64_t) cand[hi].L; hi++;
     }
     const size_t n = hi - lo;
     DevBuf d_idx, d_xoff, d_sc, d_stt, d_tot, d_fx;
     P7G_CHECK(upload_idx(ctx, idx, &d_idx)); P7G_CHECK(upload_idx(ctx, xoff, &d_xoff));
     P7G_CHECK(d_sc.alloc(4 * n, st)); P7G_CHECK(d_stt.alloc(4 * n, st)); P7G_CHECK(d_tot.alloc(4 * n, st));
     P7G_CHECK(d_fx.alloc(4 * ext, st));
-    P7G_CHECK(launch_fwd(ctx, 0, prof, dbv, d_idx.as<int64_t>(), (int64_t) n, d_sc.as<float>(), d_stt.as<int32_t>(),
-                         d_fx.as<float>(), d_xoff.as<int64_t>(), d_tot.as<float>()));
+    if (exact) P7G_CHECK(launch_fbx_fwd(ctx, 0, prof, dbv, d_idx.as<int64_t>(), (int64_t) n, d_sc.as<float>(), d_stt.as<int32_t>(),
+                                        d_fx.as<float>(), d_xoff.as<int64_t>(), d_tot.as<float>()));
+    else       P7G_CHECK(launch_fwd(ctx, 0, prof, dbv, d_idx.as<int64_t>(), (int64_t) n, d_sc.as<float>(), d_stt.as<int32_t>(),
+                                    d_fx.as<float>(), d_xoff.as<int64_t>(), d_tot.as<float>()));
     std::vector<float> fsc(n), ftot(n);
     P7G_CUDA(cudaMemcpyAsync(fsc.data(), d_sc.p, 4 * n, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaMemcpyAsync(ftot.data(), d_tot.p, 4 * n, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaStreamSynchronize(st));
+    if (exact && F3 < 1.0) {                                     // the F3 test needs the exact score: host libm on the specials
+      if (!exact_fx.resize(ext)) { set_error("pipeline: out of host memory for %zu floats of specials", ext); return P7GPU_EMEM; }
+      P7G_CHECK(d2h_large(ctx, exact_fx.data(), d_fx.p, 4 * ext));
+      const LenConst *hl = prof->h_len.data();
+      parallel_for(n, [&](size_t a, size_t b) {
+        for (size_t k = a; k < b; k++) { int stt; fbx_host_fwd_score(exact_fx.data() + xoff[k], cand[lo + k].L, hl[cand[lo + k].L].pmove, &ftot[k], &fsc[k], &stt); }
+      });
+    }
     tr.mark("  slice: forward done");
     std::vector<int64_t> bidx, boff; std::vector<size_t> bwhere;
     for (size_t k = 0; k < n; k++) {
@@ -509,9 +546,12 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       P7G_CHECK(d_own.alloc(4 * nb, st));
       const bool keep_bx = o->want_specials || o->region_trigger;
       P7G_CHECK(d_bx.alloc(keep_bx ? 4 * ext : 256, st));
-      P7G_CHECK(launch_bwd(ctx, 0, prof, dbv, d_bidx.as<int64_t>(), (int64_t) nb, d_fx.as<float>(), d_boff.as<int64_t>(),
-                           d_bsc.as<float>(), d_bst.as<int32_t>(), keep_bx ? d_bx.as<float>() : nullptr, d_btot.as<float>(),
-                           d_own.as<int32_t>()));
+      if (exact) P7G_CHECK(launch_fbx_bwd(ctx, 0, prof, dbv, d_bidx.as<int64_t>(), (int64_t) nb, d_fx.as<float>(), d_boff.as<int64_t>(),
+                                          d_bsc.as<float>(), d_bst.as<int32_t>(), keep_bx ? d_bx.as<float>() : nullptr, d_btot.as<float>(),
+                                          d_own.as<int32_t>()));
+      else       P7G_CHECK(launch_bwd(ctx, 0, prof, dbv, d_bidx.as<int64_t>(), (int64_t) nb, d_fx.as<float>(), d_boff.as<int64_t>(),
+                                      d_bsc.as<float>(), d_bst.as<int32_t>(), keep_bx ? d_bx.as<float>() : nullptr, d_btot.as<float>(),
+                                      d_own.as<int32_t>()));
       std::vector<float> bsc(nb), btot(nb), mocc(nb, NAN); std::vector<int32_t> own(nb), flag(nb, -1);
       P7G_CUDA(cudaMemcpyAsync(bsc.data(), d_bsc.p, 4 * nb, cudaMemcpyDeviceToHost, st));
       P7G_CUDA(cudaMemcpyAsync(btot.data(), d_btot.p, 4 * nb, cudaMemcpyDeviceToHost, st));
@@ -562,6 +602,17 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
           P7G_CUDA(cudaStreamSynchronize(st));                       // the staging vectors and buffers die with this scope
         }
         P7G_CUDA(cudaStreamSynchronize(st));
+        if (exact) {                                                 // scores of what the host sees: its own libm on the specials
+          const LenConst *hl = prof->h_len.data();
+          parallel_for(nb, [&](size_t a, size_t b) {
+            for (size_t k = a; k < b; k++) {
+              if (host_off[k] < 0) continue;
+              Cand &c = cand[bwhere[k]]; int stt;
+              fbx_host_fwd_score(res->fwd_xmx.data() + host_off[k], c.L, hl[c.L].pmove, &c.ftot, &c.fwdsc, &stt);
+              fbx_host_bwd_score(res->bck_xmx.data() + host_off[k], c.L, &btot[k], &bsc[k], &stt);
+            }
+          });
+        }
       }
       tr.mark("  slice: specials on the host");
       for (size_t k = 0; k < nb; k++) {
@@ -904,6 +955,76 @@ int p7gpu_pipeline_run_host5(p7gpu_ctx *ctx, const p7gpu_profile *prof, const ui
 {
   if (nseq > 0 && !packed5) return P7GPU_EINVAL;
   return run_host_impl(ctx, prof, nullptr, packed5, nbytes, offsets, lengths, nseq, opts, ret_res);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Several GPUs from one C host (include/p7gpu.h section 9): contiguous shards balanced by residue count, one host thread and
+// one context per shard, no data-path exchange; the caller merges counters (p7gpu_counters_merge) and hit lists.
+// ------------------------------------------------------------------------------------------------------------------
+int p7gpu_shard_plan(const int64_t *offsets, const int32_t *lengths, int64_t nseq, int nshards, int64_t *first)
+{
+  if (nshards < 1 || nseq < 0 || !first || (nseq > 0 && (!offsets || !lengths))) return P7GPU_EINVAL;
+  first[0] = 0;
+  if (nseq == 0) { for (int k = 1; k <= nshards; k++) first[k] = 0; return P7GPU_OK; }
+  // offsets grow with the residues before a target (plus the same padding per target everywhere): cut them evenly
+  const int64_t lo0 = offsets[0], span = offsets[nseq - 1] + lengths[nseq - 1] - lo0;
+  for (int k = 1; k < nshards; k++) {
+    const int64_t want = lo0 + (int64_t) ((double) span * k / nshards);
+    int64_t lo = first[k - 1], hi = nseq;
+    while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (offsets[mid] < want) lo = mid + 1; else hi = mid; }
+    first[k] = lo;
+  }
+  first[nshards] = nseq;
+  return P7GPU_OK;
+}
+
+void p7gpu_counters_merge(p7gpu_pipeline_counters *into, const p7gpu_pipeline_counters *from)
+{
+  if (!into || !from) return;
+  into->nseqs += from->nseqs; into->nres += from->nres; into->n_past_msv += from->n_past_msv;
+  into->n_past_bias += from->n_past_bias; into->n_past_vit += from->n_past_vit; into->n_past_fwd += from->n_past_fwd;
+}
+
+int p7gpu_pipeline_run_sharded(p7gpu_ctx *const *ctxs, const p7gpu_profile *const *profs, int nshards,
+                               const uint8_t *residues, const uint8_t *packed5, int64_t nbytes,
+                               const int64_t *offsets, const int32_t *lengths, int64_t nseq,
+                               const p7gpu_pipeline_opts *opts, int64_t *first, p7gpu_pipeline_result **ret_res)
+{
+  if (!ctxs || !profs || nshards < 1 || !opts || !first || !ret_res || nseq < 0 || (nseq > 0 && ((!residues && !packed5) || !offsets || !lengths))) return P7GPU_EINVAL;
+  for (int k = 0; k < nshards; k++) { ret_res[k] = nullptr; if (!ctxs[k] || !profs[k] || profs[k]->ctx != ctxs[k]) { set_error("run_sharded: shard %d: profile and context do not belong together", k); return P7GPU_EINVAL; } }
+  P7G_CHECK(p7gpu_shard_plan(offsets, lengths, nseq, nshards, first));
+  std::vector<int> rc((size_t) nshards, P7GPU_OK);
+  std::vector<std::string> err((size_t) nshards);
+  auto work = [&](int k) {
+    const int64_t s_lo = first[k], s_hi = first[k + 1], cn = s_hi - s_lo;
+    if (cn == 0) { rc[k] = run_host_impl(ctxs[k], profs[k], residues, packed5, 0, nullptr, nullptr, 0, opts, &ret_res[k]); return; }
+    // the shard's slice of the packed array starts on a 64-byte boundary at or before its first target's leading sentinel
+    // (64 bytes = one group of the 5-bit transfer format; the kernels' 16-byte residue vectors keep their alignment)
+    const int64_t base = (offsets[s_lo] - 1) & ~(int64_t) 63;
+    const int64_t end  = std::min<int64_t>(nbytes, offsets[s_hi - 1] + lengths[s_hi - 1] + 1);
+    std::vector<int64_t> off((size_t) cn);
+    for (int64_t j = 0; j < cn; j++) off[(size_t) j] = offsets[s_lo + j] - base;
+    if (off[0] < 1) { err[k] = "run_sharded: no sentinel byte before the shard's first target"; rc[k] = P7GPU_EINVAL; return; }
+    rc[k] = run_host_impl(ctxs[k], profs[k], residues ? residues + base : nullptr, packed5 ? packed5 + base / 64 * 40 : nullptr, end - base,
+                          off.data(), lengths + s_lo, cn, opts, &ret_res[k]);
+    if (rc[k] != P7GPU_OK) { err[k] = p7gpu_last_error(); return; }
+    p7gpu_pipeline_result *r = ret_res[k];                           // shard numbering -> database numbering
+    for (auto &sv : r->survivors) sv.seqidx += s_lo;
+    for (auto &mv : r->msv_pass) mv.seqidx += s_lo;
+  };
+  if (nshards == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int k = 0; k < nshards; k++) th.emplace_back(work, k);
+    for (auto &t : th) t.join();
+  }
+  for (int k = 0; k < nshards; k++)
+    if (rc[k] != P7GPU_OK) {
+      set_error("%s", err[k].c_str());
+      for (int j = 0; j < nshards; j++) { p7gpu_result_destroy(ret_res[j]); ret_res[j] = nullptr; }
+      return rc[k];
+    }
+  return P7GPU_OK;
 }
 
 // Diagnostic: the float threshold the device-side stage decisions use for "P(seq_score) > F" (kind 0: esl_gumbel_surv with

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libp7gpu.so")
 
 OK, EMEM, EINVAL, ESYS, ERANGE, ENORESULT = 0, 5, 11, 12, 16, 19
-KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD, KERNEL_BIAS, KERNEL_TRIG = range(7)
+KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD, KERNEL_BIAS, KERNEL_TRIG, KERNEL_FWDX, KERNEL_BWDX = range(9)
 
 EXPORTS = [
     "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
@@ -23,13 +23,14 @@ EXPORTS = [
     "p7gpu_seqdb_upload", "p7gpu_seqdb_adopt_device", "p7gpu_seqdb_destroy", "p7gpu_seqdb_nseq", "p7gpu_seqdb_nres",
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
     "p7gpu_backward_batch", "p7gpu_region_trigger_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
-    "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser",
+    "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser", "p7gpu_BackwardParser2",
     "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_stage_threshold", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
     "p7gpu_dbfile_from_fasta", "p7gpu_dbfile_open", "p7gpu_dbfile_close", "p7gpu_dbfile_nseq", "p7gpu_dbfile_nres",
     "p7gpu_dbfile_nbytes", "p7gpu_dbfile_maxlength", "p7gpu_dbfile_residues", "p7gpu_dbfile_offsets", "p7gpu_dbfile_lengths",
     "p7gpu_dbfile_name", "p7gpu_dbfile_desc", "p7gpu_dbfile_pin", "p7gpu_pipeline_run_file",
+    "p7gpu_shard_plan", "p7gpu_pipeline_run_sharded", "p7gpu_pipeline_run_file_sharded", "p7gpu_counters_merge",
 ]
 
 
@@ -42,7 +43,7 @@ class P7GpuError(RuntimeError):
 class PipelineOpts(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double),
                 ("do_biasfilter", C.c_int32), ("do_max", C.c_int32), ("want_specials", C.c_int32),
-                ("stop_after_msv", C.c_int32), ("region_trigger", C.c_int32), ("reserved", C.c_int32)]
+                ("stop_after_msv", C.c_int32), ("region_trigger", C.c_int32), ("fb_exact", C.c_int32)]
 
 
 class MsvSurvivor(C.Structure):
@@ -124,7 +125,13 @@ def lib():
             getattr(L, nm).argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
         L.p7gpu_ForwardParser.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.p7gpu_BackwardParser.argtypes = [vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.p7gpu_BackwardParser2.argtypes = [vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.p7gpu_pipeline_run.argtypes = [vp, vp, vp, C.POINTER(PipelineOpts), C.POINTER(vp)]
+        L.p7gpu_shard_plan.argtypes = [vp, vp, i64, C.c_int, vp]
+        L.p7gpu_pipeline_run_sharded.argtypes = [vp, vp, C.c_int, vp, vp, i64, vp, vp, i64, C.POINTER(PipelineOpts), vp, vp]
+        L.p7gpu_pipeline_run_file_sharded.argtypes = [vp, vp, C.c_int, vp, C.POINTER(PipelineOpts), vp, vp]
+        L.p7gpu_counters_merge.argtypes = [C.POINTER(PipelineCounters), C.POINTER(PipelineCounters)]
+        L.p7gpu_counters_merge.restype = None
         L.p7gpu_dbfile_from_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]
         L.p7gpu_dbfile_open.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.p7gpu_dbfile_close.argtypes = [vp]
@@ -414,7 +421,7 @@ class PipelineResult:
         c = L.p7gpu_result_counters(h).contents
         self.counters = np.array([c.nseqs, c.nres, c.n_past_msv, c.n_past_bias, c.n_past_vit, c.n_past_fwd], np.uint64)
         sr = L.p7gpu_result_stage_residues(h)
-        self.stage_residues = {k: int(sr[i]) for i, k in enumerate(("msv", "bias", "vit", "fwd", "bwd"))}
+        self.stage_residues = {k: int(sr[i]) for i, k in enumerate(("msv", "bias", "vit", "fwd", "bwd", "fwdx"))}
         n = L.p7gpu_result_nsurvivors(h)      # one structured array (a --max run returns millions of records)
         self.survivors = _view(L.p7gpu_result_survivors(h), n * C.sizeof(Survivor), SURVIVOR_NP, own) if n else np.zeros(0, SURVIVOR_NP)
         have = self.survivors["xmx_offset"] >= 0
@@ -436,23 +443,23 @@ class PipelineResult:
 MSV_NP = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")])
 
 
-def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger=False):
-    return PipelineOpts(F1, F2, F3, int(do_biasfilter), int(do_max), int(want_specials), int(stop_after_msv), int(region_trigger), 0)
+def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger=False, fb_exact=False):
+    return PipelineOpts(F1, F2, F3, int(do_biasfilter), int(do_max), int(want_specials), int(stop_after_msv), int(region_trigger), int(fb_exact))
 
 
 def pipeline_run(ctx, prof, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                 stop_after_msv=False, region_trigger=False):
+                 stop_after_msv=False, region_trigger=False, fb_exact=False):
     """The batched p7_Pipeline() over a resident database (defaults: p7_pipeline.c:214-216)."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run(ctx.h, prof.h, db.h, C.byref(o), C.byref(h)))
     return PipelineResult(h)
 
 
 def pipeline_run_many(ctx, profs, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False):
     """Many profiles against one resident database (p7gpu_pipeline_run_many) -> list of PipelineResult."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
     n = len(profs)
     ph = (C.c_void_p * n)(*[p.h for p in profs])
     rh = (C.c_void_p * n)()
@@ -461,9 +468,9 @@ def pipeline_run_many(ctx, profs, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=T
 
 
 def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False):
     """Same for a HOST PackedDB: the upload is streamed under the MSV stage."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
                                          _p(packed.lengths), packed.nseq, C.byref(o), C.byref(h)))
@@ -492,9 +499,9 @@ def pack5(residues, out=None, nthreads=0):
 
 
 def pipeline_run_host5(ctx, prof, packed5, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                       stop_after_msv=False, region_trigger=False):
+                       stop_after_msv=False, region_trigger=False, fb_exact=False):
     """pipeline_run_host with the residues in the 5-bit transfer format; `packed` supplies offsets, lengths and the unpacked size."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host5(ctx.h, prof.h, _p(packed5), packed.residues.shape[0], _p(packed.offsets), _p(packed.lengths),
                                           packed.nseq, C.byref(o), C.byref(h)))
@@ -539,12 +546,46 @@ class DbFile:
 
 
 def pipeline_run_file(ctx, prof, dbfile, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False):
     """The batched pipeline over a mapped packed database file (p7gpu_pipeline_run_file)."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_file(ctx.h, prof.h, dbfile.h, C.byref(o), C.byref(h)))
     return PipelineResult(h)
+
+
+def shard_plan(packed, nshards):
+    """Contiguous shards balanced by residue count (p7gpu_shard_plan) -> int64[nshards + 1] boundaries."""
+    first = np.zeros(nshards + 1, np.int64)
+    _check(lib().p7gpu_shard_plan(_p(packed.offsets), _p(packed.lengths), packed.nseq, nshards, _p(first)))
+    return first
+
+
+def merge_counters(results):
+    """Sum of the shards' P7_PIPELINE counters (p7gpu_counters_merge == p7_pipeline_Merge, p7_pipeline.c:597-636)."""
+    tot = PipelineCounters()
+    for r in results:
+        c = PipelineCounters(*[int(x) for x in r.counters])
+        lib().p7gpu_counters_merge(C.byref(tot), C.byref(c))
+    return np.array([tot.nseqs, tot.nres, tot.n_past_msv, tot.n_past_bias, tot.n_past_vit, tot.n_past_fwd], np.uint64)
+
+
+def pipeline_run_sharded(ctxs, profs, packed, packed5=None, dbfile=None, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False,
+                         want_specials=True, stop_after_msv=False, region_trigger=False, fb_exact=False):
+    """One HOST database over several GPUs of this process: one context, one contiguous shard and one host thread per GPU
+    (p7gpu_pipeline_run_sharded / _file_sharded).  Returns (first[nshards+1], [PipelineResult per shard]); survivor seqidx are
+    database indices.  Merge like the reference merges its workers: merge_counters() + the hit lists through p7_tophits_Merge."""
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
+    n = len(ctxs)
+    ch = (C.c_void_p * n)(*[c.h for c in ctxs]); ph = (C.c_void_p * n)(*[p.h for p in profs]); rh = (C.c_void_p * n)()
+    first = np.zeros(n + 1, np.int64)
+    if dbfile is not None:
+        _check(lib().p7gpu_pipeline_run_file_sharded(ch, ph, n, dbfile.h, C.byref(o), _p(first), rh))
+    else:
+        _check(lib().p7gpu_pipeline_run_sharded(ch, ph, n, _p(packed.residues) if packed5 is None else None, _p(packed5),
+                                                packed.residues.shape[0], _p(packed.offsets), _p(packed.lengths), packed.nseq,
+                                                C.byref(o), _p(first), rh))
+    return first, [PipelineResult(C.c_void_p(rh[i])) for i in range(n)]
 
 
 # ---- signature-level wrappers (one target per call), same meaning as impl_sse.h:309-344 ----
@@ -572,12 +613,17 @@ def p7_ForwardParser(ctx, dsq, L, om):
     return st, np.float32(sc.value), xmx, np.float32(tot.value)
 
 
-def p7_BackwardParser(ctx, dsq, L, om, fwd_xmx):
-    sc = C.c_float(0); tot = C.c_float(0)
+def p7_BackwardParser(ctx, dsq, L, om, fwd_xmx, want_own=False):
+    sc = C.c_float(0); tot = C.c_float(0); own = C.c_int(0)
     bx = np.zeros((L + 1, 6), np.float32)
     dsq = np.ascontiguousarray(dsq, np.uint8)
     fwd_xmx = np.ascontiguousarray(fwd_xmx, np.float32)
-    st = lib().p7gpu_BackwardParser(ctx.h, _p(dsq), L, om.h, _p(fwd_xmx), _p(bx), C.byref(tot), C.byref(sc))
+    if want_own:
+        st = lib().p7gpu_BackwardParser2(ctx.h, _p(dsq), L, om.h, _p(fwd_xmx), _p(bx), C.byref(tot), C.byref(sc), C.byref(own))
+    else:
+        st = lib().p7gpu_BackwardParser(ctx.h, _p(dsq), L, om.h, _p(fwd_xmx), _p(bx), C.byref(tot), C.byref(sc))
     if st not in (OK, ERANGE):
         _check(st)
+    if want_own:
+        return st, np.float32(sc.value), bx, np.float32(tot.value), own.value
     return st, np.float32(sc.value), bx, np.float32(tot.value)

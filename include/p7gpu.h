@@ -83,7 +83,9 @@ int         p7gpu_ctx_set_stream(p7gpu_ctx *ctx, void *cuda_stream);
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches claim) */
 int64_t     p7gpu_ctx_launch_count(const p7gpu_ctx *ctx);
 int         p7gpu_ctx_synchronize(p7gpu_ctx *ctx);
-/* engine options (no reference counterpart).  "vit_exact_only"=1: p7gpu_vitfilter_* skips the packed 2 x int16 fast
+/* engine options (no reference counterpart).  "fb_exact"=1: p7gpu_forward_batch/p7gpu_backward_batch run the exact-order kernels
+ * (csrc/fbx.cu: bit-identical to the reference); "fb_fast"=1: the one-target wrappers run the fast kernels instead of the
+ * exact-order ones; "fbx_global", "fbx_warps": where the exact-order kernels keep their DP row (diagnostics).  "vit_exact_only"=1: p7gpu_vitfilter_* skips the packed 2 x int16 fast
  * path and runs the exact 32-bit kernel on every target (the two must agree bit for bit; tests use this). */
 int         p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value);
 /* how many targets of the last Viterbi launch on the ctx's main stream left the packed kernel's window and were
@@ -101,7 +103,9 @@ int64_t     p7gpu_ctx_last_vit_redo(p7gpu_ctx *ctx);
 #define P7GPU_KERNEL_BWD  4
 #define P7GPU_KERNEL_BIAS 5
 #define P7GPU_KERNEL_TRIG 6
-#define P7GPU_NKERNELS    7
+#define P7GPU_KERNEL_FWDX 7   /* exact-order Forward (csrc/fbx.cu) */
+#define P7GPU_KERNEL_BWDX 8   /* exact-order Backward */
+#define P7GPU_NKERNELS    9
 int         p7gpu_ctx_set_timing  (p7gpu_ctx *ctx, int on);
 int         p7gpu_ctx_reset_timing(p7gpu_ctx *ctx);
 int         p7gpu_ctx_kernel_time (p7gpu_ctx *ctx, int kind, double *ms_total, int64_t *nlaunches);
@@ -285,7 +289,8 @@ int  p7gpu_pack5(const uint8_t *residues, int64_t nbytes, uint8_t *out, int nthr
 int  p7gpu_pipeline_run_host5(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *packed5, int64_t nbytes,
                               const int64_t *offsets, const int32_t *lengths, int64_t nseq,
                               const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
-/* residues seen by each stage {MSV, bias, Viterbi, Forward, Backward}: the denominators of per-stage cells/s
+/* residues seen by each stage {MSV, bias, Viterbi, Forward, Backward, exact-order Forward recomputation (fb_exact under the default
+ * thresholds; 0 otherwise)}: the denominators of per-stage cells/s
  * (the reference reports one Mc/s figure for the whole pipeline, p7_pipeline.c:1789-1793) */
 const uint64_t                *p7gpu_result_stage_residues(const p7gpu_pipeline_result *res);
 int64_t                        p7gpu_result_nmsvpass  (const p7gpu_pipeline_result *res);

@@ -302,7 +302,10 @@ main(int argc, char **argv)
   if (db) p7gpu_dbfile_close(db);
   p7_bg_Destroy(bg);  p7_hmmfile_Close(hfp);  esl_alphabet_Destroy(abc);  esl_stopwatch_Destroy(w);
   if (ofp != stdout) fclose(ofp);
-  if (afp) fclose(afp);  if (tblfp) fclose(tblfp);  if (domtblfp) fclose(domtblfp);  if (pfamtblfp) fclose(pfamtblfp);
+  if (afp)       fclose(afp);
+  if (tblfp)     fclose(tblfp);
+  if (domtblfp)  fclose(domtblfp);
+  if (pfamtblfp) fclose(pfamtblfp);
   esl_getopts_Destroy(go);
   return eslOK;
 
