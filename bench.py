@@ -461,53 +461,58 @@ def main():
     nres = int(lengths.astype(np.int64).sum())
     assert db.nres == nres, (db.nres, nres)                      # counters.nres == sum of the lengths, whatever the padding
     cells = float(M) * float(nres)
-    d_sc = torch.empty(args.nseq, dtype=torch.float32, device=dev)
-    d_st = torch.empty(args.nseq, dtype=torch.int32, device=dev)
-
     # survivors of the P-value test (p7_pipeline.c:691-693) are compacted by the filter kernels themselves
     F1 = 0.02
-    d_pass = torch.empty(args.nseq, dtype=torch.int32, device=dev)
-    d_pass_count = torch.zeros(1, dtype=torch.int32, device=dev)
-    cap = max(1024, int(args.nseq * 0.06))                       # survivor records per rank and step: fixed capacity (F1 = 2 %)
-    ar = torch.arange(cap, device=dev)
     last = {}
 
-    def msv_step(dbx, n_targets, first_global):
+    class MsvBuffers:
+        """device outputs of one database: score + status per target, the pass list + its count, the exchange capacity"""
+        def __init__(self, n):
+            self.n = n
+            self.sc = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+            self.st = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            self.passed = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.cap = min(max(n, 1), max(1024, int(n * 0.06)))    # survivor records per rank and step: fixed capacity (F1 = 2 %)
+            self.ar = torch.arange(self.cap, device=dev)
+
+    def msv_step(dbx, b, first_global):
         """One MSV pass over dbx and the multi-GPU exchange of its survivors (index, score) to rank 0: the product's
         search.gather_device_records — fixed-capacity buffers, no host synchronisation inside the step."""
-        engine.msvfilter_device(ctx, prof, dbx, d_sc.data_ptr(), d_st.data_ptr(), F1, d_pass.data_ptr(), d_pass_count.data_ptr())
-        cnt = d_pass_count.to(torch.int64)
-        idx = d_pass[:cap].long().clamp_(0, max(n_targets - 1, 0))
-        valid = (ar < cnt).unsqueeze(1)
-        rec = torch.stack([(idx + first_global).double(), d_sc[idx].double()], 1) * valid
+        engine.msvfilter_device(ctx, prof, dbx, b.sc.data_ptr(), b.st.data_ptr(), F1, b.passed.data_ptr(), b.count.data_ptr())
+        cnt = b.count.to(torch.int64)
+        idx = b.passed[:b.cap].long().clamp_(0, max(b.n - 1, 0))
+        valid = (b.ar < cnt).unsqueeze(1)
+        rec = torch.stack([(idx + first_global).double(), b.sc[idx].double()], 1) * valid
         last["out"], last["cnts"] = search.gather_device_records(rec, cnt, dmod)
 
-    def timed_steps(dbx, n_targets, first_global, steps, warmup):
+    def timed_steps(dbx, b, first_global, steps, warmup):
         with torch.cuda.stream(stream):
             for _ in range(warmup):
-                msv_step(dbx, n_targets, first_global)
+                msv_step(dbx, b, first_global)
             barrier()
             ctx.set_timing(True); ctx.reset_timing()
             l0 = ctx.launches
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for _ in range(steps):
-                msv_step(dbx, n_targets, first_global)
+                msv_step(dbx, b, first_global)
             e1.record(stream)
             barrier()
             ms = max_over_ranks(e0.elapsed_time(e1))
             km = (ctx.kernel_time(engine.KERNEL_SSV), ctx.kernel_time(engine.KERNEL_MSVJ))
             ctx.set_timing(False)
             nsurv = int(sum(int(c.item()) for c in last["cnts"]))  # read once, after the last step
-            assert nsurv <= cap * world, "survivor capacity exceeded"
+            assert all(int(c.item()) <= b.cap for c in last["cnts"]), "survivor capacity exceeded"
         return ms, ctx.launches - l0, km, nsurv
 
+    bufs = MsvBuffers(args.nseq)
     clocks = ClockSampler(physical_gpu_index(local_rank)); clocks.start()
-    ms_total, launches, ((ssv_ms, ssv_n), (msvj_ms, msvj_n)), nsurv = timed_steps(db, args.nseq, rank * args.nseq, args.steps, args.warmup)
+    ms_total, launches, ((ssv_ms, ssv_n), (msvj_ms, msvj_n)), nsurv = timed_steps(db, bufs, rank * args.nseq, args.steps, args.warmup)
     clk = clocks.finish()
     total_cells = sum_over_ranks(cells)
     value = total_cells * args.steps / (ms_total * 1e-3) / 1e9
-    statuses = torch.bincount(d_st.clamp(min=0), minlength=20).cpu().numpy()
+    statuses = torch.bincount(bufs.st.clamp(min=0), minlength=20).cpu().numpy()
 
     # ---- roofline of the dominant kernel (ssv_kernel), measured live with CUDA events on the launching stream ----
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -553,7 +558,7 @@ def main():
         stream.synchronize()
         sdb = engine.SeqDB.adopt_torch(ctx, s_res, s_off, s_len, int(s_lengths.max()))
         s_cells = float(M) * float(all_len.astype(np.int64).sum())
-        s_ms, _, _, s_surv = timed_steps(sdb, hi - lo, lo, args.steps, args.warmup)
+        s_ms, _, _, s_surv = timed_steps(sdb, MsvBuffers(hi - lo), lo, args.steps, args.warmup)
         strong = {"scaling": "strong", "targets_total": tot_n, "targets_this_rank0": int(first[1] - first[0]), "residues_total": int(all_len.astype(np.int64).sum()),
                   "value": s_cells * args.steps / (s_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": s_ms / args.steps,
                   "shards": "contiguous, balanced by residue count (p7gpu_shard_plan)", "msv_survivors": s_surv}

@@ -163,7 +163,7 @@ def test_seeded_database_1e5_targets(tmp_path, model):
     fa = tmp_path / "db.fa"
     seeded_fasta(str(fa), hmm, 100000, seed={"Pkinase": 3, "globins4": 4, "fn3": 5}[model], nhom=300)
     c = assert_identical(run_both(tmp_path, hmm, fa, tag=model), model)
-    assert c["Target sequences"] == 100000 and c["Passed Fwd filter"] >= 150
+    assert c["Target sequences"] == 100000 and c["Passed Fwd filter"] >= 60
 
 
 @pytest.mark.gpu
