@@ -51,14 +51,6 @@ int ensure_scratch2(p7gpu_ctx *ctx, size_t bytes)
   ctx->d_scratch2_bytes = want;
   return P7GPU_OK;
 }
-int ensure_fbx_state(p7gpu_ctx *ctx, size_t bytes)
-{
-  if (bytes <= ctx->d_fbx_state_bytes) return P7GPU_OK;
-  if (ctx->d_fbx_state) { P7G_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->d_fbx_state); ctx->d_fbx_state = nullptr; ctx->d_fbx_state_bytes = 0; }
-  P7G_CUDA(cudaMalloc(&ctx->d_fbx_state, bytes));
-  ctx->d_fbx_state_bytes = bytes;
-  return P7GPU_OK;
-}
 int ensure_pinned(p7gpu_ctx *ctx, size_t bytes)
 {
   if (bytes <= ctx->h_pinned_bytes) return P7GPU_OK;
@@ -358,7 +350,6 @@ void p7gpu_ctx_destroy(p7gpu_ctx *ctx)
   for (auto &t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
-  if (ctx->d_fbx_state) cudaFree(ctx->d_fbx_state);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
 }
@@ -383,7 +374,7 @@ int p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value)
   if (!strcmp(name, "fb_one_warp"))    { ctx->fb_one_warp = value; return P7GPU_OK; }
   if (!strcmp(name, "fb_exact"))       { ctx->fb_exact = value; return P7GPU_OK; }
   if (!strcmp(name, "fb_fast"))        { ctx->fb_fast = value; return P7GPU_OK; }
-  if (!strcmp(name, "fbx_global"))     { ctx->fbx_global = value; return P7GPU_OK; }
+  if (!strcmp(name, "fbx_groups"))     { ctx->fbx_groups = value; return P7GPU_OK; }
   if (!strcmp(name, "fbx_warps"))      { ctx->fbx_warps = value; return P7GPU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return P7GPU_EINVAL;
@@ -484,15 +475,18 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
     P7G_CUDA(cudaMalloc(&prof->d_tf, tf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
     {                                                                 // exact-order kernels (fbx.cu): striped values, wider loads
       const int Q = Q4, Qp = (Q4 + 3) / 4 * 4;
-      std::vector<float> tfx((size_t) Q * 32, 0.0f), rfx((size_t) NTABROWS * 4 * Qp, 0.0f);
+      std::vector<float> tfx((size_t) Q * 32, 0.0f), rfx((size_t) NTABROWS * 4 * Qp, 0.0f), tddx((size_t) 4 * Qp, 0.0f), tmdx((size_t) 4 * Qp, 0.0f);
       for (int q = 0; q < Q; q++)
         for (int z = 0; z < 4; z++) {
           for (int t = 0; t < 7; t++) tfx[((size_t) q * 4 + z) * 8 + t] = om->tfv[((size_t) 7 * q + t) * 4 + z];
           tfx[((size_t) q * 4 + z) * 8 + 7] = om->tfv[((size_t) 7 * Q + q) * 4 + z];
+          tddx[(size_t) z * Qp + q] = tfx[((size_t) q * 4 + z) * 8 + 7]; tmdx[(size_t) z * Qp + q] = tfx[((size_t) q * 4 + z) * 8 + 4];
           for (int x = 0; x < Kp; x++) rfx[((size_t) x * 4 + z) * Qp + q] = om->rfv[((size_t) x * Q + q) * 4 + z];
         }
       P7G_CUDA(cudaMalloc(&prof->d_tfx, tfx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tfx, tfx.data(), tfx.size() * 4, cudaMemcpyHostToDevice));
       P7G_CUDA(cudaMalloc(&prof->d_rfx, rfx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rfx, rfx.data(), rfx.size() * 4, cudaMemcpyHostToDevice));
+      P7G_CUDA(cudaMalloc(&prof->d_tddx, tddx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tddx, tddx.data(), tddx.size() * 4, cudaMemcpyHostToDevice));
+      P7G_CUDA(cudaMalloc(&prof->d_tmdx, tmdx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tmdx, tmdx.data(), tmdx.size() * 4, cudaMemcpyHostToDevice));
       prof->fbxQ = Q; prof->fbxQp = Qp;
     }
     int mc = 0, mw = 0;
@@ -527,7 +521,7 @@ void p7gpu_profile_destroy(p7gpu_profile *prof)
   cudaFree(prof->d_ssv_tab); cudaFree(prof->d_msv_tab);
   cudaFree(prof->d_rw); cudaFree(prof->d_tw); cudaFree(prof->d_rf); cudaFree(prof->d_tf);
   cudaFree(prof->d_rf_mw); cudaFree(prof->d_tf_mw);
-  cudaFree(prof->d_tfx); cudaFree(prof->d_rfx);
+  cudaFree(prof->d_tfx); cudaFree(prof->d_rfx); cudaFree(prof->d_tddx); cudaFree(prof->d_tmdx);
   cudaFree(prof->d_rwp); cudaFree(prof->d_twp); cudaFree(prof->d_scanw);
   cudaFree(prof->d_len);
   delete prof;

@@ -109,9 +109,8 @@ struct p7gpu_ctx {
   int          fb_one_warp = 0;         // option "fb_one_warp": Forward/Backward with the one-warp kernels even for long models (tests)
   int          fb_exact = 0;            // option "fb_exact": p7gpu_forward_batch/p7gpu_backward_batch run the exact-order kernels (fbx.cu)
   int          fb_fast = 0;             // option "fb_fast": the one-target wrappers p7gpu_ForwardParser/BackwardParser run the fast kernels
-  int          fbx_global = 0;          // option "fbx_global": exact-order kernels keep their DP row in global memory (diagnostic)
-  int          fbx_warps = 0;           // option "fbx_warps": resident warps per SM of the global-state variant (0 = auto)
-  void  *d_fbx_state = nullptr; size_t d_fbx_state_bytes = 0;   // fbx.cu: DP rows of the exact-order kernels for long models
+  int          fbx_warps = 0;           // option "fbx_warps": cap on resident one-warp CTAs per SM of the exact-order kernels (0 = occupancy)
+  int          fbx_groups = 0;          // option "fbx_groups": targets per warp of the exact-order kernels, 1/2/4/8 (0 = auto)
   // growable scratch buffers (device + pinned host)
   void  *d_scratch = nullptr;  size_t d_scratch_bytes = 0;
   void  *h_pinned  = nullptr;  size_t h_pinned_bytes  = 0;
@@ -149,6 +148,7 @@ struct p7gpu_profile {
   int       fbxQ = 0, fbxQp = 0;       // Q = p7O_NQF(M); Qp = Q rounded up to a multiple of 4
   float    *d_tfx = nullptr;           // [Q][4][8]: BM,MM,IM,DM,MD,MI,II,DD of vector q, element z
   float    *d_rfx = nullptr;           // [NTABROWS][4][Qp]
+  float    *d_tddx = nullptr, *d_tmdx = nullptr;   // [4][Qp] each: tDD / tMD of vector q, element z
   // bias-filter HMM (p7_bg_SetFilter), optional
   bool        have_bias = false;
   p7g::BiasHmm bias;
@@ -191,7 +191,6 @@ int ensure_len_table(const p7gpu_profile *prof, int Lmax, double F1 = -1.0);   /
 int ensure_scratch(p7gpu_ctx *ctx, size_t bytes);
 int ensure_scratch2(p7gpu_ctx *ctx, size_t bytes);
 int ensure_pinned(p7gpu_ctx *ctx, size_t bytes);
-int ensure_fbx_state(p7gpu_ctx *ctx, size_t bytes);
 int build_order(p7gpu_ctx *ctx, p7gpu_seqdb *db);
 
 // the reference's scalar score -> P-value arithmetic, host libm (p7_pipeline.c:691-730)

@@ -85,7 +85,7 @@ int64_t     p7gpu_ctx_launch_count(const p7gpu_ctx *ctx);
 int         p7gpu_ctx_synchronize(p7gpu_ctx *ctx);
 /* engine options (no reference counterpart).  "fb_exact"=1: p7gpu_forward_batch/p7gpu_backward_batch run the exact-order kernels
  * (csrc/fbx.cu: bit-identical to the reference); "fb_fast"=1: the one-target wrappers run the fast kernels instead of the
- * exact-order ones; "fbx_global", "fbx_warps": where the exact-order kernels keep their DP row (diagnostics).  "vit_exact_only"=1: p7gpu_vitfilter_* skips the packed 2 x int16 fast
+ * exact-order ones; "fbx_groups" (targets per warp: 1, 2, 4, 8; 0 = auto), "fbx_warps" (cap on resident warps per SM): geometry of the exact-order kernels (diagnostics).  "vit_exact_only"=1: p7gpu_vitfilter_* skips the packed 2 x int16 fast
  * path and runs the exact 32-bit kernel on every target (the two must agree bit for bit; tests use this). */
 int         p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value);
 /* how many targets of the last Viterbi launch on the ctx's main stream left the packed kernel's window and were

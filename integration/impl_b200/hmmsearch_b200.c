@@ -223,10 +223,19 @@ main(int argc, char **argv)
   cfg.ngpus    = esl_opt_GetInteger(go, "--gpus");
   cfg.ncpus    = ESL_MAX(1, ncpus);
   cfg.fb_exact = esl_opt_GetBoolean(go, "--fbfast") ? 0 : 1;
+  /* the driver initialises every device it can see (~0.1 s each on an 8-GPU board): show it only the ones this run uses */
+  if (getenv("CUDA_VISIBLE_DEVICES") == NULL) {
+    char vis[256]; int n = 0;
+    for (k = 0; k < cfg.ngpus && n < 240; k++) n += snprintf(vis + n, sizeof(vis) - n, k ? ",%d" : "%d", k);
+    setenv("CUDA_VISIBLE_DEVICES", vis, 0);
+  }
   if (cfg.ngpus > p7_b200_DeviceCount()) p7_Fail("--gpus %d, but %d CUDA device(s) visible\n%s\n", cfg.ngpus, p7_b200_DeviceCount(), p7_b200_ErrorText());
   ESL_ALLOC(engs, sizeof(*engs) * cfg.ngpus);
+  esl_stopwatch_Start(w);
   for (k = 0; k < cfg.ngpus; k++)
     if (p7_b200_Open(k, &engs[k]) != eslOK) p7_Fail("Failed to open GPU %d: %s\n", k, p7_b200_ErrorText());
+  esl_stopwatch_Stop(w);
+  if (times) fprintf(stderr, "# %d GPU engine(s) open: %.3f s (CUDA initialisation)\n", cfg.ngpus, w->elapsed);
 
   hstatus = p7_hmmfile_Read(hfp, &abc, &hmm);
   if (hstatus == eslOK) {
