@@ -98,4 +98,71 @@ int launch_gather_xmx(p7gpu_ctx *ctx, int lane, const float *d_fx, const float *
   return P7GPU_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// p7_DomainDecoding itself (impl_sse/decoding.c:166-200) for the flagged survivors: btot[i], etot[i], mocc[i], i = 0..L, in the
+// reference's own order of float operations — btot and etot are running sums, so one lane chain does the adds while the 32
+// lanes compute the terms of 32 rows at a time.  The host then needs 12 bytes per row instead of the 48 of both sets of
+// specials: p7_domaindef_ByPosteriorHeuristics reads nothing else of the two parser matrices (p7_domaindef.c:392-407).
+// Each block of the output also carries Forward's SCALE column and xC(L), from which the host recomputes totscale and the
+// Forward score with its own libm (fwdback.c:434,:463).  Layout per item at dec + doff[j]: btot[L+1], etot[L+1], mocc[L+1],
+// fscale[L+1], xC(L), 0.
+struct DecParams {
+  const float *fx, *bx; const int64_t *xoff, *doff;
+  const int64_t *idx; const int32_t *len; const LenConst *lc;
+  long long n;
+  float *dec;
+};
+
+__global__ void __launch_bounds__(128) domain_decoding_kernel(const DecParams p)
+{
+  const int lane = threadIdx.x & 31;
+  const long long j = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= p.n) return;
+  const int L = p.len[p.idx ? p.idx[j] : j];
+  const float *f = p.fx + p.xoff[j], *b = p.bx + p.xoff[j];
+  float *btot = p.dec + p.doff[j], *etot = btot + (L + 1), *mocc = etot + (L + 1), *fsc = mocc + (L + 1);
+  const float ploop = 1.0f - p.lc[L].pmove;
+  const float sp = (float) (1.0 / (double) b[1]);                     // decoding.c:169 (has_own_scales targets never come here)
+  float bt = 0.0f, et = 0.0f;
+  if (lane == 0) { btot[0] = 0.0f; etot[0] = 0.0f; mocc[0] = 0.0f; fsc[0] = f[5]; fsc[L + 1] = f[(size_t) L * 6 + 4]; fsc[L + 2] = 0.0f; }
+  for (int i0 = 1; i0 <= L; i0 += 32) {
+    const int i = i0 + lane;
+    float tb = 0.0f, te = 0.0f;
+    if (i <= L) {
+      const float *fp = f + (size_t) (i - 1) * 6, *fr = f + (size_t) i * 6, *bp = b + (size_t) (i - 1) * 6, *br = b + (size_t) i * 6;
+      tb = __fmul_rn(__fmul_rn(__fmul_rn(fp[3], bp[3]), fp[5]), sp);                        // :177-178
+      te = __fmul_rn(__fmul_rn(__fmul_rn(fr[0], br[0]), fr[5]), sp);                        // :183-184
+      float njcp =           __fmul_rn(__fmul_rn(__fmul_rn(fp[1], br[1]), ploop), sp);      // :186-188
+      njcp = __fadd_rn(njcp, __fmul_rn(__fmul_rn(__fmul_rn(fp[2], br[2]), ploop), sp));
+      njcp = __fadd_rn(njcp, __fmul_rn(__fmul_rn(__fmul_rn(fp[4], br[4]), ploop), sp));
+      mocc[i] = (float) (1.0 - (double) njcp);                                              // :189
+      fsc[i] = fr[5];
+    }
+    const int m = min(32, L - i0 + 1);
+    float myb = 0.0f, mye = 0.0f;
+    for (int k = 0; k < m; k++) {                                      // the running sums, in row order (every lane carries them)
+      bt = __fadd_rn(bt, __shfl_sync(0xffffffffu, tb, k));
+      et = __fadd_rn(et, __shfl_sync(0xffffffffu, te, k));
+      if (k == lane) { myb = bt; mye = et; }
+    }
+    if (i <= L) { btot[i] = myb; etot[i] = mye; }
+  }
+}
+
+int launch_domain_decoding(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+                           const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int64_t *d_doff, float *d_dec)
+{
+  if (n <= 0) return P7GPU_OK;
+  P7G_CHECK(ensure_len_table(prof, db.max_length));
+  const Lane &ln = ctx->lanes[lane];
+  DecParams p;
+  p.fx = d_fx; p.bx = d_bx; p.xoff = d_xoff; p.doff = d_doff; p.idx = d_idx; p.len = db.len; p.lc = prof->d_len; p.n = n; p.dec = d_dec;
+  const long long blocks = (n * 32 + 127) / 128;
+  { LaunchTimer t(ctx, P7GPU_KERNEL_TRIG, ln.stream); domain_decoding_kernel<<<(unsigned) blocks, 128, 0, ln.stream>>>(p); }
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return P7GPU_OK;
+}
+
 }  // namespace p7g

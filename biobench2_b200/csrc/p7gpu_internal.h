@@ -232,6 +232,9 @@ int launch_region_trigger(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, c
                           float *d_mocc_max, int32_t *d_flag, unsigned int *d_nflag);
 int launch_gather_xmx(p7gpu_ctx *ctx, int lane, const float *d_fx, const float *d_bx, const int64_t *d_src, const int64_t *d_dst,
                       const int32_t *d_nfloats, int64_t n, float *d_ofx, float *d_obx);
+// decode.cu: p7_DomainDecoding (btot, etot, mocc per row + Forward's SCALE column and xC(L)) for selected targets, 4*(L+1)+2 floats each
+int launch_domain_decoding(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
+                           const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int64_t *d_doff, float *d_dec);
 int launch_bias(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                 float *d_filtersc);
 }  // namespace p7g

@@ -50,7 +50,7 @@ struct p7gpu_pipeline_result {
   p7gpu_ctx *ctx = nullptr;                       // the MSV-survivor buffer goes back to this context's cache on destroy
   p7gpu_pipeline_counters counters;
   std::vector<p7gpu_survivor> survivors;
-  RawFloats fwd_xmx, bck_xmx;
+  RawFloats fwd_xmx, bck_xmx, dec;                // dec: opts.decode blocks (btot, etot, mocc, fwd SCALE per row)
   std::vector<p7gpu_msv_survivor> msv_pass;       // only when opts->stop_after_msv
   uint64_t stage_nres[6] = {0, 0, 0, 0, 0, 0};    // residues seen by the MSV, bias, Viterbi, Forward, Backward stages and the exact-order Forward recomputation
   uint64_t n_region_flagged = 0;                  // survivors whose specials were returned
@@ -565,17 +565,51 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       }
       P7G_CUDA(cudaStreamSynchronize(st));
       tr.mark("  slice: backward + trigger done");
-      // which survivors' specials go to the host: all of them, or those whose region trigger fired
-      std::vector<int64_t> src, dst; std::vector<int32_t> nfl; std::vector<int64_t> host_off(nb, -1);
-      size_t need = 0;
+      // which survivors' specials go to the host: all of them, or those whose region trigger fired; with opts->decode the flagged
+      // ones get their p7_DomainDecoding arrays instead (16 bytes per row for 48), except those the host must decide itself
+      std::vector<int64_t> src, dst; std::vector<int32_t> nfl; std::vector<int64_t> host_off(nb, -1), dec_off(nb, -1);
+      std::vector<int64_t> didx, dxoff, ddoff; std::vector<size_t> dwhere;
+      const bool decode = o->decode && o->want_specials && o->region_trigger;
+      size_t need = 0, dneed = 0;
       if (o->want_specials)
         for (size_t k = 0; k < nb; k++) {
           if (o->region_trigger && flag[k] == 0) continue;
-          const size_t len = (size_t) (cand[bwhere[k]].L + 1) * 6;
+          const int Lk = cand[bwhere[k]].L;
+          if (decode && !own[k] && std::isfinite(mocc[k])) {          // mocc_max is NaN/inf only when the scale product is not finite
+            didx.push_back(bidx[k]); dxoff.push_back(boff[k]); ddoff.push_back((int64_t) dneed); dwhere.push_back(k);
+            dec_off[k] = (int64_t) (res->dec.n + dneed);
+            dneed += (size_t) 4 * (Lk + 1) + 2;
+            continue;
+          }
+          const size_t len = (size_t) (Lk + 1) * 6;
           src.push_back(boff[k]); dst.push_back((int64_t) need); nfl.push_back((int32_t) len);
           host_off[k] = (int64_t) (host_floats + need);
           need += len;
         }
+      if (dneed) {
+        DevBuf d_didx, d_dxoff, d_ddoff, d_dec;
+        P7G_CHECK(upload_idx(ctx, didx, &d_didx)); P7G_CHECK(upload_idx(ctx, dxoff, &d_dxoff)); P7G_CHECK(upload_idx(ctx, ddoff, &d_ddoff));
+        P7G_CHECK(d_dec.alloc(4 * dneed, st));
+        P7G_CHECK(launch_domain_decoding(ctx, 0, prof, dbv, d_didx.as<int64_t>(), (int64_t) didx.size(), d_fx.as<float>(), d_bx.as<float>(),
+                                         d_dxoff.as<int64_t>(), d_ddoff.as<int64_t>(), d_dec.as<float>()));
+        const size_t base = res->dec.n;
+        if (!res->ctx) { res->ctx = ctx; res->fwd_xmx.swap(hs.xmx_cache[0]); res->bck_xmx.swap(hs.xmx_cache[1]); res->fwd_xmx.n = res->bck_xmx.n = 0; }
+        if (!res->dec.resize(base + dneed)) { set_error("pipeline: out of host memory for %zu floats of decoding arrays", base + dneed); return P7GPU_EMEM; }
+        P7G_CHECK(d2h_large(ctx, res->dec.data() + base, d_dec.p, 4 * dneed));
+        P7G_CUDA(cudaStreamSynchronize(st));
+        const LenConst *hl = prof->h_len.data();
+        parallel_for(dwhere.size(), [&](size_t a, size_t b) {          // Forward totscale and score from the SCALE column, host libm
+          for (size_t t = a; t < b; t++) {
+            const size_t k = dwhere[t]; Cand &c = cand[bwhere[k]];
+            const float *blk = res->dec.data() + dec_off[k], *fs = blk + (size_t) 3 * (c.L + 1);
+            float tot = 0.0f;
+            for (int i = 1; i <= c.L; i++) if (fs[i] != 1.0f) tot = (float) ((double) tot + log((double) fs[i]));
+            const float xC = fs[c.L + 1];
+            c.ftot = tot;
+            if (exact && !(std::isnan(xC) || (c.L > 0 && xC == 0.0f) || std::isinf(xC))) c.fwdsc = (float) ((double) tot + log((double) (xC * hl[c.L].pmove)));
+          }
+        });
+      }
       if (need) {
         if ((host_floats + need) * 8 > ((size_t) 48 << 30)) {
           set_error("pipeline: Forward/Backward specials of the survivors exceed 48 GiB of host memory; run with region_trigger=1 "
@@ -624,10 +658,11 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
         s.bck_own_scales = own[k];
         s.xmx_offset = host_off[k];
         s.region_flag = flag[k]; s.mocc_max = mocc[k];
+        s.dec_offset = dec_off[k];
         res->survivors.push_back(s);
       }
       host_floats += need;
-      res->n_region_flagged += (uint64_t) src.size();
+      res->n_region_flagged += (uint64_t) (src.size() + didx.size());
       tr.mark("  slice: survivor records");
     }
     lo = hi;
@@ -1111,6 +1146,7 @@ int64_t p7gpu_result_nsurvivors(const p7gpu_pipeline_result *res) { return res ?
 const p7gpu_survivor *p7gpu_result_survivors(const p7gpu_pipeline_result *res) { return res ? res->survivors.data() : nullptr; }
 const float *p7gpu_result_fwd_xmx(const p7gpu_pipeline_result *res) { return res ? res->fwd_xmx.data() : nullptr; }
 const float *p7gpu_result_bck_xmx(const p7gpu_pipeline_result *res) { return res ? res->bck_xmx.data() : nullptr; }
+const float *p7gpu_result_decoding(const p7gpu_pipeline_result *res) { return res ? res->dec.data() : nullptr; }
 const uint64_t *p7gpu_result_stage_residues(const p7gpu_pipeline_result *res) { return res ? res->stage_nres : nullptr; }
 int64_t p7gpu_result_nmsvpass(const p7gpu_pipeline_result *res) { return res ? (int64_t) res->msv_pass.size() : 0; }
 const p7gpu_msv_survivor *p7gpu_result_msvpass(const p7gpu_pipeline_result *res) { return res ? res->msv_pass.data() : nullptr; }

@@ -25,7 +25,7 @@ EXPORTS = [
     "p7gpu_backward_batch", "p7gpu_region_trigger_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
     "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser", "p7gpu_BackwardParser2",
     "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_stage_threshold", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
-    "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_destroy",
+    "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_decoding", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
     "p7gpu_dbfile_from_fasta", "p7gpu_dbfile_open", "p7gpu_dbfile_close", "p7gpu_dbfile_nseq", "p7gpu_dbfile_nres",
     "p7gpu_dbfile_nbytes", "p7gpu_dbfile_maxlength", "p7gpu_dbfile_residues", "p7gpu_dbfile_offsets", "p7gpu_dbfile_lengths",
@@ -43,7 +43,8 @@ class P7GpuError(RuntimeError):
 class PipelineOpts(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double),
                 ("do_biasfilter", C.c_int32), ("do_max", C.c_int32), ("want_specials", C.c_int32),
-                ("stop_after_msv", C.c_int32), ("region_trigger", C.c_int32), ("fb_exact", C.c_int32)]
+                ("stop_after_msv", C.c_int32), ("region_trigger", C.c_int32), ("fb_exact", C.c_int32),
+                ("decode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class MsvSurvivor(C.Structure):
@@ -59,14 +60,15 @@ class Survivor(C.Structure):
     _fields_ = [("seqidx", C.c_int64), ("L", C.c_int32), ("msv_status", C.c_int32), ("vit_status", C.c_int32),
                 ("usc", C.c_float), ("vfsc", C.c_float), ("fwdsc", C.c_float), ("bcksc", C.c_float),
                 ("nullsc", C.c_float), ("filtersc", C.c_float), ("fwd_totscale", C.c_float), ("bck_totscale", C.c_float),
-                ("bck_own_scales", C.c_int32), ("xmx_offset", C.c_int64), ("region_flag", C.c_int32), ("mocc_max", C.c_float)]
+                ("bck_own_scales", C.c_int32), ("xmx_offset", C.c_int64), ("region_flag", C.c_int32), ("mocc_max", C.c_float),
+                ("dec_offset", C.c_int64)]
 
 
 SURVIVOR_NP = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("vit_status", "<i4"),
                         ("usc", "<f4"), ("vfsc", "<f4"), ("fwdsc", "<f4"), ("bcksc", "<f4"), ("nullsc", "<f4"),
                         ("filtersc", "<f4"), ("fwd_totscale", "<f4"), ("bck_totscale", "<f4"), ("bck_own_scales", "<i4"),
-                        ("xmx_offset", "<i8"), ("region_flag", "<i4"), ("mocc_max", "<f4")])
-assert SURVIVOR_NP.itemsize == C.sizeof(Survivor) == 72
+                        ("xmx_offset", "<i8"), ("region_flag", "<i4"), ("mocc_max", "<f4"), ("dec_offset", "<i8")])
+assert SURVIVOR_NP.itemsize == C.sizeof(Survivor) == 80
 
 
 _lib = None
@@ -159,6 +161,8 @@ def lib():
         L.p7gpu_result_fwd_xmx.argtypes = [vp]
         L.p7gpu_result_bck_xmx.restype = C.POINTER(C.c_float)
         L.p7gpu_result_bck_xmx.argtypes = [vp]
+        L.p7gpu_result_decoding.restype = C.POINTER(C.c_float)
+        L.p7gpu_result_decoding.argtypes = [vp]
         L.p7gpu_result_destroy.argtypes = [vp]
         L.p7gpu_nullsc.restype = C.c_float
         L.p7gpu_nullsc.argtypes = [C.c_int]
@@ -411,6 +415,12 @@ def _view(ptr, nbytes, dtype, owner):
     return a
 
 
+def decoding_block(result, sv):
+    """(btot, etot, mocc, fwd_scale, fwd_xC_L) of one survivor record of an opts.decode run"""
+    L = int(sv["L"]); o = int(sv["dec_offset"]); d = result.decoding
+    return d[o: o + L + 1], d[o + L + 1: o + 2 * (L + 1)], d[o + 2 * (L + 1): o + 3 * (L + 1)], d[o + 3 * (L + 1): o + 4 * (L + 1)], d[o + 4 * (L + 1)]
+
+
 class PipelineResult:
     """A p7gpu_pipeline_result.  The record arrays are views of the library's own buffers (no copy).  They stay valid while
     they (or this object) are referenced, or until close(); all of it must end before the Context is closed."""
@@ -431,35 +441,39 @@ class PipelineResult:
             self.bck_xmx = _view(L.p7gpu_result_bck_xmx(h), ext * 4, np.float32, own)
         else:
             self.fwd_xmx = self.bck_xmx = np.zeros(0, np.float32)
+        hd = self.survivors["dec_offset"] >= 0 if n else np.zeros(0, bool)
+        dext = int((self.survivors["dec_offset"][hd] + 4 * (self.survivors["L"][hd].astype(np.int64) + 1) + 2).max()) if hd.any() else 0
+        self.decoding = _view(L.p7gpu_result_decoding(h), dext * 4, np.float32, own) if dext else np.zeros(0, np.float32)
         m = L.p7gpu_result_nmsvpass(h)
         self.msv_pass = _view(L.p7gpu_result_msvpass(h), m * C.sizeof(MsvSurvivor), MSV_NP, own) if m else np.zeros(0, MSV_NP)
 
     def close(self):
         """Release the library buffers now (the arrays of this result must not be used afterwards)."""
-        self.survivors = self.fwd_xmx = self.bck_xmx = self.msv_pass = None
+        self.survivors = self.fwd_xmx = self.bck_xmx = self.msv_pass = self.decoding = None
         self._own.destroy()
 
 
 MSV_NP = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")])
 
 
-def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger=False, fb_exact=False):
-    return PipelineOpts(F1, F2, F3, int(do_biasfilter), int(do_max), int(want_specials), int(stop_after_msv), int(region_trigger), int(fb_exact))
+def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger=False, fb_exact=False, decode=False):
+    return PipelineOpts(F1, F2, F3, int(do_biasfilter), int(do_max), int(want_specials), int(stop_after_msv), int(region_trigger), int(fb_exact),
+                        int(decode), 0)
 
 
 def pipeline_run(ctx, prof, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                 stop_after_msv=False, region_trigger=False, fb_exact=False):
+                 stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
     """The batched p7_Pipeline() over a resident database (defaults: p7_pipeline.c:214-216)."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run(ctx.h, prof.h, db.h, C.byref(o), C.byref(h)))
     return PipelineResult(h)
 
 
 def pipeline_run_many(ctx, profs, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False, fb_exact=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
     """Many profiles against one resident database (p7gpu_pipeline_run_many) -> list of PipelineResult."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
     n = len(profs)
     ph = (C.c_void_p * n)(*[p.h for p in profs])
     rh = (C.c_void_p * n)()
@@ -468,9 +482,9 @@ def pipeline_run_many(ctx, profs, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=T
 
 
 def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False, fb_exact=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
     """Same for a HOST PackedDB: the upload is streamed under the MSV stage."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
                                          _p(packed.lengths), packed.nseq, C.byref(o), C.byref(h)))
@@ -499,9 +513,9 @@ def pack5(residues, out=None, nthreads=0):
 
 
 def pipeline_run_host5(ctx, prof, packed5, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                       stop_after_msv=False, region_trigger=False, fb_exact=False):
+                       stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
     """pipeline_run_host with the residues in the 5-bit transfer format; `packed` supplies offsets, lengths and the unpacked size."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host5(ctx.h, prof.h, _p(packed5), packed.residues.shape[0], _p(packed.offsets), _p(packed.lengths),
                                           packed.nseq, C.byref(o), C.byref(h)))
@@ -546,9 +560,9 @@ class DbFile:
 
 
 def pipeline_run_file(ctx, prof, dbfile, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False, fb_exact=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
     """The batched pipeline over a mapped packed database file (p7gpu_pipeline_run_file)."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_file(ctx.h, prof.h, dbfile.h, C.byref(o), C.byref(h)))
     return PipelineResult(h)
@@ -571,11 +585,11 @@ def merge_counters(results):
 
 
 def pipeline_run_sharded(ctxs, profs, packed, packed5=None, dbfile=None, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False,
-                         want_specials=True, stop_after_msv=False, region_trigger=False, fb_exact=False):
+                         want_specials=True, stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
     """One HOST database over several GPUs of this process: one context, one contiguous shard and one host thread per GPU
     (p7gpu_pipeline_run_sharded / _file_sharded).  Returns (first[nshards+1], [PipelineResult per shard]); survivor seqidx are
     database indices.  Merge like the reference merges its workers: merge_counters() + the hit lists through p7_tophits_Merge."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
     n = len(ctxs)
     ch = (C.c_void_p * n)(*[c.h for c in ctxs]); ph = (C.c_void_p * n)(*[p.h for p in profs]); rh = (C.c_void_p * n)()
     first = np.zeros(n + 1, np.int64)

@@ -239,6 +239,13 @@ typedef struct p7gpu_pipeline_opts {   /* the fields of P7_PIPELINE the path rea
                                         *    SSE order of impl_sse/fwdback.c:257-465, :469-735; csrc/fbx.cu) and is therefore
                                         *    bit-identical to p7_ForwardParser/p7_BackwardParser; the fast kernels (1e-4 relative)
                                         *    then only pre-filter for the F3 test.  0: fast kernels only.                    */
+  int32_t decode;                      /* 1 (with want_specials and region_trigger): run p7_DomainDecoding (impl_sse/decoding.c:
+                                        *    166-200) on the device for the flagged survivors and return btot/etot/mocc per row —
+                                        *    all p7_domaindef_ByPosteriorHeuristics reads of the two parser matrices — plus Forward's
+                                        *    SCALE column instead of both sets of specials: 16 bytes per row instead of 48.
+                                        *    Survivors the host must decide itself (Backward own scales, non-finite scale product)
+                                        *    still get their specials.                                                          */
+  int32_t reserved;
 } p7gpu_pipeline_opts;
 
 typedef struct p7gpu_pipeline_counters { /* P7_PIPELINE accounting (hmmer.h:1224-1231), merged like p7_pipeline_Merge */
@@ -257,6 +264,9 @@ typedef struct p7gpu_survivor {        /* one per target that passed the Forward
   int32_t region_flag;                 /* -1 not evaluated; 0: mocc[i] < rt1 everywhere, no region (nregions = 0);
                                         *  1: the trigger fires somewhere (or the host must decide): specials returned */
   float   mocc_max;                    /* max_i ddef->mocc[i] (NaN when not evaluated)                            */
+  int64_t dec_offset;                  /* opts.decode: float offset of this target's block in p7gpu_result_decoding(), or -1.
+                                        *  Block: btot[L+1], etot[L+1], mocc[L+1] (P7_DOMAINDEF arrays, p7_domaindef.c:392-407),
+                                        *  fwd SCALE[L+1], fwd xC(L), 0                                                   */
 } p7gpu_survivor;
 
 typedef struct p7gpu_msv_survivor {    /* stop_after_msv: one per target with P(MSV) <= F1 (p7_pipeline.c:693-694) */
@@ -300,6 +310,7 @@ int64_t                        p7gpu_result_nsurvivors(const p7gpu_pipeline_resu
 const p7gpu_survivor          *p7gpu_result_survivors (const p7gpu_pipeline_result *res);
 const float                   *p7gpu_result_fwd_xmx  (const p7gpu_pipeline_result *res);
 const float                   *p7gpu_result_bck_xmx  (const p7gpu_pipeline_result *res);
+const float                   *p7gpu_result_decoding (const p7gpu_pipeline_result *res);   /* opts.decode blocks, see p7gpu_survivor.dec_offset */
 void                           p7gpu_result_destroy  (p7gpu_pipeline_result *res);   /* before p7gpu_ctx_destroy of its context:
                                                                                       a result hands its largest buffer back to the context */
 

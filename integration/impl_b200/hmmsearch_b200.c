@@ -61,6 +61,7 @@ static ESL_OPTIONS options[] = {
   /* B200 engine */
   { "--gpus",       eslARG_INT,     "1",     "HMMER_NGPU", "n>=1",   NULL,   NULL, NULL,             "number of GPUs; the database is sharded by sequence",         13 },
   { "--fbfast",     eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "Forward/Backward specials within 1e-4 instead of bit-exact",  13 },
+  { "--hostdecode", eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "p7_DomainDecoding on the host from returned specials",        13 },
   { "--p7db",       eslARG_OUTFILE, NULL,    NULL,         NULL,     NULL,   NULL, NULL,             "keep the packed digital database in file <f> for later runs", 13 },
   { "--times",      eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "report wall time of each phase on stderr",                    13 },
   {  0, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
@@ -223,6 +224,7 @@ main(int argc, char **argv)
   cfg.ngpus    = esl_opt_GetInteger(go, "--gpus");
   cfg.ncpus    = ESL_MAX(1, ncpus);
   cfg.fb_exact = esl_opt_GetBoolean(go, "--fbfast") ? 0 : 1;
+  cfg.decode   = esl_opt_GetBoolean(go, "--hostdecode") ? 0 : 1;
   /* the driver initialises every device it can see (~0.1 s each on an 8-GPU board): show it only the ones this run uses */
   if (getenv("CUDA_VISIBLE_DEVICES") == NULL) {
     char vis[256]; int n = 0;

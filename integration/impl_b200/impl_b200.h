@@ -8,6 +8,7 @@
  *     p7_SSVFilter       impl_sse.h:311      p7_MSVFilter      impl_sse.h:309
  *     p7_ViterbiFilter   impl_sse.h:344      p7_ForwardParser  impl_sse.h:325      p7_BackwardParser  impl_sse.h:328
  *
+ * and, for targets finished from GPU results, p7_DomainDecoding (impl_sse.h:299; decoding.c:166-200),
  * with calls into libp7gpu.so (include/p7gpu.h), plus the batched worker loop that replaces hmmsearch.c:1399-1411.
  * integration/Makefile compiles the reference's own sources where they lie, with the five impl_sse definitions renamed
  * to p7_*_sse on the compiler command line (nothing is edited or copied), so both engines live in one binary and can be
@@ -28,6 +29,7 @@ extern int p7_MSVFilter_sse     (const ESL_DSQ *dsq, int L, const P7_OPROFILE *o
 extern int p7_ViterbiFilter_sse (const ESL_DSQ *dsq, int L, const P7_OPROFILE *om, P7_OMX *ox, float *ret_sc);
 extern int p7_ForwardParser_sse (const ESL_DSQ *dsq, int L, const P7_OPROFILE *om, P7_OMX *fwd, float *opt_sc);
 extern int p7_BackwardParser_sse(const ESL_DSQ *dsq, int L, const P7_OPROFILE *om, const P7_OMX *fwd, P7_OMX *bck, float *opt_sc);
+extern int p7_DomainDecoding_sse(const P7_OPROFILE *om, const P7_OMX *oxf, const P7_OMX *oxb, P7_DOMAINDEF *ddef);
 
 /* ---- engine: one per GPU (the counterpart of one WORKER_INFO, hmmsearch.c:36-44) ---- */
 typedef struct p7_b200_s P7_B200;
@@ -51,7 +53,8 @@ typedef struct {
   const ESL_DSQ *dsq; int L;
   int   msv_status, vit_status;            /* eslOK / eslERANGE as the filters returned them            */
   float usc, vfsc, fwdsc, bcksc;
-  const float *fwd_xmx, *bck_xmx;          /* (L+1)*p7X_NXCELLS floats each                             */
+  const float *fwd_xmx, *bck_xmx;          /* (L+1)*p7X_NXCELLS floats each, or NULL when <dec> is given */
+  const float *dec;                        /* p7_DomainDecoding done on the device: btot[L+1], etot[L+1], mocc[L+1] (p7gpu_survivor.dec_offset) */
   float fwd_totscale, bck_totscale;
   int   bck_own_scales;
 } P7_B200_REPLAY;
@@ -62,6 +65,7 @@ typedef struct {
   int      ngpus;            /* engines to use                                                            */
   int      ncpus;            /* host threads finishing survivors through p7_Pipeline (>= 1)               */
   int      fb_exact;         /* 1: specials in the reference's own summation order (bit-identical hits)    */
+  int      decode;           /* 1: p7_DomainDecoding on the device; 16 bytes per row come back instead of 48 */
   double   gpu_seconds;      /* out: wall time inside the GPU pipeline calls                              */
   double   post_seconds;     /* out: wall time of the survivors' host post-processing                     */
   uint64_t nsurvivors;       /* out                                                                        */

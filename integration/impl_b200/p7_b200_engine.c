@@ -221,8 +221,8 @@ p7_ForwardParser(const ESL_DSQ *dsq, int L, const P7_OPROFILE *om, P7_OMX *fwd, 
   int st; float sc = 0.0f;
   if (fwd->allocXR < L + 1) ESL_EXCEPTION(eslEINVAL, "impl_b200: forward matrix has too few rows of specials");
   fwd->M = om->M;  fwd->L = L;  fwd->has_own_scales = TRUE;          /* fwdback.c:283-285 */
-  if (r && r->dsq == dsq && r->L == L && r->fwd_xmx) {
-    memcpy(fwd->xmx, r->fwd_xmx, sizeof(float) * (size_t) (L + 1) * p7X_NXCELLS);
+  if (r && r->dsq == dsq && r->L == L && (r->fwd_xmx || r->dec)) {
+    if (r->fwd_xmx) memcpy(fwd->xmx, r->fwd_xmx, sizeof(float) * (size_t) (L + 1) * p7X_NXCELLS);   /* else: only p7_DomainDecoding would read them */
     fwd->totscale = r->fwd_totscale;
     if (opt_sc) *opt_sc = r->fwdsc;
     return eslOK;
@@ -246,8 +246,8 @@ p7_BackwardParser(const ESL_DSQ *dsq, int L, const P7_OPROFILE *om, const P7_OMX
   int st; float sc = 0.0f; int own = 0;
   if (bck->allocXR < L + 1) ESL_EXCEPTION(eslEINVAL, "impl_b200: backward matrix has too few rows of specials");
   bck->M = om->M;  bck->L = L;
-  if (r && r->dsq == dsq && r->L == L && r->bck_xmx) {
-    memcpy(bck->xmx, r->bck_xmx, sizeof(float) * (size_t) (L + 1) * p7X_NXCELLS);
+  if (r && r->dsq == dsq && r->L == L && (r->bck_xmx || r->dec)) {
+    if (r->bck_xmx) memcpy(bck->xmx, r->bck_xmx, sizeof(float) * (size_t) (L + 1) * p7X_NXCELLS);
     bck->totscale = r->bck_totscale;  bck->has_own_scales = r->bck_own_scales;         /* fwdback.c:661-663 */
     if (opt_sc) *opt_sc = r->bcksc;
     return eslOK;
@@ -262,4 +262,22 @@ p7_BackwardParser(const ESL_DSQ *dsq, int L, const P7_OPROFILE *om, const P7_OMX
   if (opt_sc) *opt_sc = sc;
   if (st == P7GPU_ERANGE) ESL_EXCEPTION(eslERANGE, "backward score out of range");     /* fwdback.c:731-733 */
   return gpu_status(st);
+}
+
+/* impl_sse.h:299; decoding.c:166-200.  The only reader of the two parser matrices after the Backward parser
+ * (p7_domaindef_ByPosteriorHeuristics, p7_domaindef.c:392-407).  When the replay record carries the arrays the device computed
+ * — in the reference's own order of float operations (csrc/decode.cu) — they are handed over; otherwise the reference's code runs. */
+int
+p7_DomainDecoding(const P7_OPROFILE *om, const P7_OMX *oxf, const P7_OMX *oxb, P7_DOMAINDEF *ddef)
+{
+  const P7_B200_REPLAY *r = tl_replay;
+  if (r && r->dec && oxf->L == r->L) {
+    const size_t n = (size_t) r->L + 1;
+    memcpy(ddef->btot, r->dec,         sizeof(float) * n);
+    memcpy(ddef->etot, r->dec + n,     sizeof(float) * n);
+    memcpy(ddef->mocc, r->dec + 2 * n, sizeof(float) * n);
+    ddef->L = oxf->L;
+    return eslOK;                        /* non-finite scale products never take this path: the host gets their specials */
+  }
+  return p7_DomainDecoding_sse(om, oxf, oxb, ddef);
 }

@@ -81,6 +81,7 @@ post_thread(void *arg)
       rec.usc = sv->usc;  rec.vfsc = sv->vfsc;  rec.fwdsc = sv->fwdsc;  rec.bcksc = sv->bcksc;
       rec.fwd_xmx = (sv->xmx_offset >= 0) ? p7gpu_result_fwd_xmx(w->res[k]) + sv->xmx_offset : NULL;
       rec.bck_xmx = (sv->xmx_offset >= 0) ? p7gpu_result_bck_xmx(w->res[k]) + sv->xmx_offset : NULL;
+      rec.dec     = (sv->dec_offset >= 0) ? p7gpu_result_decoding(w->res[k]) + sv->dec_offset : NULL;
       rec.fwd_totscale = sv->fwd_totscale;  rec.bck_totscale = sv->bck_totscale;  rec.bck_own_scales = sv->bck_own_scales;
       p7_b200_ReplayArm(&rec);
       p7_bg_SetLength(w->bg, sq->n);                       /* hmmsearch.c:1404-1405 */
@@ -120,6 +121,7 @@ p7_b200_SearchDatabase(P7_B200 **engs, P7_B200_SEARCH *cfg, ESL_GETOPTS *go, con
   o.want_specials = 1;
   o.fb_exact = cfg->fb_exact;
   o.region_trigger = (cfg->fb_exact || pli->do_max) ? 1 : 0;   /* exact on exact specials; otherwise only where it pays (--max) */
+  o.decode = (cfg->decode && o.region_trigger) ? 1 : 0;
 
   t0 = now_seconds();
   if (p7gpu_pipeline_run_file_sharded(ctxs, profs, ng, db, &o, first, res) != P7GPU_OK)
