@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <time.h>
 
 #define REPOPTS     "-E,-T,--cut_ga,--cut_nc,--cut_tc"
 #define DOMREPOPTS  "--domE,--domT,--cut_ga,--cut_nc,--cut_tc"
@@ -63,9 +64,20 @@ static ESL_OPTIONS options[] = {
   { "--fbfast",     eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "Forward/Backward specials within 1e-4 instead of bit-exact",  13 },
   { "--hostdecode", eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "p7_DomainDecoding on the host from returned specials",        13 },
   { "--p7db",       eslARG_OUTFILE, NULL,    NULL,         NULL,     NULL,   NULL, NULL,             "keep the packed digital database in file <f> for later runs", 13 },
+  { "--teardown",   eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "free every resource before exit (leak checkers)",             13 },
   { "--times",      eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "report wall time of each phase on stderr",                    13 },
   {  0, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
 };
+
+static double
+since_start(void)
+{
+  static struct timespec t0; static int have = 0;
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  if (!have) { t0 = t; have = 1; }
+  return (double) (t.tv_sec - t0.tv_sec) + 1e-9 * (double) (t.tv_nsec - t0.tv_nsec);
+}
 
 static char usage[]  = "[options] <hmmfile> <seqdb>";
 static char banner[] = "search profile(s) against a sequence database";
@@ -190,6 +202,7 @@ main(int argc, char **argv)
   double         t_db = 0.0;
   int            textw, nquery = 0, hstatus, status, k, ncpus = 0, times;
 
+  since_start();
   impl_Init();                 /* FTZ/DAZ for the host code that stays (impl_sse.h:356-376) */
   p7_FLogsumInit();
 
@@ -237,7 +250,7 @@ main(int argc, char **argv)
   for (k = 0; k < cfg.ngpus; k++)
     if (p7_b200_Open(k, &engs[k]) != eslOK) p7_Fail("Failed to open GPU %d: %s\n", k, p7_b200_ErrorText());
   esl_stopwatch_Stop(w);
-  if (times) fprintf(stderr, "# %d GPU engine(s) open: %.3f s (CUDA initialisation)\n", cfg.ngpus, w->elapsed);
+  if (times) fprintf(stderr, "# %d GPU engine(s) open: %.3f s (CUDA initialisation; %.3f s since start)\n", cfg.ngpus, w->elapsed, since_start());
 
   hstatus = p7_hmmfile_Read(hfp, &abc, &hmm);
   if (hstatus == eslOK) {
@@ -308,16 +321,24 @@ main(int argc, char **argv)
   if (pfamtblfp) p7_tophits_TabularTail(pfamtblfp, "hmmsearch", p7_SEARCH_SEQS, hmmfile, seqfile, go);
   fprintf(ofp, "[ok]\n");
 
-  for (k = 0; k < cfg.ngpus; k++) p7_b200_Close(engs[k]);
-  free(engs);
-  if (db) p7gpu_dbfile_close(db);
-  p7_bg_Destroy(bg);  p7_hmmfile_Close(hfp);  esl_alphabet_Destroy(abc);  esl_stopwatch_Destroy(w);
-  if (ofp != stdout) fclose(ofp);
+  if (ofp != stdout) fclose(ofp); else fflush(stdout);
   if (afp)       fclose(afp);
   if (tblfp)     fclose(tblfp);
   if (domtblfp)  fclose(domtblfp);
   if (pfamtblfp) fclose(pfamtblfp);
+  if (times) fprintf(stderr, "# results written: %.3f s since start\n", since_start());
+  if (!esl_opt_GetBoolean(go, "--teardown")) {
+    /* every output is on disk; unmapping the database, freeing page-locked memory and destroying the CUDA contexts in an
+     * orderly way costs about a second that the process exit does for free */
+    fflush(stderr);
+    _exit(0);
+  }
+  for (k = 0; k < cfg.ngpus; k++) p7_b200_Close(engs[k]);
+  free(engs);
+  if (db) p7gpu_dbfile_close(db);
+  p7_bg_Destroy(bg);  p7_hmmfile_Close(hfp);  esl_alphabet_Destroy(abc);  esl_stopwatch_Destroy(w);
   esl_getopts_Destroy(go);
+  if (times) fprintf(stderr, "# teardown done: %.3f s since start\n", since_start());
   return eslOK;
 
  ERROR:
