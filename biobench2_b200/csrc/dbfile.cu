@@ -245,10 +245,19 @@ int p7gpu_dbfile_open(const char *path, p7gpu_dbfile **ret)
   if (map == MAP_FAILED) { close(fd); set_error("dbfile_open: mmap of %s failed: %s", path, strerror(errno)); return P7GPU_ESYS; }
   const Header *h = (const Header *) map;
   const uint64_t sz = (uint64_t) sb.st_size;
-  const bool ok = memcmp(h->magic, MAGIC, 8) == 0 && h->version == 1 && h->Kp == P7GPU_KP &&
-                  h->off_residues + h->nbytes <= sz && h->off_offsets + 8 * h->nseq <= sz && h->off_lengths + 4 * h->nseq <= sz &&
-                  h->off_nameidx + 8 * h->nseq <= sz && h->off_names + h->names_bytes <= sz;
-  if (!ok) { munmap(map, (size_t) sb.st_size); close(fd); set_error("dbfile_open: %s: bad magic, version or section table", path); return P7GPU_EINVAL; }
+  // every (offset, size) pair is checked against the file size without forming a sum or product that could wrap
+  auto fits = [sz](uint64_t off, uint64_t bytes) { return off <= sz && bytes <= sz - off && (off & 4095) == 0; };
+  bool ok = memcmp(h->magic, MAGIC, 8) == 0 && h->version == 1 && h->Kp == P7GPU_KP && h->max_length >= 0 &&
+            h->nseq <= sz / 8 && h->nseq <= 0x7fffffffffULL && h->nbytes >= 1 &&
+            fits(h->off_residues, h->nbytes) && fits(h->off_offsets, 8 * h->nseq) && fits(h->off_lengths, 4 * h->nseq) &&
+            fits(h->off_nameidx, 8 * h->nseq) && fits(h->off_names, h->names_bytes);
+  if (ok && h->nseq > 0) {                                            // the names section ends in a NUL: no accessor can run off the mapping
+    const char *names = (const char *) map + h->off_names;
+    ok = h->names_bytes >= 2 && names[h->names_bytes - 1] == 0;
+  }
+  // (per-target offsets and lengths are validated by the search itself, chunk by chunk while earlier chunks compute: stream_msv;
+  //  per-target name indices by p7gpu_dbfile_name/desc — neither costs a pass over a 10^7-entry index at open time)
+  if (!ok) { munmap(map, (size_t) sb.st_size); close(fd); set_error("dbfile_open: %s: bad magic, version, section table or index (truncated or corrupt file)", path); return P7GPU_EINVAL; }
   p7gpu_dbfile *d = new p7gpu_dbfile();
   d->map = map; d->map_bytes = (size_t) sb.st_size; d->fd = fd; d->h = h;
   *ret = d;
@@ -278,12 +287,16 @@ const char *p7gpu_dbfile_name(const p7gpu_dbfile *d, int64_t s)
 {
   if (!d || s < 0 || (uint64_t) s >= d->h->nseq) return nullptr;
   const uint64_t *idx = (const uint64_t *) ((const char *) d->map + d->h->off_nameidx);
-  return (const char *) d->map + d->h->off_names + idx[s];
+  if (idx[s] >= d->h->names_bytes) { set_error("dbfile_name: corrupt name index for target %lld", (long long) s); return nullptr; }
+  return (const char *) d->map + d->h->off_names + idx[s];          // NUL-terminated inside the section (checked at open)
 }
 const char *p7gpu_dbfile_desc(const p7gpu_dbfile *d, int64_t s)
 {
   const char *nm = p7gpu_dbfile_name(d, s);
-  return nm ? nm + strlen(nm) + 1 : nullptr;
+  if (!nm) return nullptr;
+  const char *end = (const char *) d->map + d->h->off_names + d->h->names_bytes;
+  const char *ds = nm + strlen(nm) + 1;
+  return ds < end ? ds : end - 1;                                    // a record cut off after its name: empty description
 }
 
 // Load the database into page-locked host memory so that the streamed upload runs at full PCIe rate (optional, once per open;

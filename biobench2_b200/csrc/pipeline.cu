@@ -106,6 +106,7 @@ __global__ void gather_pass_kernel(const int32_t *pass, unsigned n, const float 
 
 struct Cand {              // a target still alive after the bias stage
   int64_t idx; int32_t L, msv_st, vit_st; float usc, nullsc, filtersc, vfsc, fwdsc, bcksc, ftot, btot; double P;
+  int32_t pos;             // position in the MSV survivor list (opts->stage_records), else -1
 };
 
 // Host-side working arrays of the batched pipeline, kept with the context: a database-sized search allocates tens of MB of
@@ -366,7 +367,7 @@ static int bias_vit_on_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const D
     for (unsigned k = 0; k < nf; k++) {
       Cand &c = cand[k]; const CandRec &r = rec[k];
       c.idx = r.idx; c.L = r.L; c.msv_st = r.msv_st; c.vit_st = r.vit_st; c.usc = r.usc; c.nullsc = hl[r.L].nullsc; c.filtersc = r.filtersc;
-      c.vfsc = r.vfsc; c.fwdsc = NAN; c.bcksc = NAN; c.ftot = 0.f; c.btot = 0.f; c.P = 0.0;
+      c.vfsc = r.vfsc; c.fwdsc = NAN; c.bcksc = NAN; c.ftot = 0.f; c.btot = 0.f; c.P = 0.0; c.pos = -1;
     }
   }
   return P7GPU_OK;
@@ -390,7 +391,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   MsvPass mp(hs);
   // default thresholds: the bias and Viterbi stages decide on the device (float thresholds found and verified on the host)
   float T1 = 0.f, T2 = 0.f, Tv = 0.f;
-  bool dev_decide = do_bias && !o->stop_after_msv && F1 > 0 && F1 < 1 && F2 > 0 && F2 < 1 && !getenv("P7GPU_HOST_DECISIONS");
+  bool dev_decide = do_bias && !o->stop_after_msv && !o->stage_records && F1 > 0 && F1 < 1 && F2 > 0 && F2 < 1 && !getenv("P7GPU_HOST_DECISIONS");
   if (dev_decide) {
     auto gum = [&](double F, float mu, float lam) { return (float) (mu - log(-log1p(-F)) / lam); };
     dev_decide = pvalue_threshold([&](float x) { return !(host_gumbel_surv((double) x, ev[0], ev[1]) > F1); }, gum(F1, ev[0], ev[1]), &T1)
@@ -404,12 +405,14 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     res->msv_pass.swap(hs.msv_cache);             // a buffer a previous result gave back: already mapped, no page faults
     res->msv_pass.resize(npass);
     parallel_for(npass, [&](size_t lo, size_t hi) {
-      for (size_t j = lo; j < hi; j++) res->msv_pass[j] = {mp.idx[j], mp.len[j], mp.st[j], mp.usc[j]};
+      for (size_t j = lo; j < hi; j++) res->msv_pass[j] = {mp.idx[j], mp.len[j], mp.st[j], mp.usc[j], 1};
     });
     return P7GPU_OK;
   }
 
   std::vector<Cand> &cand = hs.cand; cand.clear();
+  std::vector<uint8_t> stage;                                      // opts->stage_records: how far each MSV survivor got (1 MSV .. 4 Forward)
+  if (o->stage_records) stage.assign(npass, 1);
   if (dev_decide) {
     P7G_CHECK(bias_vit_on_device(ctx, prof, dbv, mp, npass, T1, T2, Tv, cand, res));
     tr.mark("after_msv: bias + viterbi (device decisions)");
@@ -435,6 +438,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     Cand c;
     c.idx = mp.idx[j]; c.L = mp.len[j]; c.msv_st = mp.st[j]; c.vit_st = -1; c.usc = mp.usc[j]; c.nullsc = hl[c.L].nullsc;
     c.filtersc = do_bias ? filtersc[j] : c.nullsc; c.vfsc = NAN; c.fwdsc = NAN; c.bcksc = NAN; c.ftot = 0.f; c.btot = 0.f; c.P = Pv[j];
+    c.pos = (int32_t) j;
     cand.push_back(c);
   }
   res->counters.n_past_bias = cand.size();
@@ -467,6 +471,10 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   }
   }   // host decisions
   res->counters.n_past_vit = cand.size();
+  if (o->stage_records) {
+    for (unsigned j = 0; j < npass; j++) if (!(do_bias && hs.P[j] > F1)) stage[j] = 2;     // passed the bias filter (or it is off)
+    for (const Cand &c : cand) if (c.pos >= 0) stage[(size_t) c.pos] = 3;
+  }
   tr.mark("after_msv: viterbi stage");
 
   // ---- D + E. Forward parser, F3 test, Backward parser for the survivors (:727-735), in slices bounded by the
@@ -536,6 +544,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       c.P = host_filter_pvalue_exp(c.fwdsc, c.filtersc, ev[4], ev[5]);
       if (c.P > F3) continue;
       bidx.push_back(c.idx); boff.push_back(xoff[k]); bwhere.push_back(lo + k); res->stage_nres[4] += (uint64_t) c.L;
+      if (o->stage_records && c.pos >= 0) stage[(size_t) c.pos] = 4;
     }
     res->counters.n_past_fwd += bidx.size();
     if (!bidx.empty()) {
@@ -666,6 +675,10 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       tr.mark("  slice: survivor records");
     }
     lo = hi;
+  }
+  if (o->stage_records) {
+    res->msv_pass.resize(npass);
+    for (unsigned j = 0; j < npass; j++) res->msv_pass[j] = {mp.idx[j], mp.len[j], mp.st[j], mp.usc[j], (int32_t) stage[j]};
   }
   tr.mark("after_msv: forward/backward");
   return P7GPU_OK;

@@ -44,11 +44,11 @@ class PipelineOpts(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double),
                 ("do_biasfilter", C.c_int32), ("do_max", C.c_int32), ("want_specials", C.c_int32),
                 ("stop_after_msv", C.c_int32), ("region_trigger", C.c_int32), ("fb_exact", C.c_int32),
-                ("decode", C.c_int32), ("reserved", C.c_int32)]
+                ("decode", C.c_int32), ("stage_records", C.c_int32)]
 
 
 class MsvSurvivor(C.Structure):
-    _fields_ = [("seqidx", C.c_int64), ("L", C.c_int32), ("msv_status", C.c_int32), ("usc", C.c_float)]
+    _fields_ = [("seqidx", C.c_int64), ("L", C.c_int32), ("msv_status", C.c_int32), ("usc", C.c_float), ("stage", C.c_int32)]
 
 
 class PipelineCounters(C.Structure):
@@ -453,27 +453,28 @@ class PipelineResult:
         self._own.destroy()
 
 
-MSV_NP = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")])
+MSV_NP = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("stage", "<i4")])
 
 
-def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger=False, fb_exact=False, decode=False):
+def _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger=False, fb_exact=False, decode=False,
+          stage_records=False):
     return PipelineOpts(F1, F2, F3, int(do_biasfilter), int(do_max), int(want_specials), int(stop_after_msv), int(region_trigger), int(fb_exact),
-                        int(decode), 0)
+                        int(decode), int(stage_records))
 
 
 def pipeline_run(ctx, prof, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                 stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
+                 stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False, stage_records=False):
     """The batched p7_Pipeline() over a resident database (defaults: p7_pipeline.c:214-216)."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode, stage_records)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run(ctx.h, prof.h, db.h, C.byref(o), C.byref(h)))
     return PipelineResult(h)
 
 
 def pipeline_run_many(ctx, profs, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False, stage_records=False):
     """Many profiles against one resident database (p7gpu_pipeline_run_many) -> list of PipelineResult."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode, stage_records)
     n = len(profs)
     ph = (C.c_void_p * n)(*[p.h for p in profs])
     rh = (C.c_void_p * n)()
@@ -482,9 +483,9 @@ def pipeline_run_many(ctx, profs, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=T
 
 
 def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False, stage_records=False):
     """Same for a HOST PackedDB: the upload is streamed under the MSV stage."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode, stage_records)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host(ctx.h, prof.h, _p(packed.residues), packed.residues.shape[0], _p(packed.offsets),
                                          _p(packed.lengths), packed.nseq, C.byref(o), C.byref(h)))
@@ -513,9 +514,9 @@ def pack5(residues, out=None, nthreads=0):
 
 
 def pipeline_run_host5(ctx, prof, packed5, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                       stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
+                       stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False, stage_records=False):
     """pipeline_run_host with the residues in the 5-bit transfer format; `packed` supplies offsets, lengths and the unpacked size."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode, stage_records)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_host5(ctx.h, prof.h, _p(packed5), packed.residues.shape[0], _p(packed.offsets), _p(packed.lengths),
                                           packed.nseq, C.byref(o), C.byref(h)))
@@ -560,9 +561,9 @@ class DbFile:
 
 
 def pipeline_run_file(ctx, prof, dbfile, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,
-                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
+                      stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False, stage_records=False):
     """The batched pipeline over a mapped packed database file (p7gpu_pipeline_run_file)."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode, stage_records)
     h = C.c_void_p()
     _check(lib().p7gpu_pipeline_run_file(ctx.h, prof.h, dbfile.h, C.byref(o), C.byref(h)))
     return PipelineResult(h)
@@ -585,11 +586,11 @@ def merge_counters(results):
 
 
 def pipeline_run_sharded(ctxs, profs, packed, packed5=None, dbfile=None, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False,
-                         want_specials=True, stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False):
+                         want_specials=True, stop_after_msv=False, region_trigger=False, fb_exact=False, decode=False, stage_records=False):
     """One HOST database over several GPUs of this process: one context, one contiguous shard and one host thread per GPU
     (p7gpu_pipeline_run_sharded / _file_sharded).  Returns (first[nshards+1], [PipelineResult per shard]); survivor seqidx are
     database indices.  Merge like the reference merges its workers: merge_counters() + the hit lists through p7_tophits_Merge."""
-    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode)
+    o = _opts(F1, F2, F3, do_biasfilter, do_max, want_specials, stop_after_msv, region_trigger, fb_exact, decode, stage_records)
     n = len(ctxs)
     ch = (C.c_void_p * n)(*[c.h for c in ctxs]); ph = (C.c_void_p * n)(*[p.h for p in profs]); rh = (C.c_void_p * n)()
     first = np.zeros(n + 1, np.int64)

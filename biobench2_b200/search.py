@@ -14,7 +14,7 @@ SURVIVOR_DTYPE = np.dtype([
     ("usc", "<f4"), ("vfsc", "<f4"), ("fwdsc", "<f4"), ("bcksc", "<f4"), ("nullsc", "<f4"), ("filtersc", "<f4"),
     ("fwd_totscale", "<f4"), ("bck_totscale", "<f4"), ("bck_own_scales", "<i4"), ("xmx_offset", "<i8"),
     ("region_flag", "<i4"), ("mocc_max", "<f4"), ("dec_offset", "<i8")])                             # = p7gpu_survivor, 80 bytes
-MSV_DTYPE = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("_pad", "<i4")])
+MSV_DTYPE = np.dtype([("seqidx", "<i8"), ("L", "<i4"), ("msv_status", "<i4"), ("usc", "<f4"), ("stage", "<i4")])
 assert SURVIVOR_DTYPE.itemsize == 80 and MSV_DTYPE.itemsize == 24
 
 

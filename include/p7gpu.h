@@ -245,7 +245,10 @@ typedef struct p7gpu_pipeline_opts {   /* the fields of P7_PIPELINE the path rea
                                         *    SCALE column instead of both sets of specials: 16 bytes per row instead of 48.
                                         *    Survivors the host must decide itself (Backward own scales, non-finite scale product)
                                         *    still get their specials.                                                          */
-  int32_t reserved;
+  int32_t stage_records;               /* 1: also return one p7gpu_msv_survivor per target that passed the MSV filter, with the
+                                        *    stage it reached (p7gpu_result_msvpass): what a scan pipeline needs to keep the
+                                        *    per-query accounting of hmmscan (p7_pipeline.c:694,705,723,731).  Stage decisions are
+                                        *    then evaluated on the host.                                                        */
 } p7gpu_pipeline_opts;
 
 typedef struct p7gpu_pipeline_counters { /* P7_PIPELINE accounting (hmmer.h:1224-1231), merged like p7_pipeline_Merge */
@@ -271,6 +274,7 @@ typedef struct p7gpu_survivor {        /* one per target that passed the Forward
 
 typedef struct p7gpu_msv_survivor {    /* stop_after_msv: one per target with P(MSV) <= F1 (p7_pipeline.c:693-694) */
   int64_t seqidx; int32_t L; int32_t msv_status; float usc;
+  int32_t stage;                       /* 1 passed MSV, 2 passed the bias filter, 3 passed Viterbi, 4 passed Forward (1 when stop_after_msv) */
 } p7gpu_msv_survivor;
 
 typedef struct p7gpu_pipeline_result p7gpu_pipeline_result;

@@ -41,6 +41,8 @@ extern const char *p7_b200_ErrorText(void);                              /* p7gp
 /* hand the query over once, after p7_oprofile_Convert + p7_pli_NewModel (hmmsearch.c:500-512): de-stripes and uploads <om>,
  * and the bias-filter HMM that p7_bg_SetFilter built in <bg> (p7_pipeline.c:505) */
 extern int         p7_b200_SetModel(P7_B200 *eng, const P7_OPROFILE *om, const P7_BG *bg);
+/* same for a profile of which only the MSV part has been read (p7_oprofile_ReadMSV, impl_sse/io.c:233): the MSV/SSV stage only */
+extern int         p7_b200_SetModelMSV(P7_B200 *eng, const P7_OPROFILE *om);
 extern p7gpu_ctx     *p7_b200_Ctx    (P7_B200 *eng);
 extern p7gpu_profile *p7_b200_Profile(P7_B200 *eng);
 extern void        p7_b200_ViewOf(const P7_OPROFILE *om, p7gpu_oprofile_view *v);

@@ -96,14 +96,20 @@ p7_b200_Close(P7_B200 *e)
   free(e);
 }
 
-int
-p7_b200_SetModel(P7_B200 *e, const P7_OPROFILE *om, const P7_BG *bg)
+static int set_model(P7_B200 *e, const P7_OPROFILE *om, const P7_BG *bg, int msv_only);
+
+int p7_b200_SetModel   (P7_B200 *e, const P7_OPROFILE *om, const P7_BG *bg) { return set_model(e, om, bg, FALSE); }
+int p7_b200_SetModelMSV(P7_B200 *e, const P7_OPROFILE *om)                  { return set_model(e, om, NULL, TRUE); }
+
+static int
+set_model(P7_B200 *e, const P7_OPROFILE *om, const P7_BG *bg, int msv_only)
 {
   p7gpu_oprofile_view v;
   int st;
   pthread_mutex_lock(&e->lock);
   if (e->prof) { p7gpu_profile_destroy(e->prof); e->prof = NULL; }
   p7_b200_ViewOf(om, &v);
+  if (msv_only) { v.rwv = NULL; v.twv = NULL; v.rfv = NULL; v.tfv = NULL; }     /* not read yet: p7gpu_profile_upload skips those parts */
   st = p7gpu_profile_upload(e->ctx, &v, &e->prof);
   if (st == P7GPU_OK && bg && bg->fhmm) {
     float t6[6], pi3[3], eo[P7GPU_KP * 2];
@@ -113,7 +119,7 @@ p7_b200_SetModel(P7_B200 *e, const P7_OPROFILE *om, const P7_BG *bg)
     for (x = 0; x < om->abc->Kp && x < P7GPU_KP; x++) for (k = 0; k < 2; k++) eo[x*2+k] = bg->fhmm->eo[x][k];
     st = p7gpu_profile_set_biasfilter(e->prof, t6, pi3, eo);
   }
-  e->finger  = fingerprint(om);
+  e->finger  = msv_only ? 0 : fingerprint(om);
   e->om_addr = om;
   pthread_mutex_unlock(&e->lock);
   return (st == P7GPU_OK) ? eslOK : eslESYS;
