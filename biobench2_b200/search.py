@@ -101,6 +101,58 @@ def gather_device_records(d_rec, d_count, dist_mod=None, dst=0):
     return out, cnts
 
 
+def gather_floats(arr, dist_mod=None, device=None, dst=0):
+    """Gather variable-length float32 arrays (e.g. the survivors' Forward/Backward specials) to `dst`: one all_gather of the
+    lengths, one gather of the payload padded to the longest.  Returns (concatenated array, per-rank start offsets) on `dst`,
+    (None, None) elsewhere."""
+    import torch
+    arr = np.ascontiguousarray(arr, np.float32)
+    if dist_mod is None or not dist_mod.is_initialized() or dist_mod.get_world_size() == 1:
+        return arr, np.zeros(1, np.int64)
+    world, rank = dist_mod.get_world_size(), dist_mod.get_rank()
+    device = _dev(dist_mod, device)
+    cnt = torch.tensor([arr.shape[0]], dtype=torch.int64, device=device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist_mod.all_gather(cnts, cnt)
+    counts = [int(c.item()) for c in cnts]
+    mx = max(max(counts), 1)
+    pad = np.zeros(mx, np.float32); pad[: arr.shape[0]] = arr
+    t = torch.from_numpy(pad).to(device)
+    out = [torch.zeros_like(t) for _ in range(world)] if rank == dst else None
+    dist_mod.gather(t, out, dst=dst)
+    if rank != dst:
+        return None, None
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+    return np.concatenate([out[r].cpu().numpy()[: counts[r]] for r in range(world)]), starts
+
+
+def sharded_search_with_specials(ctx, prof, packed, dist_mod=None, **opts):
+    """sharded_pipeline plus the survivors' specials on rank 0: what the master needs to build the hit list from every rank's
+    survivors (the MPI master's role, hmmsearch.c:1008-1029).  Returns (counters, records, fwd_xmx, bck_xmx) on rank 0 with
+    records['xmx_offset'] rebased into the concatenated arrays; four Nones elsewhere."""
+    from . import engine
+    world = dist_mod.get_world_size() if dist_mod is not None and dist_mod.is_initialized() else 1
+    rank = dist_mod.get_rank() if world > 1 else 0
+    shard, first = shard_db(packed, rank, world)
+    res = engine.pipeline_run_host(ctx, prof, shard, want_specials=True, **opts)
+    rec = survivors_to_records(res, first)
+    nrec = np.array([rec.shape[0]], np.int64)
+    fx, starts = gather_floats(res.fwd_xmx, dist_mod)
+    bx, _ = gather_floats(res.bck_xmx, dist_mod)
+    allrec = gather_records(rec, dist_mod)
+    counts = gather_records(nrec.view([("n", "<i8")]), dist_mod)
+    counters = reduce_counters(res.counters, dist_mod)
+    if rank != 0:
+        return None, None, None, None
+    if world > 1:                                                   # each rank's offsets point into its own arrays: rebase
+        lo = 0
+        for r in range(world):
+            n = int(counts["n"][r]); seg = allrec[lo: lo + n]
+            seg["xmx_offset"] = np.where(seg["xmx_offset"] >= 0, seg["xmx_offset"] + starts[r], -1)
+            lo += n
+    return counters, allrec, fx, bx
+
+
 def reduce_counters(counters, dist_mod=None, device=None, dst=0):
     """Sum the six pipeline counters over ranks (p7_pipeline_Merge, p7_pipeline.c:597-636).  Result valid on `dst`."""
     import torch

@@ -222,3 +222,20 @@ def test_fast_specials_report_differing_lines(tmp_path):
     da, dbb = payload(res["ref"][2]), payload(res["b200"][2])
     nddiff = sum(x != y for x, y in zip(da, dbb)) + abs(len(da) - len(dbb))
     print("--fbfast: %d of %d --tblout lines and %d of %d --domtblout lines differ in text from the reference" % (ndiff, len(a), nddiff, len(da)))
+
+
+@pytest.mark.gpu
+def test_two_ranks_nccl_gather_into_the_reference_hit_list():
+    """one process per GPU (torch.distributed, NCCL): survivors + specials gathered to rank 0, finished by the reference's
+    post-processing and p7_tophits_SortBySortkey/Threshold == the same search on one rank == the reference's own pipeline"""
+    from oracle import ref
+    if engine.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    if not ref.available():
+        pytest.skip("oracle/_ref/libp7ref.so not built")
+    p = subprocess.run(["python", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(ROOT, "scripts", "nccl_merge_check.py"), "Pkinase", "60000"],
+                       capture_output=True, text=True, timeout=1500)
+    print(p.stdout[-2000:])
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert '"identical": true' in p.stdout

@@ -84,3 +84,48 @@ def test_more_ranks_than_targets():
         shard, first = search.shard_db(db, r, 8)
         got.extend(range(first, first + shard.nseq))
     assert got == [0, 1, 2]
+
+
+def _worker2(rank, world, port, counts, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    f = (np.arange(counts[rank], dtype=np.float32) + 100 * rank)
+    allf, starts = search.gather_floats(f, dist)
+    # records that are "still on the device": fixed capacity, a count tensor, no host read inside the exchange
+    cap = 6
+    rec = torch.zeros((cap, 2), dtype=torch.float64); n = min(cap, counts[rank])
+    rec[:n, 0] = torch.arange(n, dtype=torch.float64) + 10 * rank; rec[:n, 1] = rank
+    out, cnts = search.gather_device_records(rec, torch.tensor([n], dtype=torch.int64), dist)
+    if rank == 0:
+        np.save(os.path.join(outdir, "f.npy"), allf); np.save(os.path.join(outdir, "starts.npy"), starts)
+        np.save(os.path.join(outdir, "dev.npy"), np.stack([o.numpy() for o in out])); np.save(os.path.join(outdir, "cnts.npy"), np.array([int(c.item()) for c in cnts]))
+    else:
+        assert allf is None and starts is None and out is None
+        assert [int(c.item()) for c in cnts] == [min(cap, c) for c in counts]      # the counts are all-gathered: every rank has them
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,counts", [(2, [4, 9]), (2, [0, 3]), (3, [5, 0, 1])])
+def test_float_and_device_record_gathers_over_gloo(tmp_path, world, counts):
+    port = _free_port()
+    mp.spawn(_worker2, args=(world, port, counts, str(tmp_path)), nprocs=world, join=True)
+    f = np.load(tmp_path / "f.npy"); starts = np.load(tmp_path / "starts.npy")
+    want = np.concatenate([np.arange(counts[r], dtype=np.float32) + 100 * r for r in range(world)])
+    assert np.array_equal(f, want) and list(starts) == list(np.concatenate([[0], np.cumsum(counts)[:-1]]))
+    dev = np.load(tmp_path / "dev.npy"); cnts = np.load(tmp_path / "cnts.npy")
+    for r in range(world):
+        n = min(6, counts[r])
+        assert cnts[r] == n and np.array_equal(dev[r, :n, 0], np.arange(n) + 10 * r) and (dev[r, :n, 1] == r).all() and (dev[r, n:] == 0).all()
+
+
+@pytest.mark.parametrize("nshards", [1, 2, 3, 8])
+def test_c_shard_plan_balances_residues(nshards):
+    """p7gpu_shard_plan (the C host's sharding, include/p7gpu.h section 9): contiguous, covering, balanced by residue count"""
+    from biobench2_b200 import engine
+    db = seqdb.synth_db(5000, mean=250, seed=9)
+    packed = seqdb.pack([db.residues[db.offsets[s]: db.offsets[s] + db.lengths[s]] for s in range(db.nseq)], align=16)
+    first = engine.shard_plan(packed, nshards)
+    assert first[0] == 0 and first[-1] == packed.nseq and all(first[k] <= first[k + 1] for k in range(nshards))
+    for k in range(nshards):
+        res = int(packed.lengths[first[k]: first[k + 1]].astype(np.int64).sum())
+        assert abs(res - packed.nres / nshards) <= 0.03 * packed.nres + 4000
