@@ -6,6 +6,12 @@
 // and a double-precision log() of the row maximum (float sc[i] = log(max), accumulated in float) — O(L) work with
 // no parallelism inside a target worth a warp.  Float operations are issued in the reference's order with explicit
 // round-to-nearest intrinsics (no FMA contraction); the L-dependent logf() terms come from the host-built per-L table.
+//
+// The one libm call is (float) log((double) max).  CUDA's log() and glibc's are both within 1 ulp of the true value but not
+// bit-identical, and the float they round to differs only when the true value lies within that distance of a float rounding
+// boundary.  The kernel checks exactly that — does rounding d*(1 +- 2^-48) give the same float as rounding d? — and reports
+// the (about three per 10^7-target pass) targets where it cannot be sure; host_bias_filtersc (p7gpu_host.cu) recomputes those
+// with the host libm.  filtersc is therefore the reference's bit for bit by construction, not by probability.
 #include "p7gpu_internal.h"
 
 namespace p7g {
@@ -15,7 +21,18 @@ struct BiasParams {
   const LenConst *lc;
   BiasHmm h;
   float *filtersc;
+  double window;                 // relative half-width of the "cannot be sure" test (2^-48; tests widen it)
+  int32_t *unsure_list; unsigned int *unsure_count;   // work items whose score the host must recompute
 };
+
+// (float) log((double) v); *unsure is set when a 1-ulp difference in the double logarithm could change the float
+__device__ __forceinline__ float log_checked(float v, double window, bool *unsure)
+{
+  const double d = log((double) v);
+  const float f = (float) d;
+  if ((float) (d * (1.0 + window)) != f || (float) (d * (1.0 - window)) != f) *unsure = true;
+  return f;
+}
 
 __global__ void __launch_bounds__(128) bias_kernel(const BiasParams p)
 {
@@ -29,6 +46,7 @@ __global__ void __launch_bounds__(128) bias_kernel(const BiasParams p)
   const float t10 = p.h.t[1][0], t11 = p.h.t[1][1], t02 = p.h.t[0][2], t12 = p.h.t[1][2];
   const float len_term_a = __fmul_rn((float) L, p.lc[L].logf_p1), len_term_b = p.lc[L].logf_1mp1;
   float logsc = 0.0f;
+  bool unsure = false;
   if (L == 0) {                                        // esl_hmm.c:362-368 (not reached by the pipeline, :682)
     p.filtersc[j] = __fadd_rn(__fadd_rn((float) log((double) p.h.pi[2]), len_term_a), len_term_b);
     return;
@@ -37,22 +55,23 @@ __global__ void __launch_bounds__(128) bias_kernel(const BiasParams p)
   float dp1 = __fmul_rn(p.h.eo[x[0]][1], p.h.pi[1]);
   float mx = 0.0f; if (dp0 > mx) mx = dp0; if (dp1 > mx) mx = dp1;
   dp0 = __fdiv_rn(dp0, mx); dp1 = __fdiv_rn(dp1, mx);
-  logsc = __fadd_rn(logsc, (float) log((double) mx));
+  logsc = __fadd_rn(logsc, log_checked(mx, p.window, &unsure));
   for (int i = 2; i <= L; i++) {
     const int r = x[i - 1];
     float n0 = __fadd_rn(0.0f, __fmul_rn(dp0, t00)); n0 = __fadd_rn(n0, __fmul_rn(dp1, t10)); n0 = __fmul_rn(n0, p.h.eo[r][0]);
     float n1 = __fadd_rn(0.0f, __fmul_rn(dp0, t01)); n1 = __fadd_rn(n1, __fmul_rn(dp1, t11)); n1 = __fmul_rn(n1, p.h.eo[r][1]);
     mx = 0.0f; if (n0 > mx) mx = n0; if (n1 > mx) mx = n1;
     dp0 = __fdiv_rn(n0, mx); dp1 = __fdiv_rn(n1, mx);
-    logsc = __fadd_rn(logsc, (float) log((double) mx));
+    logsc = __fadd_rn(logsc, log_checked(mx, p.window, &unsure));
   }
   float last = __fadd_rn(0.0f, __fmul_rn(dp0, t02)); last = __fadd_rn(last, __fmul_rn(dp1, t12));
-  logsc = __fadd_rn(logsc, (float) log((double) last));
+  logsc = __fadd_rn(logsc, log_checked(last, p.window, &unsure));
   p.filtersc[j] = __fadd_rn(__fadd_rn(logsc, len_term_a), len_term_b);          // p7_bg.c:481
+  if (unsure && p.unsure_list) p.unsure_list[atomicAdd(p.unsure_count, 1u)] = (int32_t) j;
 }
 
 int launch_bias(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
-                float *d_filtersc)
+                float *d_filtersc, int32_t *d_unsure_list, unsigned int *d_unsure_count)
 {
   if (n <= 0) return P7GPU_OK;
   if (!prof->have_bias) { set_error("bias filter: the profile has no filter HMM (p7gpu_profile_set_biasfilter)"); return P7GPU_EINVAL; }
@@ -61,6 +80,9 @@ int launch_bias(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbVie
   BiasParams p;
   p.res = db.res; p.off = db.off; p.len = db.len; p.idx = d_idx; p.first = db.first; p.n = n;
   p.lc = prof->d_len; p.h = prof->bias; p.filtersc = d_filtersc;
+  p.window = ctx->bias_window > 0 ? (double) ctx->bias_window : 3.552713678800501e-15;   // 2^-48
+  p.unsure_list = d_unsure_list; p.unsure_count = d_unsure_count;
+  if (d_unsure_count) P7G_CUDA(cudaMemsetAsync(d_unsure_count, 0, sizeof(unsigned int), ln.stream));
   { LaunchTimer t(ctx, P7GPU_KERNEL_BIAS, ln.stream); bias_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ln.stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;

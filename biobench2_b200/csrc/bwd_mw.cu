@@ -8,7 +8,7 @@
 // so the scan over P (one Kogge-Stone pass with constant multipliers, the xB partial sums riding along) runs BEFORE xE is
 // known; lane 0 publishes the warp's map and sum, and after the barrier every thread finishes the row from shared memory.
 // The k+1 neighbour across a warp boundary is rebuilt by the reader from three published numbers (Ma + xE*Mq + Mk*Yz).
-// Arithmetic inside a cell is that of fwdbwd.cu (no FMA, FTZ); only the association order of the D<-D sums differs.
+// Arithmetic inside a cell is that of fwdbwd.cu (FTZ; these production kernels allow FMA contraction, csrc/Makefile); only the association order of the D<-D sums differs.
 #include "fwdbwd_mw.cuh"
 
 namespace p7g {

@@ -20,7 +20,7 @@ struct TrigParams {
   const int64_t *idx; const int32_t *len; const LenConst *lc;
   const int32_t *own;            // Backward's has_own_scales per work item, may be null
   long long n;
-  float rt1;
+  float rt1;                     // p7_domaindef.c:109 minus the slack below
   float *mocc_max; int32_t *flag;
   unsigned int *nflag;           // optional count of flagged items
 };
@@ -56,14 +56,16 @@ __global__ void __launch_bounds__(256) region_trigger_kernel(const TrigParams p)
 
 int launch_region_trigger(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                           const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int32_t *d_own,
-                          float *d_mocc_max, int32_t *d_flag, unsigned int *d_nflag)
+                          float *d_mocc_max, int32_t *d_flag, unsigned int *d_nflag, float slack)
 {
   if (n <= 0) return P7GPU_OK;
   P7G_CHECK(ensure_len_table(prof, db.max_length));
   const Lane &ln = ctx->lanes[lane];
   TrigParams p;
   p.fx = d_fx; p.bx = d_bx; p.xoff = d_xoff; p.idx = d_idx; p.len = db.len; p.lc = prof->d_len; p.own = d_own; p.n = n;
-  p.rt1 = 0.25f;                                                       // p7_domaindef.c:109
+  // rt1 = 0.25 (p7_domaindef.c:109).  On exact-order specials mocc is the reference's bit for bit and slack is 0; on the fast
+  // kernels' specials (<= 1e-4 relative) a target within 1e-4 of the trigger is flagged, i.e. left to the host to decide
+  p.rt1 = 0.25f - slack;
   p.mocc_max = d_mocc_max; p.flag = d_flag; p.nflag = d_nflag;
   const long long blocks = (n * 32 + 255) / 256;
   { LaunchTimer t(ctx, P7GPU_KERNEL_TRIG, ln.stream); region_trigger_kernel<<<(unsigned) blocks, 256, 0, ln.stream>>>(p); }

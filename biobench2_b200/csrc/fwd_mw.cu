@@ -9,7 +9,7 @@
 //   warp      ONE Kogge-Stone pass over (P, U) composes the lane maps (constants kB/kV per step, built once per CTA)
 //   CTA       lane 31 publishes the warp's (P, U) and its last node's M, I, D-part; after the barrier every thread
 //             runs the <= W-step recurrence X_{v+1} = P_v + B_v X_v and xE = sum_v U_v + V_v X_v from shared memory.
-// Arithmetic inside a cell is that of fwdbwd.cu (no FMA, FTZ); only the association order of the D->D sums differs.
+// Arithmetic inside a cell is that of fwdbwd.cu (FTZ; these production kernels allow FMA contraction, csrc/Makefile); only the association order of the D->D sums differs.
 #include "fwdbwd_mw.cuh"
 
 namespace p7g {

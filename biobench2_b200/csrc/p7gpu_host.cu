@@ -96,6 +96,61 @@ void fbx_host_bwd_score(const float *xmx, int L, float *totscale, float *sc, int
   else { *status = P7GPU_OK; *sc = (float) ((double) tot + log((double) xN)); }
 }
 
+float host_bias_filtersc(const BiasHmm &h, const uint8_t *x, int L)
+{
+  const float p1 = (float) L / (float) (L + 1);                                  // p7_bg_SetLength, p7_bg.c:193-196
+  const float t00 = p1, t01 = 1.0f - p1, t10 = h.t[1][0], t11 = h.t[1][1], t02 = h.t[0][2], t12 = h.t[1][2];
+  const float la = (float) L * logf(p1), lb = logf(1.0f - p1);                   // p7_bg.c:481
+  float logsc = 0.0f;
+  if (L == 0) return ((float) log((double) h.pi[2]) + la) + lb;
+  float dp0 = h.eo[x[0]][0] * h.pi[0], dp1 = h.eo[x[0]][1] * h.pi[1];
+  float mx = 0.0f; if (dp0 > mx) mx = dp0; if (dp1 > mx) mx = dp1;
+  dp0 = dp0 / mx; dp1 = dp1 / mx;
+  logsc = logsc + (float) log((double) mx);
+  for (int i = 2; i <= L; i++) {
+    const int r = x[i - 1];
+    float n0 = 0.0f + dp0 * t00; n0 = n0 + dp1 * t10; n0 = n0 * h.eo[r][0];
+    float n1 = 0.0f + dp0 * t01; n1 = n1 + dp1 * t11; n1 = n1 * h.eo[r][1];
+    mx = 0.0f; if (n0 > mx) mx = n0; if (n1 > mx) mx = n1;
+    dp0 = n0 / mx; dp1 = n1 / mx;
+    logsc = logsc + (float) log((double) mx);
+  }
+  float last = 0.0f + dp0 * t02; last = last + dp1 * t12;
+  logsc = logsc + (float) log((double) last);
+  return (logsc + la) + lb;
+}
+
+int fix_unsure_filtersc(p7gpu_ctx *ctx, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, float *d_filtersc,
+                        const int32_t *d_unsure_list, const unsigned int *d_unsure_count, float *h_filtersc, unsigned *nfixed)
+{
+  unsigned n = 0;
+  if (nfixed) *nfixed = 0;
+  if (!d_unsure_list || !d_unsure_count) return P7GPU_OK;
+  cudaStream_t st = ctx->stream;
+  P7G_CUDA(cudaMemcpyAsync(&n, d_unsure_count, sizeof(n), cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaStreamSynchronize(st));
+  if (n == 0) return P7GPU_OK;
+  std::vector<int32_t> list(n);
+  P7G_CUDA(cudaMemcpyAsync(list.data(), d_unsure_list, 4 * (size_t) n, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaStreamSynchronize(st));
+  std::vector<uint8_t> seq;
+  for (unsigned k = 0; k < n; k++) {
+    const int32_t j = list[k];
+    int64_t s = db.first + j, off = 0; int32_t L = 0;
+    if (d_idx) P7G_CUDA(cudaMemcpy(&s, d_idx + j, 8, cudaMemcpyDeviceToHost));
+    P7G_CUDA(cudaMemcpy(&off, db.off + s, 8, cudaMemcpyDeviceToHost));
+    P7G_CUDA(cudaMemcpy(&L, db.len + s, 4, cudaMemcpyDeviceToHost));
+    seq.resize((size_t) std::max(L, 1));
+    if (L > 0) P7G_CUDA(cudaMemcpy(seq.data(), db.res + off, (size_t) L, cudaMemcpyDeviceToHost));
+    const float f = host_bias_filtersc(prof->bias, seq.data(), L);
+    P7G_CUDA(cudaMemcpy(d_filtersc + j, &f, 4, cudaMemcpyHostToDevice));
+    if (h_filtersc) h_filtersc[j] = f;
+  }
+  ctx->bias_fixed += n;
+  if (nfixed) *nfixed = n;
+  return P7GPU_OK;
+}
+
 float host_nullsc(int L)                                   // p7_bg_NullOne, p7_bg.c:358-363 (double math, float result)
 {
   float p1 = (float) L / (float) (L + 1);
@@ -375,10 +430,13 @@ int p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value)
   if (!strcmp(name, "fb_exact"))       { ctx->fb_exact = value; return P7GPU_OK; }
   if (!strcmp(name, "fb_fast"))        { ctx->fb_fast = value; return P7GPU_OK; }
   if (!strcmp(name, "fbx_groups"))     { ctx->fbx_groups = value; return P7GPU_OK; }
+  if (!strcmp(name, "bias_window_log2")) { ctx->bias_window = value > 0 ? ldexpf(1.0f, -value) : 0.f; return P7GPU_OK; }
   if (!strcmp(name, "fbx_warps"))      { ctx->fbx_warps = value; return P7GPU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return P7GPU_EINVAL;
 }
+
+int64_t p7gpu_ctx_bias_recomputed(const p7gpu_ctx *ctx) { return ctx ? ctx->bias_fixed : -1; }
 
 int64_t p7gpu_ctx_last_vit_redo(p7gpu_ctx *ctx)
 {
@@ -755,7 +813,10 @@ int p7gpu_biasfilter_batch(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gp
   P7G_CUDA(cudaSetDevice(ctx->device));
   BatchBufs b;
   P7G_CHECK(setup_batch(ctx, db, idx, n, &b));
-  P7G_CHECK(launch_bias(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc));
+  int32_t *d_unsure = (int32_t *) b.d_list;                                   // [n] work items + one counter behind them
+  unsigned int *d_ucount = (unsigned int *) (d_unsure + std::max<int64_t>(b.n, 1));
+  P7G_CHECK(launch_bias(ctx, 0, prof, db->view(), b.d_idx, b.n, b.d_sc, d_unsure, d_ucount));
+  P7G_CHECK(fix_unsure_filtersc(ctx, prof, db->view(), b.d_idx, b.d_sc, d_unsure, d_ucount, nullptr, nullptr));
   return fetch_batch(ctx, b, filtersc, nullptr);
 }
 

@@ -110,6 +110,8 @@ struct p7gpu_ctx {
   int          fb_exact = 0;            // option "fb_exact": p7gpu_forward_batch/p7gpu_backward_batch run the exact-order kernels (fbx.cu)
   int          fb_fast = 0;             // option "fb_fast": the one-target wrappers p7gpu_ForwardParser/BackwardParser run the fast kernels
   int          fbx_warps = 0;           // option "fbx_warps": cap on resident one-warp CTAs per SM of the exact-order kernels (0 = occupancy)
+  float        bias_window = 0.f;       // option "bias_window_log2": half-width 2^-n of the bias kernel's log() certainty test (tests widen it)
+  int64_t      bias_fixed = 0;          // targets whose filtersc the host recomputed so far (diagnostic)
   int          fbx_groups = 0;          // option "fbx_groups": targets per warp of the exact-order kernels, 1/2/4/8 (0 = auto)
   // growable scratch buffers (device + pinned host)
   void  *d_scratch = nullptr;  size_t d_scratch_bytes = 0;
@@ -229,12 +231,19 @@ void fbx_host_bwd_score(const float *xmx, int L, float *totscale, float *sc, int
 // decode.cu: the region trigger of p7_domaindef_ByPosteriorHeuristics (max_i mocc[i] >= rt1) and the gather of selected specials
 int launch_region_trigger(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                           const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int32_t *d_own,
-                          float *d_mocc_max, int32_t *d_flag, unsigned int *d_nflag);
+                          float *d_mocc_max, int32_t *d_flag, unsigned int *d_nflag, float slack = 0.0f);
 int launch_gather_xmx(p7gpu_ctx *ctx, int lane, const float *d_fx, const float *d_bx, const int64_t *d_src, const int64_t *d_dst,
                       const int32_t *d_nfloats, int64_t n, float *d_ofx, float *d_obx);
 // decode.cu: p7_DomainDecoding (btot, etot, mocc per row + Forward's SCALE column and xC(L)) for selected targets, 4*(L+1)+2 floats each
 int launch_domain_decoding(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                            const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int64_t *d_doff, float *d_dec);
 int launch_bias(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
-                float *d_filtersc);
+                float *d_filtersc, int32_t *d_unsure_list = nullptr, unsigned int *d_unsure_count = nullptr);
+// p7_bg_FilterScore (p7_bg.c:472-484; esl_hmm_Forward, easel/esl_hmm.c:351-409) on the host, host libm: the bias kernel's arithmetic
+// for the few targets where it reports that a 1-ulp difference between CUDA's and glibc's log() could show (bias.cu)
+float host_bias_filtersc(const BiasHmm &h, const uint8_t *x, int L);
+// recompute filtersc on the host for the work items the bias kernel could not be sure of and patch them into d_filtersc;
+// h_filtersc (optional) is patched as well.  *nfixed (optional) receives their number.
+int fix_unsure_filtersc(p7gpu_ctx *ctx, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, float *d_filtersc,
+                        const int32_t *d_unsure_list, const unsigned int *d_unsure_count, float *h_filtersc, unsigned *nfixed);
 }  // namespace p7g

@@ -317,17 +317,28 @@ static int bias_vit_on_device(p7gpu_ctx *ctx, const p7gpu_profile *prof, const D
   P7G_CHECK(d_sums.alloc(16, st)); P7G_CHECK(d_pos.alloc(4 * (size_t) npass, st)); P7G_CHECK(d_vpos.alloc(4 * (size_t) npass, st));
   P7G_CHECK(d_cnt.alloc(16, st)); P7G_CHECK(d_vf.alloc(4 * (size_t) npass, st)); P7G_CHECK(d_vs.alloc(4 * (size_t) npass, st));
   P7G_CUDA(cudaMemsetAsync(d_sums.p, 0, 16, st)); P7G_CUDA(cudaMemsetAsync(d_cnt.p, 0, 16, st));
-  P7G_CHECK(launch_bias(ctx, 0, prof, dbv, mp.d_idx64.as<int64_t>(), npass, d_f.as<float>()));
+  DevBuf d_unsure, d_ucount;
+  P7G_CHECK(d_unsure.alloc(4 * (size_t) npass, st)); P7G_CHECK(d_ucount.alloc(16, st));
+  P7G_CHECK(launch_bias(ctx, 0, prof, dbv, mp.d_idx64.as<int64_t>(), npass, d_f.as<float>(), d_unsure.as<int32_t>(), d_ucount.as<unsigned int>()));
   const unsigned nb = (npass + 255) / 256;
+  bool refixed = false;
+redo_decisions:
+  P7G_CUDA(cudaMemsetAsync(d_sums.p, 0, 16, st));
   bias_decide_kernel<<<nb, 256, 0, st>>>(npass, mp.g_usc.as<float>(), d_f.as<float>(), mp.g_len.as<int32_t>(), T1, T2,
                                          d_keep.as<uint8_t>(), d_need.as<uint8_t>(), d_sums.as<unsigned long long>());
   P7G_CUDA(cudaGetLastError());
   unsigned *cnt = d_cnt.as<unsigned>();
   P7G_CHECK(select_positions(ctx, d_keep.as<uint8_t>(), npass, d_pos.as<int32_t>(), cnt + 0));
   P7G_CHECK(select_positions(ctx, d_need.as<uint8_t>(), npass, d_vpos.as<int32_t>(), cnt + 1));
-  unsigned h_cnt[4] = {0, 0, 0, 0};
+  unsigned h_cnt[4] = {0, 0, 0, 0}, h_unsure = 0;
   P7G_CUDA(cudaMemcpyAsync(h_cnt, cnt, 8, cudaMemcpyDeviceToHost, st));
+  P7G_CUDA(cudaMemcpyAsync(&h_unsure, d_ucount.p, 4, cudaMemcpyDeviceToHost, st));
   P7G_CUDA(cudaStreamSynchronize(st));
+  if (h_unsure && !refixed) {                                        // ~3 targets per 10^7: filtersc from the host libm, decisions again
+    P7G_CHECK(fix_unsure_filtersc(ctx, prof, dbv, mp.d_idx64.as<int64_t>(), d_f.as<float>(), d_unsure.as<int32_t>(), d_ucount.as<unsigned int>(), nullptr, nullptr));
+    refixed = true;
+    goto redo_decisions;
+  }
   const unsigned nc = h_cnt[0], nv = h_cnt[1];
   res->counters.n_past_bias = nc;
   ctx->launches += 1;
@@ -422,7 +433,10 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   if (do_bias && npass) {
     DevBuf d_f; P7G_CHECK(d_f.alloc(4 * (size_t) npass, st));
     for (unsigned j = 0; j < npass; j++) res->stage_nres[1] += (uint64_t) mp.len[j];
-    P7G_CHECK(launch_bias(ctx, 0, prof, dbv, mp.d_idx64.as<int64_t>(), npass, d_f.as<float>()));
+    DevBuf d_unsure, d_ucount;
+    P7G_CHECK(d_unsure.alloc(4 * (size_t) npass, st)); P7G_CHECK(d_ucount.alloc(16, st));
+    P7G_CHECK(launch_bias(ctx, 0, prof, dbv, mp.d_idx64.as<int64_t>(), npass, d_f.as<float>(), d_unsure.as<int32_t>(), d_ucount.as<unsigned int>()));
+    P7G_CHECK(fix_unsure_filtersc(ctx, prof, dbv, mp.d_idx64.as<int64_t>(), d_f.as<float>(), d_unsure.as<int32_t>(), d_ucount.as<unsigned int>(), nullptr, nullptr));
     P7G_CUDA(cudaMemcpyAsync(filtersc.data(), d_f.p, 4 * (size_t) npass, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaStreamSynchronize(st));
   }
@@ -568,7 +582,8 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
       if (o->region_trigger) {                                       // p7_domaindef.c:419 on the device (decode.cu)
         P7G_CHECK(d_mocc.alloc(4 * nb, st)); P7G_CHECK(d_flag.alloc(4 * nb, st));
         P7G_CHECK(launch_region_trigger(ctx, 0, prof, dbv, d_bidx.as<int64_t>(), (int64_t) nb, d_fx.as<float>(), d_bx.as<float>(),
-                                        d_boff.as<int64_t>(), d_own.as<int32_t>(), d_mocc.as<float>(), d_flag.as<int32_t>(), nullptr));
+                                        d_boff.as<int64_t>(), d_own.as<int32_t>(), d_mocc.as<float>(), d_flag.as<int32_t>(), nullptr,
+                                        exact ? 0.0f : 1.0e-4f));
         P7G_CUDA(cudaMemcpyAsync(mocc.data(), d_mocc.p, 4 * nb, cudaMemcpyDeviceToHost, st));
         P7G_CUDA(cudaMemcpyAsync(flag.data(), d_flag.p, 4 * nb, cudaMemcpyDeviceToHost, st));
       }

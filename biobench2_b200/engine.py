@@ -17,7 +17,7 @@ KERNEL_SSV, KERNEL_MSVJ, KERNEL_VIT, KERNEL_FWD, KERNEL_BWD, KERNEL_BIAS, KERNEL
 
 EXPORTS = [
     "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
-    "p7gpu_ctx_launch_count", "p7gpu_ctx_synchronize", "p7gpu_ctx_set_option", "p7gpu_ctx_last_vit_redo",
+    "p7gpu_ctx_launch_count", "p7gpu_ctx_synchronize", "p7gpu_ctx_set_option", "p7gpu_ctx_last_vit_redo", "p7gpu_ctx_bias_recomputed",
     "p7gpu_ctx_set_timing", "p7gpu_ctx_reset_timing", "p7gpu_ctx_kernel_time", "p7gpu_measure_peaks",
     "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M", "p7gpu_profile_set_biasfilter",
     "p7gpu_seqdb_upload", "p7gpu_seqdb_adopt_device", "p7gpu_seqdb_destroy", "p7gpu_seqdb_nseq", "p7gpu_seqdb_nres",
@@ -93,6 +93,8 @@ def lib():
         L.p7gpu_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int]
         L.p7gpu_ctx_last_vit_redo.restype = i64
         L.p7gpu_ctx_last_vit_redo.argtypes = [vp]
+        L.p7gpu_ctx_bias_recomputed.restype = i64
+        L.p7gpu_ctx_bias_recomputed.argtypes = [vp]
         L.p7gpu_ctx_set_timing.argtypes = [vp, C.c_int]
         L.p7gpu_ctx_reset_timing.argtypes = [vp]
         L.p7gpu_ctx_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
@@ -216,6 +218,11 @@ class Context:
     def last_vit_redo(self):
         """targets of the last Viterbi launch that left the packed kernel's window and were redone exactly"""
         return lib().p7gpu_ctx_last_vit_redo(self.h)
+
+    @property
+    def bias_recomputed(self):
+        """bias-filter scores recomputed on the host so far (targets the bias kernel could not certify, bias.cu)"""
+        return lib().p7gpu_ctx_bias_recomputed(self.h)
 
     def set_timing(self, on=True):
         _check(lib().p7gpu_ctx_set_timing(self.h, int(on)))

@@ -91,6 +91,11 @@ int         p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value);
 /* how many targets of the last Viterbi launch on the ctx's main stream left the packed kernel's window and were
  * recomputed by the exact kernel (diagnostic) */
 int64_t     p7gpu_ctx_last_vit_redo(p7gpu_ctx *ctx);
+/* how many bias-filter scores this ctx has recomputed on the host so far: the bias kernel reports the targets for which a
+ * 1-ulp difference between CUDA's and glibc's double log() could change the float it is rounded to (about three per 10^7-target
+ * pass), and those are redone with the host libm, so p7_bg_FilterScore is the reference's bit for bit by construction
+ * (option "bias_window_log2" = n widens the test to 2^-n, for tests) */
+int64_t     p7gpu_ctx_bias_recomputed(const p7gpu_ctx *ctx);
 
 /* Diagnostics for bench.py's roofline line (no reference counterpart; cf. the Mc/s drivers msvfilter.c:512-600).
  * With timing on, every kernel launch is bracketed by CUDA events on the launching stream;

@@ -278,3 +278,31 @@ def test_unsupported_model_length_is_rejected(ctx):
     with pytest.raises(engine.P7GpuError) as e:
         engine.Profile(ctx, Fake())
     assert e.value.code == engine.EINVAL
+
+
+@pytest.mark.parametrize("name", ["globins4", "synth_M400", "tufa420_sprot"])
+def test_bias_filter_score_is_exact_by_construction(gpu_ctx, name):
+    """bias.cu certifies every (float) log((double) x) it takes; targets it cannot certify are recomputed with the host libm.
+    With the certainty window widened from 2^-48 to 2^-16 most targets take the host path: filtersc must stay the reference's
+    bit for bit, the pipeline counters must not move, and the host path must actually have run."""
+    from conftest import golden_set, bits
+    g = golden_set(name)
+    prof = engine.Profile(gpu_ctx, g.oprofile); db = engine.SeqDB.upload(gpu_ctx, g.db)
+    idx = np.nonzero(g.db.lengths > 0)[0].astype(np.int64)
+    try:
+        before = gpu_ctx.bias_recomputed
+        f0 = engine.biasfilter_batch(gpu_ctx, prof, db, idx)
+        assert np.array_equal(bits(f0), bits(g.vec["filtersc"][idx]))
+        normal = gpu_ctx.bias_recomputed - before
+        gpu_ctx.set_option("bias_window_log2", 16)
+        f1 = engine.biasfilter_batch(gpu_ctx, prof, db, idx)
+        forced = gpu_ctx.bias_recomputed - before - normal
+        assert np.array_equal(bits(f1), bits(g.vec["filtersc"][idx]))
+        assert forced > normal and forced >= len(idx) // 20, (normal, forced, len(idx))
+        r1 = engine.pipeline_run(gpu_ctx, prof, db, want_specials=False)
+        gpu_ctx.set_option("bias_window_log2", 0)
+        r0 = engine.pipeline_run(gpu_ctx, prof, db, want_specials=False)
+        assert list(r1.counters) == list(r0.counters) == list(g.vec["pli_counters"])
+    finally:
+        gpu_ctx.set_option("bias_window_log2", 0)
+        db.close(); prof.close()

@@ -64,7 +64,9 @@ def test_max_pipeline_returns_specials_only_where_the_trigger_fires(ctx, name):
         n = (int(a["L"]) + 1) * 6
         fx = full.fwd_xmx[a["xmx_offset"]: a["xmx_offset"] + n]; bx = full.bck_xmx[a["xmx_offset"]: a["xmx_offset"] + n]
         d = o.domain_decoding(int(a["L"]), fx, bx, int(a["bck_own_scales"]))
-        assert b["region_flag"] == (1 if (d["triggered"] or a["bck_own_scales"]) else 0)
+        # fast specials (<= 1e-4 relative): the pipeline flags conservatively, rt1 - 1e-4 (decode.cu); exact-order specials: rt1 itself
+        want = 1 if (d["triggered"] or a["bck_own_scales"] or d["mocc_max"] >= np.float32(0.25) - np.float32(1.0e-4)) else 0
+        assert b["region_flag"] == want
         assert bits(b["mocc_max"]) == bits(d["mocc_max"])
         if b["region_flag"] == 1:                 # the returned specials are the same bytes
             assert np.array_equal(bits(trig.fwd_xmx[b["xmx_offset"]: b["xmx_offset"] + n]), bits(fx))
