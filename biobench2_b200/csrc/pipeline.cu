@@ -447,13 +447,18 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     for (size_t j = lo; j < hi; j++)
       Pv[j] = host_filter_pvalue_gumbel(mp.usc[j], do_bias ? filtersc[j] : hl[mp.len[j]].nullsc, ev[0], ev[1]);
   });
-  for (unsigned j = 0; j < npass; j++) {
-    if (do_bias && Pv[j] > F1) continue;
+  auto make_cand = [&](unsigned j) {
     Cand c;
     c.idx = mp.idx[j]; c.L = mp.len[j]; c.msv_st = mp.st[j]; c.vit_st = -1; c.usc = mp.usc[j]; c.nullsc = hl[c.L].nullsc;
     c.filtersc = do_bias ? filtersc[j] : c.nullsc; c.vfsc = NAN; c.fwdsc = NAN; c.bcksc = NAN; c.ftot = 0.f; c.btot = 0.f; c.P = Pv[j];
     c.pos = (int32_t) j;
-    cand.push_back(c);
+    return c;
+  };
+  if (!do_bias) {                                                    // --max / --nobias: every MSV survivor goes on (10^7 records under --max)
+    cand.resize(npass);
+    parallel_for(npass, [&](size_t lo, size_t hi) { for (size_t j = lo; j < hi; j++) cand[j] = make_cand((unsigned) j); });
+  } else {
+    for (unsigned j = 0; j < npass; j++) if (!(Pv[j] > F1)) cand.push_back(make_cand(j));
   }
   res->counters.n_past_bias = cand.size();
   tr.mark("after_msv: bias P-values");
@@ -525,6 +530,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
   for (size_t lo = 0; lo < cand.size();) {
     size_t hi = lo, ext = 0;
     std::vector<int64_t> idx, xoff;
+    idx.reserve(std::min<size_t>(cand.size() - lo, (size_t) 1 << 20)); xoff.reserve(idx.capacity());
     while (hi < cand.size() && (hi == lo || ext + (size_t) (cand[hi].L + 1) * 6 <= slice_floats)) {
       idx.push_back(cand[hi].idx); xoff.push_back((int64_t) ext); ext += (size_t) (cand[hi].L + 1) * 6;
       res->stage_nres[exact && F3 < 1.0 ? 5 : 3] += (uint64_t) cand[hi].L; hi++;
@@ -541,7 +547,8 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     std::vector<float> fsc(n), ftot(n);
     P7G_CUDA(cudaMemcpyAsync(fsc.data(), d_sc.p, 4 * n, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaMemcpyAsync(ftot.data(), d_tot.p, 4 * n, cudaMemcpyDeviceToHost, st));
-    P7G_CUDA(cudaStreamSynchronize(st));
+    const bool allpass = F3 >= 1.0;                                  // --max: no decision between the two parsers, so no host round trip either
+    if (!allpass) P7G_CUDA(cudaStreamSynchronize(st));
     if (exact && F3 < 1.0) {                                     // the F3 test needs the exact score: host libm on the specials
       if (!exact_fx.resize(ext)) { set_error("pipeline: out of host memory for %zu floats of specials", ext); return P7GPU_EMEM; }
       P7G_CHECK(d2h_large(ctx, exact_fx.data(), d_fx.p, 4 * ext));
@@ -552,6 +559,12 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     }
     tr.mark("  slice: forward done");
     std::vector<int64_t> bidx, boff; std::vector<size_t> bwhere;
+    if (allpass) {                                                   // --max: P <= 1 always passes (p7_pipeline.c:730); no P-value, no compaction
+      bidx = idx; boff = xoff; bwhere.resize(n);
+      parallel_for(n, [&](size_t a, size_t b) { for (size_t k = a; k < b; k++) bwhere[k] = lo + k; });   // scores are read after the Backward sync
+      res->stage_nres[4] += (uint64_t) ext / 6 - n;                  // sum of L over the slice: ext = sum (L+1)*6
+      if (o->stage_records) for (size_t k = 0; k < n; k++) if (cand[lo + k].pos >= 0) stage[(size_t) cand[lo + k].pos] = 4;
+    } else
     for (size_t k = 0; k < n; k++) {
       Cand &c = cand[lo + k];
       c.fwdsc = fsc[k]; c.ftot = ftot[k];
@@ -564,7 +577,8 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     if (!bidx.empty()) {
       const size_t nb = bidx.size();
       DevBuf d_bidx, d_boff, d_bsc, d_bst, d_btot, d_bx, d_own, d_mocc, d_flag;
-      P7G_CHECK(upload_idx(ctx, bidx, &d_bidx)); P7G_CHECK(upload_idx(ctx, boff, &d_boff));
+      if (allpass) { d_bidx.p = d_idx.p; d_bidx.s = st; d_idx.p = nullptr; d_boff.p = d_xoff.p; d_boff.s = st; d_xoff.p = nullptr; }   // same lists: hand the buffers over
+      else { P7G_CHECK(upload_idx(ctx, bidx, &d_bidx)); P7G_CHECK(upload_idx(ctx, boff, &d_boff)); }
       P7G_CHECK(d_bsc.alloc(4 * nb, st)); P7G_CHECK(d_bst.alloc(4 * nb, st)); P7G_CHECK(d_btot.alloc(4 * nb, st));
       P7G_CHECK(d_own.alloc(4 * nb, st));
       const bool keep_bx = o->want_specials || o->region_trigger;
@@ -588,6 +602,7 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
         P7G_CUDA(cudaMemcpyAsync(flag.data(), d_flag.p, 4 * nb, cudaMemcpyDeviceToHost, st));
       }
       P7G_CUDA(cudaStreamSynchronize(st));
+      if (allpass) parallel_for(n, [&](size_t a, size_t b) { for (size_t k = a; k < b; k++) { Cand &c = cand[lo + k]; c.fwdsc = fsc[k]; c.ftot = ftot[k]; c.P = 0.0; } });
       tr.mark("  slice: backward + trigger done");
       // which survivors' specials go to the host: all of them, or those whose region trigger fired; with opts->decode the flagged
       // ones get their p7_DomainDecoding arrays instead (16 bytes per row for 48), except those the host must decide itself
@@ -673,17 +688,25 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
         }
       }
       tr.mark("  slice: specials on the host");
-      for (size_t k = 0; k < nb; k++) {
-        const Cand &c = cand[bwhere[k]];
-        p7gpu_survivor s;
-        s.seqidx = c.idx; s.L = c.L; s.msv_status = c.msv_st; s.vit_status = c.vit_st;
-        s.usc = c.usc; s.vfsc = c.vfsc; s.fwdsc = c.fwdsc; s.bcksc = bsc[k]; s.nullsc = c.nullsc; s.filtersc = c.filtersc;
-        s.fwd_totscale = c.ftot; s.bck_totscale = btot[k];
-        s.bck_own_scales = own[k];
-        s.xmx_offset = host_off[k];
-        s.region_flag = flag[k]; s.mocc_max = mocc[k];
-        s.dec_offset = dec_off[k];
-        res->survivors.push_back(s);
+      {
+        const size_t base = res->survivors.size();
+        if (F3 >= 1.0 && res->survivors.capacity() < cand.size()) res->survivors.reserve(cand.size());   // --max: one allocation, not a doubling series
+        res->survivors.resize(base + nb);
+        p7gpu_survivor *out = res->survivors.data() + base;
+        parallel_for(nb, [&](size_t a, size_t b) {
+          for (size_t k = a; k < b; k++) {
+            const Cand &c = cand[bwhere[k]];
+            p7gpu_survivor s;
+            s.seqidx = c.idx; s.L = c.L; s.msv_status = c.msv_st; s.vit_status = c.vit_st;
+            s.usc = c.usc; s.vfsc = c.vfsc; s.fwdsc = c.fwdsc; s.bcksc = bsc[k]; s.nullsc = c.nullsc; s.filtersc = c.filtersc;
+            s.fwd_totscale = c.ftot; s.bck_totscale = btot[k];
+            s.bck_own_scales = own[k];
+            s.xmx_offset = host_off[k];
+            s.region_flag = flag[k]; s.mocc_max = mocc[k];
+            s.dec_offset = dec_off[k];
+            out[k] = s;
+          }
+        });
       }
       host_floats += need;
       res->n_region_flagged += (uint64_t) (src.size() + didx.size());
