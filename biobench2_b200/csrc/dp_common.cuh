@@ -46,4 +46,10 @@ __device__ __forceinline__ bool next_target(const DpCommon &p, int lane, long lo
   X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(16) X(18) X(20) X(24) X(28) X(32) \
   X(40) X(48) X(56) X(64) X(80) X(96) X(112) X(130)
 
+// the first-generation one-warp Forward/Backward kernels (fwdbwd.cu) are a cross-check only (option "fb_one_warp"); beyond
+// C = 32 cells per lane (M > 1024) they spilled to 3-5 KB of local memory per thread, so they are not instantiated there —
+// the exact-order kernels (fbx.cu) against the bit-exact striped oracle are the stronger check at every M
+#define P7G_FB_ONEWARP_C_CASES(X) \
+  X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(16) X(18) X(20) X(24) X(28) X(32)
+
 }  // namespace p7g

@@ -365,9 +365,9 @@ int launch_fwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   }
   switch (prof->dpC) {
 #define X(CV) case CV: return launch_fb_c<CV, false>(ctx, ln.stream, p);
-    P7G_DP_C_CASES(X)
+    P7G_FB_ONEWARP_C_CASES(X)
 #undef X
-  default: set_error("fwd: unsupported cells-per-lane %d", prof->dpC); return P7GPU_EINVAL;
+  default: set_error("fwd: the one-warp cross-check kernels cover M <= 1024 (cells per lane %d)", prof->dpC); return P7GPU_EINVAL;
   }
 }
 
@@ -387,9 +387,9 @@ int launch_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   }
   switch (prof->dpC) {
 #define X(CV) case CV: return launch_fb_c<CV, true>(ctx, ln.stream, p);
-    P7G_DP_C_CASES(X)
+    P7G_FB_ONEWARP_C_CASES(X)
 #undef X
-  default: set_error("bwd: unsupported cells-per-lane %d", prof->dpC); return P7GPU_EINVAL;
+  default: set_error("bwd: the one-warp cross-check kernels cover M <= 1024 (cells per lane %d)", prof->dpC); return P7GPU_EINVAL;
   }
 }
 

@@ -75,7 +75,7 @@ def test_cta_per_target_kernels_vs_golden(ctx, name, cmax):
         db.close(); prof.close()
 
 
-@pytest.mark.parametrize("name", ["synth_M2000", "synth_M800", "Pkinase"])
+@pytest.mark.parametrize("name", ["synth_M800", "synth_M400", "Pkinase"])        # the one-warp cross-check kernels cover M <= 1024
 def test_cta_per_target_kernels_vs_one_warp_kernels(ctx, name):
     g = golden_set(name)
     with forced_geometry(1, 0):
