@@ -162,23 +162,32 @@ struct VitpParams {
   VitScalars s;
   VitPacked w;
   long long *redo_list; unsigned int *redo_count;
+  uint32_t k16;         // 65536, as a kernel parameter so that ptxas keeps x * k16 / mulhi(x, k16) on the multiplier pipe
 };
 
-__device__ __forceinline__ uint32_t pack2(int v) { return (uint32_t) (v & 0xffff) * 0x00010001u; }
-// lane l receives lane l-1's register; lane 0 receives (floor, low half of lane 31) = nodes 0 and 32*C2
-__device__ __forceinline__ uint32_t rot_prev(uint32_t v, int lane, uint32_t FLv)
+__device__ __forceinline__ uint32_t pack2(int v) { return __byte_perm((uint32_t) v, 0u, 0x1010); }
+// max over the warp of both halves of v.  v * 65536 puts the low half on top, so the high half of the packed maximum is
+// max(lo, hi); a 32-bit signed maximum over the warp is decided by the high halves, and a multiply-high by 65536 brings it
+// down (arithmetic >> 16).  k16 is 65536 in a register the compiler cannot see through: both multiplies stay on the
+// multiplier pipe instead of turning into shifts on the integer pipe.
+__device__ __forceinline__ int warp_max16x2(uint32_t v, uint32_t k16)
 {
-  const uint32_t r = __shfl_sync(0xffffffffu, v, (lane + 31) & 31);
-  return lane == 0 ? __byte_perm(r, FLv, 0x1054) : r;
-}
-__device__ __forceinline__ int warp_max16x2(uint32_t v)
-{
-  const uint32_t m = __vmaxs2(v, __byte_perm(v, 0u, 0x1032));          // both halves = max(lo, hi)
-  return __reduce_max_sync(0xffffffffu, (int) m) >> 16;
+  const uint32_t m = __vmaxs2(v, v * k16);
+  int r = __reduce_max_sync(0xffffffffu, (int) m), e;
+  asm("mul.hi.s32 %0, %1, %2;" : "=r"(e) : "r"(r), "r"(k16));
+  return e;
 }
 
+// The integer pipe of sm_100 issues every instruction (plain or packed DPX) at 16 lanes per clock, and the row loop is bound
+// by it (ncu: ALU 83 % busy), so everything that is not one of the 9 max-plus operations per register is kept off that pipe:
+// residues arrive as byte loads one row ahead (no shift/mask), the rotation by one lane fixes lane 0 with one multiply-add
+// (r * 65536 + floor moves lane 31's low half up; r * 1 + 0 elsewhere), the specials live in the window domain (no
+// int16 re-truncation: max(xC, .) and max(xJ, .) never leave [-32768, 32766], xB >= xN + tNB), and the >> 16 after the warp
+// reductions is a multiply-high.
+constexpr int VITP_BIG_THREADS = 256;   // transitions in shared memory (C2 > 14): one CTA per SM, so more warps share the tables
+
 template <int C2, bool TREG>
-__global__ void __launch_bounds__(DP_THREADS) vitp_kernel(const VitpParams p)
+__global__ void __launch_bounds__(TREG ? DP_THREADS : VITP_BIG_THREADS, TREG ? (C2 <= 7 ? 4 : 2) : 1) vitp_kernel(const VitpParams p)
 {
   extern __shared__ __align__(16) uint32_t s_vp[];
   {
@@ -188,6 +197,7 @@ __global__ void __launch_bounds__(DP_THREADS) vitp_kernel(const VitpParams p)
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
+  const int prevl = (lane + 31) & 31;
   const uint32_t *s_rw = s_vp + lane;
   const uint32_t *s_tw = s_vp + NTABROWS * C2 * 32 + lane;
   uint32_t rBM[TREG ? C2 : 1], rMM[TREG ? C2 : 1], rIM[TREG ? C2 : 1], rDM[TREG ? C2 : 1], rMD[TREG ? C2 : 1],
@@ -208,39 +218,53 @@ __global__ void __launch_bounds__(DP_THREADS) vitp_kernel(const VitpParams p)
   const uint32_t wh = __ldg(p.scanw + 5 * 32 + lane);
   const int W0 = p.w.W0;
   const uint32_t FLv = pack2(W0);
+  // s_pt[j][lane] = (clamped) sum of the lane's tDD[0..j-1], both halves: what a carry entering the lane has paid by cell j
+  __shared__ uint32_t s_ptp[C2 * 32];
+  if (threadIdx.x < 32) {
+    int lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < C2; j++) {
+      s_ptp[j * 32 + lane] = ((uint32_t) max(lo, -p.w.T) & 0xffffu) | ((uint32_t) max(hi, -p.w.T) << 16);
+      const uint32_t t = TREG ? rDD[j] : s_tw[(7 * C2 + j) * 32];
+      lo += (int) (short) (t & 0xffffu); hi += (int) t >> 16;
+    }
+  }
+  __syncthreads();
+  const uint32_t *s_pt = s_ptp + lane;
+  // lane l receives lane l-1's register; lane 0 receives (floor, low half of lane 31) = nodes 0 and 32*C2
+  uint32_t rmul = lane == 0 ? 0x10000u : 1u;
+  const uint32_t radd = lane == 0 ? (FLv & 0xffffu) : 0u;
+  const uint32_t k16 = p.k16;
+  asm("" : "+r"(rmul));                                                // keep it a multiply (a shift would go to the integer pipe)
+#define ROT_(v) (__shfl_sync(0xffffffffu, (v), prevl) * rmul + radd)
+  const int cEm = p.s.xw_E_move, cEl = p.s.xw_E_loop, ddb = p.s.ddbound_w;
 
   long long s, out;
   while (next_target(p.c, lane, &s, &out)) {
     const int L = p.c.len[s];
-    const long long o = p.c.off[s];
+    const uint8_t *seq = p.c.res + p.c.off[s];
     const int xw_move = p.c.lc[L].xw_move;
     const int Fl = p.s.base_w + xw_move + p.w.floff;
     const int SH = Fl - W0;                                            // reference value = window value + SH
-    const int W1t = min(p.w.W1, 32766 - SH);                           // stay below the reference's overflow test as well
-    bool redo = Fl < -32768;
+    const unsigned span = (unsigned) max(0, min(p.w.W1, 32766 - SH) - W0);   // row maxima must stay in (W0, W0 + span]: inside the
+    bool redo = Fl < -32768;                                           // window and below the reference's overflow test
     uint32_t mp[C2], ip[C2], dp[C2];
 #pragma unroll
     for (int j = 0; j < C2; j++) mp[j] = ip[j] = dp[j] = FLv;
-    int xN = p.s.base_w, xB = (short) (xN + xw_move), xJ = VNEG, xC = VNEG;
+    // specials in window units.  vitfilter.c:178-181 truncates to int16 on assignment; max(xC, .) and max(xJ, .) start at
+    // -32768 and are fed by xE + (a cost <= 0) with xE <= 32766, and xB >= xN + tNB, so no truncation ever changes a value
+    const int xNB = p.s.base_w + xw_move - SH;
+    int xB = xNB, xJ = VNEG - SH, xC = VNEG - SH;
 
-    // residues, four per aligned 32-bit load, one word prefetched ahead
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(p.c.res + (o & ~3LL));
-    int sh = (int) (o & 3) * 8;
-    uint32_t cur = __ldg(wp), nxt = __ldg(wp + 1);
-    wp += 2;
-    if (!redo)
-#pragma unroll (TREG ? 2 : 1)
-    for (int i = 0; i < L; i++) {
-      const uint32_t x = (cur >> sh) & 0xffu;
-      sh += 8;
-      if (sh == 32) { sh = 0; cur = nxt; nxt = __ldg(wp++); }
-      const uint32_t *rwx = s_rw + x * (C2 * 32);
-      const uint32_t xBv = pack2(xB - SH);
-      uint32_t pm = rot_prev(mp[C2 - 1], lane, FLv);
-      uint32_t pi = rot_prev(ip[C2 - 1], lane, FLv);
-      uint32_t pd = rot_prev(dp[C2 - 1], lane, FLv);
+    // one DP row; false when the row maximum leaves the window (or reaches the reference's overflow test, :177)
+    uint32_t pmN = FLv, piN = FLv;                                     // row i-1's M and I, already rotated by one lane
+    auto row = [&](const uint32_t x) -> bool {
+      const uint32_t *rwx = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_rw) + x * (C2 * 128));
+      const uint32_t xBv = pack2(xB);
+      uint32_t pm = pmN;
+      uint32_t pi = piN;
+      uint32_t pd = ROT_(dp[C2 - 1]);
       uint32_t xEl = FLv, Dml = FLv, dcv = FLv, pendE = 0u, pendD = 0u;
-      bool have = false;
 #pragma unroll
       for (int j = 0; j < C2; j++) {
         uint32_t sv = __viaddmax_s16x2(xBv, TP_(BM, 0, j), FLv);       // vitfilter.c:146-150
@@ -253,35 +277,55 @@ __global__ void __launch_bounds__(DP_THREADS) vitp_kernel(const VitpParams p)
         dp[j] = dcv;                                                   // D(i,k) = M(i,k-1)+tMD so far (:160-161)
         dcv = __viaddmax_s16x2(sv, TP_(MD, 4, j), FLv);                // :166
         ip[j] = __viaddmax_s16x2(pi, TP_(II, 6, j), __viaddmax_s16x2(pm, TP_(MI, 5, j), FLv));   // :170-171
-        if (have) { xEl = __vimax3_s16x2(xEl, pendE, sv); Dml = __vimax3_s16x2(Dml, pendD, dcv); have = false; }
-        else      { pendE = sv; pendD = dcv; have = true; }
+        // row maxima of M and of the provisional D, two new values per three-input max
+        if (j == 0) { xEl = sv; Dml = dcv; }
+        else if (j & 1) { pendE = sv; pendD = dcv; }
+        else { xEl = __vimax3_s16x2(xEl, pendE, sv); Dml = __vimax3_s16x2(Dml, pendD, dcv); }
       }
-      if (have) { xEl = __vmaxs2(xEl, pendE); Dml = __vmaxs2(Dml, pendD); }
-      dp[0] = rot_prev(dcv, lane, FLv);
-      const int xEw = warp_max16x2(xEl);
-      if (xEw > W1t || xEw <= W0) { redo = true; break; }
-      const int xE = xEw + SH;
-      xC = (short) max(xC, xE + p.s.xw_E_move);                        // :178-181
-      xJ = (short) max(xJ, xE + p.s.xw_E_loop);
-      xB = (short) max(xJ + xw_move, xN + xw_move);
-      const int Dmax = warp_max16x2(Dml) + SH;
-      if (Dmax + p.s.ddbound_w > xB) {                                 // lazy F, :198-232
+      if (C2 > 1 && !(C2 & 1)) { xEl = __vmaxs2(xEl, pendE); Dml = __vmaxs2(Dml, pendD); }
+      dp[0] = ROT_(dcv);
+      pmN = ROT_(mp[C2 - 1]); piN = ROT_(ip[C2 - 1]);                  // for the next row, under the reductions' latency
+      const int xE = warp_max16x2(xEl, k16);
+      const int Dmax = warp_max16x2(Dml, k16);
+      if ((unsigned) (xE - W0 - 1) >= span) return false;
+      xC = __viaddmax_s32(xE, cEm, xC);                                // :178-181
+      xJ = __viaddmax_s32(xE, cEl, xJ);
+      xB = __viaddmax_s32(xJ, xw_move, xNB);
+      if (Dmax + ddb > xB) {                                           // lazy F, :198-232
         // max-plus prefix over k: (1) inside the lane; (2) X = value leaving the lane, Kogge-Stone over lanes with the
         // row-invariant lane-span sums wd[] (both halves at once); (3) the low half's total enters the high half (wh);
-        // (4) the carry entering each lane runs down the lane again.
+        // (4) the carry entering each lane reaches cell j after paying the lane's tDD[0..j-1] (s_pt).
 #pragma unroll
         for (int j = 1; j < C2; j++) dp[j] = __viaddmax_s16x2(dp[j - 1], TP_(DD, 7, j - 1), dp[j]);
         uint32_t X = __viaddmax_s16x2(dp[C2 - 1], TP_(DD, 7, C2 - 1), FLv);
 #pragma unroll
         for (int d = 0; d < 5; d++) X = __viaddmax_s16x2(__shfl_up_sync(0xffffffffu, X, 1 << d), wd[d], X);
-        const uint32_t u = __byte_perm(__shfl_sync(0xffffffffu, X, 31), FLv, 0x1054);   // (floor, X_lo(31))
+        const uint32_t u = __shfl_sync(0xffffffffu, X, 31) * 0x10000u + (FLv & 0xffffu);   // (floor, X_lo(31))
         X = __viaddmax_s16x2(u, wh, X);
-        uint32_t carry = __shfl_up_sync(0xffffffffu, X, 1);
-        if (lane == 0) carry = u;
-        dp[0] = __vmaxs2(dp[0], carry);
+        const uint32_t carry = ROT_(X);                                // lane 0: (floor, X_lo(31)) = u again (step 3 left X_lo alone)
 #pragma unroll
-        for (int j = 1; j < C2; j++) dp[j] = __viaddmax_s16x2(dp[j - 1], TP_(DD, 7, j - 1), dp[j]);
+        for (int j = 0; j < C2; j++) dp[j] = __viaddmax_s16x2(carry, s_pt[j * 32], dp[j]);
       }
+      return true;
+    };
+
+    // residues as byte loads, fetched one group of rows ahead (seq[L] is the sentinel byte, so reading it is safe)
+    if (!redo) {
+      int i = 0;
+      uint32_t xn = __ldg(seq);
+      if (TREG) {
+        for (; i + 4 <= L; i += 4) {
+          const uint32_t x0 = xn, x1 = __ldg(seq + i + 1), x2 = __ldg(seq + i + 2), x3 = __ldg(seq + i + 3);
+          xn = __ldg(seq + i + 4);
+          if (!(row(x0) && row(x1) && row(x2) && row(x3))) { redo = true; break; }
+        }
+      }
+      if (!redo)
+        for (; i < L; i++) {
+          const uint32_t x = xn;
+          xn = __ldg(seq + i + 1);
+          if (!row(x)) { redo = true; break; }
+        }
     }
     if (lane == 0) {
       if (redo) {
@@ -289,8 +333,8 @@ __global__ void __launch_bounds__(DP_THREADS) vitp_kernel(const VitpParams p)
         p.redo_list[2 * (long long) t] = s; p.redo_list[2 * (long long) t + 1] = out;
       } else {
         float sc;
-        if (xC > -32768) {                                             // :240-247
-          sc = (float) xC + (float) xw_move - (float) p.s.base_w;
+        if (xC + SH > -32768) {                                        // :240-247
+          sc = (float) (xC + SH) + (float) xw_move - (float) p.s.base_w;
           sc = __fdiv_rn(sc, p.s.scale_w);
           sc = __fsub_rn(sc, 3.0f);
         } else sc = -CUDART_INF_F;
@@ -300,12 +344,14 @@ __global__ void __launch_bounds__(DP_THREADS) vitp_kernel(const VitpParams p)
     }
   }
 #undef TP_
+#undef ROT_
 }
 
 template <int C2>
 static int launch_vitp_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitpParams &p, bool *launched)
 {
   constexpr bool TREG = (C2 <= 14);
+  constexpr int NT = TREG ? DP_THREADS : VITP_BIG_THREADS;
   const size_t smem = (size_t) (NTABROWS + (TREG ? 0 : 8)) * C2 * 32 * sizeof(uint32_t);
   *launched = false;
   if (smem + 1024 > (size_t) ctx->smem_optin) return P7GPU_OK;
@@ -314,14 +360,14 @@ static int launch_vitp_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitpParams &
   int &occ = occ_dev[ctx->device & 63];
   if (occ <= 0) {
     P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DP_THREADS, smem));
+    P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
     if (occ < 1) { set_error("vitp_kernel<%d>: zero occupancy", C2); return P7GPU_ESYS; }
   }
   long long blocks = (long long) ctx->sm_count * occ;
-  long long need = (p.c.n + (DP_THREADS / 32) - 1) / (DP_THREADS / 32);
+  long long need = (p.c.n + (NT / 32) - 1) / (NT / 32);
   if (need < blocks) blocks = need;
   if (blocks < 1) blocks = 1;
-  { LaunchTimer t(ctx, P7GPU_KERNEL_VIT, stream); kern<<<(unsigned) blocks, DP_THREADS, smem, stream>>>(p); }
+  { LaunchTimer t(ctx, P7GPU_KERNEL_VIT, stream); kern<<<(unsigned) blocks, NT, smem, stream>>>(p); }
   P7G_CUDA(cudaGetLastError());
   ctx->launches++;
   *launched = true;
@@ -382,7 +428,7 @@ int launch_vit(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
     P7G_CUDA(cudaMallocAsync((void **) &d_redo, (size_t) n * 2 * sizeof(long long), ln.stream));
     VitpParams q;
     q.c = p.c; q.rwp = prof->d_rwp; q.twp = prof->d_twp; q.scanw = prof->d_scanw; q.s = prof->vit; q.w = prof->vitp;
-    q.redo_list = d_redo; q.redo_count = ln.counters + CTR_VIT_REDO;
+    q.redo_list = d_redo; q.redo_count = ln.counters + CTR_VIT_REDO; q.k16 = 0x10000u;
     bool launched = false;
     int rc = P7GPU_OK;
     switch (prof->vitp.C2) {
