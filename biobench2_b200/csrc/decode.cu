@@ -101,6 +101,33 @@ int launch_gather_xmx(p7gpu_ctx *ctx, int lane, const float *d_fx, const float *
 }
 
 
+// Forward's SCALE column and xC(L) of each item, 4 bytes per row instead of the 24 of its specials: all the host needs to
+// recompute totscale and the Forward score with its own libm (fwdback.c:434,:463).  Block of item j at out + xoff[j]/6:
+// [0] = xC(L), [i] = SCALE(i) for i = 1..L.
+__global__ void __launch_bounds__(256) gather_scale_kernel(const float *fx, const int64_t *xoff, const int64_t *idx, const int32_t *len,
+                                                           long long n, float *out)
+{
+  const int lane = threadIdx.x & 31;
+  const long long j = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= n) return;
+  const int L = len[idx[j]];
+  const float *src = fx + xoff[j];
+  float *dst = out + xoff[j] / 6;
+  for (int i = lane; i <= L; i += 32) dst[i] = i == 0 ? src[(size_t) L * 6 + 4] : src[(size_t) i * 6 + 5];
+}
+
+int launch_gather_scale(p7gpu_ctx *ctx, int lane, const DbView &db, const int64_t *d_idx, int64_t n, const float *d_fx,
+                        const int64_t *d_xoff, float *d_out)
+{
+  if (n <= 0) return P7GPU_OK;
+  const Lane &ln = ctx->lanes[lane];
+  const long long blocks = (n * 32 + 255) / 256;
+  gather_scale_kernel<<<(unsigned) blocks, 256, 0, ln.stream>>>(d_fx, d_xoff, d_idx, db.len, n, d_out);
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return P7GPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // p7_DomainDecoding itself (impl_sse/decoding.c:166-200) for the flagged survivors: btot[i], etot[i], mocc[i], i = 0..L, in the
 // reference's own order of float operations — btot and etot are running sums, so one lane chain does the adds while the 32

@@ -85,6 +85,16 @@ void fbx_host_fwd_score(const float *xmx, int L, float pmove, float *totscale, f
   if (std::isnan(xC) || (L > 0 && xC == 0.0f) || std::isinf(xC)) { *status = P7GPU_ERANGE; *sc = xC; }   // :456-458
   else { *status = P7GPU_OK; *sc = (float) ((double) tot + log((double) (xC * pmove))); }
 }
+// the same from the compact block gather_scale_kernel writes: blk[0] = xC(L), blk[i] = SCALE(i)
+void fbx_host_fwd_score_compact(const float *blk, int L, float pmove, float *totscale, float *sc, int *status)
+{
+  float tot = 0.0f;
+  for (int i = 1; i <= L; i++) { const float s = blk[i]; if (s != 1.0f) tot = (float) ((double) tot + log((double) s)); }
+  const float xC = blk[0];
+  *totscale = tot;
+  if (std::isnan(xC) || (L > 0 && xC == 0.0f) || std::isinf(xC)) { *status = P7GPU_ERANGE; *sc = xC; }   // :456-458
+  else { *status = P7GPU_OK; *sc = (float) ((double) tot + log((double) (xC * pmove))); }
+}
 // same for backward_engine (:553, :689, :735): row L first, then rows L-1 .. 1
 void fbx_host_bwd_score(const float *xmx, int L, float *totscale, float *sc, int *status)
 {

@@ -226,6 +226,7 @@ int launch_fbx_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const Db
                    float *d_bck_xmx, float *d_totscale, int32_t *d_own);
 // host libm restatement of the two scores from the specials (fwdback.c:434,:463 / :553,:689,:735): totscale and score exactly as the
 // reference accumulates them; used whenever exact-order specials reach the host
+void fbx_host_fwd_score_compact(const float *blk, int L, float pmove, float *totscale, float *sc, int *status);
 void fbx_host_fwd_score(const float *xmx, int L, float pmove, float *totscale, float *sc, int *status);
 void fbx_host_bwd_score(const float *xmx, int L, float *totscale, float *sc, int *status);
 // decode.cu: the region trigger of p7_domaindef_ByPosteriorHeuristics (max_i mocc[i] >= rt1) and the gather of selected specials
@@ -235,6 +236,8 @@ int launch_region_trigger(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, c
 int launch_gather_xmx(p7gpu_ctx *ctx, int lane, const float *d_fx, const float *d_bx, const int64_t *d_src, const int64_t *d_dst,
                       const int32_t *d_nfloats, int64_t n, float *d_ofx, float *d_obx);
 // decode.cu: p7_DomainDecoding (btot, etot, mocc per row + Forward's SCALE column and xC(L)) for selected targets, 4*(L+1)+2 floats each
+int launch_gather_scale(p7gpu_ctx *ctx, int lane, const DbView &db, const int64_t *d_idx, int64_t n, const float *d_fx,
+                        const int64_t *d_xoff, float *d_out);
 int launch_domain_decoding(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                            const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int64_t *d_doff, float *d_dec);
 int launch_bias(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,

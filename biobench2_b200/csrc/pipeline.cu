@@ -548,13 +548,17 @@ static int pipeline_after_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p
     P7G_CUDA(cudaMemcpyAsync(fsc.data(), d_sc.p, 4 * n, cudaMemcpyDeviceToHost, st));
     P7G_CUDA(cudaMemcpyAsync(ftot.data(), d_tot.p, 4 * n, cudaMemcpyDeviceToHost, st));
     const bool allpass = F3 >= 1.0;                                  // --max: no decision between the two parsers, so no host round trip either
-    if (!allpass) P7G_CUDA(cudaStreamSynchronize(st));
+    if (!allpass) { P7G_CUDA(cudaStreamSynchronize(st)); tr.mark("  slice: forward kernel"); }
     if (exact && F3 < 1.0) {                                     // the F3 test needs the exact score: host libm on the specials
-      if (!exact_fx.resize(ext)) { set_error("pipeline: out of host memory for %zu floats of specials", ext); return P7GPU_EMEM; }
-      P7G_CHECK(d2h_large(ctx, exact_fx.data(), d_fx.p, 4 * ext));
+      DevBuf d_cs;                                               // SCALE column + xC(L): a sixth of the specials
+      P7G_CHECK(d_cs.alloc(4 * (ext / 6), st));
+      P7G_CHECK(launch_gather_scale(ctx, 0, dbv, d_idx.as<int64_t>(), (int64_t) n, d_fx.as<float>(), d_xoff.as<int64_t>(), d_cs.as<float>()));
+      if (!exact_fx.resize(ext / 6)) { set_error("pipeline: out of host memory for %zu floats of scale factors", ext / 6); return P7GPU_EMEM; }
+      P7G_CHECK(d2h_large(ctx, exact_fx.data(), d_cs.p, 4 * (ext / 6)));
+      P7G_CUDA(cudaStreamSynchronize(st));
       const LenConst *hl = prof->h_len.data();
       parallel_for(n, [&](size_t a, size_t b) {
-        for (size_t k = a; k < b; k++) { int stt; fbx_host_fwd_score(exact_fx.data() + xoff[k], cand[lo + k].L, hl[cand[lo + k].L].pmove, &ftot[k], &fsc[k], &stt); }
+        for (size_t k = a; k < b; k++) { int stt; fbx_host_fwd_score_compact(exact_fx.data() + xoff[k] / 6, cand[lo + k].L, hl[cand[lo + k].L].pmove, &ftot[k], &fsc[k], &stt); }
       });
     }
     tr.mark("  slice: forward done");

@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
   const int lane = threadIdx.x & 31;
   const int P = p.P, rowWords = p.rowWords;
   const uint32_t rowBytes = 4u * (uint32_t) rowWords;
-  const uint32_t tab_base = (uint32_t) __cvta_generic_to_shared(s_tab);
   const int thresh = 127 - p.s.bias_b;          // u >= thresh  <=>  xE >= 255 - bias
 
   for (;;) {
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
         }
         // byte address of this lane's first slot in table row 0 for this chunk; row x adds x*rowBytes (one IMAD),
         // the in-chunk row r and the slot q are immediate offsets of the LDS
-        const uint32_t cbase = tab_base + 4u * (uint32_t) c;
+        const uint32_t *s_lane = s_tab + c;
         uint32_t pend = 0u; bool have_pend = false;
 #pragma unroll
         for (int r = 0; r < DIAG_CHUNK; r++) {
@@ -158,9 +157,10 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
           uint32_t g[Q];
           if (SMEM && (MODE == SSV_SMEM || x < 20u || x == (uint32_t) PADRES)) {
             const uint32_t xr = (MODE == SSV_COMPACT) ? min(x, 20u) : x;
-            const uint32_t a = xr * rowBytes + cbase;
+            // one multiply-add per row for the address; the in-chunk row and the slot are immediate offsets of the LDS
+            const uint32_t *rowp = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_lane) + xr * rowBytes);
 #pragma unroll
-            for (int q = 0; q < Q; q++) asm("ld.shared.u32 %0, [%1];" : "=r"(g[q]) : "r"(a + 4u * (uint32_t) (r + q * ssv_slot_stride(Q))));
+            for (int q = 0; q < Q; q++) g[q] = rowp[r + q * ssv_slot_stride(Q)];
           } else {
             const uint32_t *rowp = p.tab + x * rowWords + c + r;
 #pragma unroll

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include <unistd.h>
 #include <time.h>
 
@@ -65,6 +66,8 @@ static ESL_OPTIONS options[] = {
   { "--hostdecode", eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "p7_DomainDecoding on the host from returned specials",        13 },
   { "--p7db",       eslARG_OUTFILE, NULL,    NULL,         NULL,     NULL,   NULL, NULL,             "keep the packed digital database in file <f> for later runs", 13 },
   { "--teardown",   eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "free every resource before exit (leak checkers)",             13 },
+  { "--nopin",      eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "never page-lock the database (default: from the 2nd query on)", 13 },
+  { "--pinfirst",   eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, "--nopin",        "page-lock the database before the first query",               13 },
   { "--times",      eslARG_NONE,    FALSE,   NULL,         NULL,     NULL,   NULL, NULL,             "report wall time of each phase on stderr",                    13 },
   {  0, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
 };
@@ -150,38 +153,55 @@ open_out(ESL_GETOPTS *go, char *opt, const char *what)
   return fp;
 }
 
-/* <seqdb> is either a packed database written earlier (--p7db) or FASTA text, digitised now with all host threads */
-static p7gpu_dbfile *
-open_database(ESL_GETOPTS *go, char *seqfile, double *ret_seconds)
+/* <seqdb> is either a packed database written earlier (--p7db) or FASTA text, digitised now with all host threads.  None of
+ * this touches the device, so it runs on its own thread while the main thread waits for the CUDA driver to initialise
+ * (0.5-1 s); failures are kept and reported by the main thread at the point where hmmsearch opens its sequence file. */
+typedef struct {
+  ESL_GETOPTS  *go;
+  char         *seqfile;
+  p7gpu_dbfile *db;
+  double        seconds, done_at;
+  char          fail[1024];        /* "" = ok */
+} DB_PREP;
+
+static void *
+prepare_database(void *arg)
 {
-  p7gpu_dbfile *db = NULL;
+  DB_PREP *pr = (DB_PREP *) arg;
+  ESL_GETOPTS *go = pr->go;
   char magic[8] = { 0 }, tmp[4096];
-  FILE *fp = fopen(seqfile, "rb");
+  FILE *fp = fopen(pr->seqfile, "rb");
   ESL_STOPWATCH *w = esl_stopwatch_Create();
   int keep = esl_opt_IsOn(go, "--p7db");
-  if (!fp) p7_Fail("Failed to open sequence file %s for reading\n", seqfile);
-  if (fread(magic, 1, 8, fp) == 0) { fclose(fp); p7_Fail("Sequence file %s is empty or misformatted\n", seqfile); }
+  pr->db = NULL;  pr->fail[0] = '\0';
+  if (!fp) { snprintf(pr->fail, sizeof(pr->fail), "Failed to open sequence file %s for reading\n", pr->seqfile); goto DONE; }
+  if (fread(magic, 1, 8, fp) == 0) { fclose(fp); snprintf(pr->fail, sizeof(pr->fail), "Sequence file %s is empty or misformatted\n", pr->seqfile); goto DONE; }
   fclose(fp);
   esl_stopwatch_Start(w);
   if (memcmp(magic, "P7GPUDB1", 8) == 0) {
-    if (p7gpu_dbfile_open(seqfile, &db) != P7GPU_OK) p7_Fail("%s\n", p7gpu_last_error());
+    if (p7gpu_dbfile_open(pr->seqfile, &pr->db) != P7GPU_OK) { snprintf(pr->fail, sizeof(pr->fail), "%s\n", p7gpu_last_error()); goto DONE; }
   } else {
     int64_t nseq = 0, nres = 0;
     const char *dir = getenv("TMPDIR");
-    if (esl_opt_IsOn(go, "--tformat") && strcasecmp(esl_opt_GetString(go, "--tformat"), "fasta") != 0)
-      p7_Fail("%s is not a sequence database file format this engine reads (fasta)\n", esl_opt_GetString(go, "--tformat"));
+    if (esl_opt_IsOn(go, "--tformat") && strcasecmp(esl_opt_GetString(go, "--tformat"), "fasta") != 0) {
+      snprintf(pr->fail, sizeof(pr->fail), "%s is not a sequence database file format this engine reads (fasta)\n", esl_opt_GetString(go, "--tformat"));
+      goto DONE;
+    }
     if (keep) snprintf(tmp, sizeof(tmp), "%s", esl_opt_GetString(go, "--p7db"));
     else      snprintf(tmp, sizeof(tmp), "%s/hmmsearch_b200.%ld.p7db", dir ? dir : "/tmp", (long) getpid());
-    if (p7gpu_dbfile_from_fasta(seqfile, tmp, 0, 16, &nseq, &nres) != P7GPU_OK)
-      p7_Fail("Parse failed (sequence file %s):\n%s\n", seqfile, p7gpu_last_error());          /* hmmsearch.c:523-524 */
-    if (p7gpu_dbfile_open(tmp, &db) != P7GPU_OK) p7_Fail("%s\n", p7gpu_last_error());
+    if (p7gpu_dbfile_from_fasta(pr->seqfile, tmp, 0, 16, &nseq, &nres) != P7GPU_OK) {                /* hmmsearch.c:523-524 */
+      snprintf(pr->fail, sizeof(pr->fail), "Parse failed (sequence file %s):\n%s\n", pr->seqfile, p7gpu_last_error());
+      goto DONE;
+    }
+    if (p7gpu_dbfile_open(tmp, &pr->db) != P7GPU_OK) { snprintf(pr->fail, sizeof(pr->fail), "%s\n", p7gpu_last_error()); goto DONE; }
     if (!keep) unlink(tmp);                                                                     /* the mapping keeps it alive */
   }
-  if (p7gpu_dbfile_pin(db) != P7GPU_OK) p7_Fail("%s\n", p7gpu_last_error());
   esl_stopwatch_Stop(w);
-  *ret_seconds = w->elapsed;
+  pr->seconds = w->elapsed;
+ DONE:
+  pr->done_at = since_start();
   esl_stopwatch_Destroy(w);
-  return db;
+  return NULL;
 }
 
 int
@@ -199,7 +219,8 @@ main(int argc, char **argv)
   ESL_STOPWATCH *w     = esl_stopwatch_Create();
   P7_B200_SEARCH cfg;
   char           errbuf[eslERRBUFSIZE];
-  double         t_db = 0.0;
+  DB_PREP        prep;
+  pthread_t      prep_tid;
   int            textw, nquery = 0, hstatus, status, k, ncpus = 0, times;
 
   since_start();
@@ -244,6 +265,8 @@ main(int argc, char **argv)
     for (k = 0; k < cfg.ngpus && n < 240; k++) n += snprintf(vis + n, sizeof(vis) - n, k ? ",%d" : "%d", k);
     setenv("CUDA_VISIBLE_DEVICES", vis, 0);
   }
+  prep.go = go;  prep.seqfile = seqfile;  prep.db = NULL;  prep.seconds = 0.0;  prep.fail[0] = '\0';
+  if (pthread_create(&prep_tid, NULL, prepare_database, &prep) != 0) p7_Fail("Failed to start the database thread\n");
   if (cfg.ngpus > p7_b200_DeviceCount()) p7_Fail("--gpus %d, but %d CUDA device(s) visible\n%s\n", cfg.ngpus, p7_b200_DeviceCount(), p7_b200_ErrorText());
   ESL_ALLOC(engs, sizeof(*engs) * cfg.ngpus);
   esl_stopwatch_Start(w);
@@ -257,9 +280,13 @@ main(int argc, char **argv)
     if (abc->type != eslAMINO) p7_Fail("The B200 engine searches protein databases; %s is not an amino acid profile\n", hmmfile);
     echo_options(ofp, go, hmmfile, seqfile);
     bg = p7_bg_Create(abc);
-    db = open_database(go, seqfile, &t_db);                  /* once, not once per query (cf. hmmsearch.c:480-487) */
-    if (times) fprintf(stderr, "# database ready: %.3f s (%lld targets, %lld residues)\n", t_db, (long long) p7gpu_dbfile_nseq(db), (long long) p7gpu_dbfile_nres(db));
-  }
+    if (times) fprintf(stderr, "# first profile read: %.3f s since start\n", since_start());
+    pthread_join(prep_tid, NULL);                            /* once, not once per query (cf. hmmsearch.c:480-487) */
+    if (prep.fail[0]) p7_Fail("%s", prep.fail);
+    db = prep.db;
+    if (times) fprintf(stderr, "# database ready: digitised in %.3f s on its own thread, done %.3f s after start (%lld targets, %lld residues); %.3f s since start\n",
+                       prep.seconds, prep.done_at, (long long) p7gpu_dbfile_nseq(db), (long long) p7gpu_dbfile_nres(db), since_start());
+  } else pthread_join(prep_tid, NULL);
 
   while (hstatus == eslOK) {
     P7_PROFILE  *gm  = p7_profile_Create (hmm->M, abc);
@@ -268,6 +295,14 @@ main(int argc, char **argv)
     P7_TOPHITS  *th  = p7_tophits_Create();
 
     nquery++;
+    /* The first query streams the database from the file mapping; page-locking it (and building the 5-bit transfer form)
+     * costs more than one pass saves, so that is done when a second query shows it will be read again. */
+    if (nquery == (esl_opt_GetBoolean(go, "--pinfirst") ? 1 : 2) && !esl_opt_GetBoolean(go, "--nopin")) {
+      esl_stopwatch_Start(w);
+      if (p7gpu_dbfile_pin(db) != P7GPU_OK) p7_Fail("%s\n", p7gpu_last_error());
+      esl_stopwatch_Stop(w);
+      if (times) fprintf(stderr, "# database page-locked for the remaining queries: %.3f s\n", w->elapsed);
+    }
     esl_stopwatch_Start(w);
     fprintf(ofp, "Query:       %s  [M=%d]\n", hmm->name, hmm->M);
     if (hmm->acc)  fprintf(ofp, "Accession:   %s\n", hmm->acc);
