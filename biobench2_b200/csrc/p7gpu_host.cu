@@ -653,19 +653,31 @@ int p7gpu_seqdb_upload(p7gpu_ctx *ctx, const uint8_t *residues, int64_t nbytes, 
   db->ctx = ctx; db->nseq = nseq; db->nbytes = nbytes; db->nres = nres; db->max_length = Lmax; db->owns = true;
   const size_t padded = ((size_t) nbytes + 15) / 16 * 16 + 32;
   uint8_t *d_res = nullptr; int64_t *d_off = nullptr; int32_t *d_len = nullptr;
-  P7G_CUDA(cudaMalloc(&d_res, padded));
+  // A handful of targets (the one-target drop-in calls, the reference's calibration loops through them: evalues.c:264,337,442)
+  // lives in the stream-ordered pool and is searched in database order: no cudaMalloc/cudaFree round trips, no sort.
+  const bool small = nseq <= 4096 && nbytes <= ((int64_t) 8 << 20);
+  db->pooled = small;
+  if (small) {
+    P7G_CUDA(cudaMallocAsync((void **) &d_res, padded, ctx->stream));
+    P7G_CUDA(cudaMallocAsync((void **) &d_off, sizeof(int64_t) * std::max<int64_t>(nseq, 1), ctx->stream));
+    P7G_CUDA(cudaMallocAsync((void **) &d_len, sizeof(int32_t) * std::max<int64_t>(nseq, 1), ctx->stream));
+  } else {
+    P7G_CUDA(cudaMalloc(&d_res, padded));
+    P7G_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * std::max<int64_t>(nseq, 1)));
+    P7G_CUDA(cudaMalloc(&d_len, sizeof(int32_t) * std::max<int64_t>(nseq, 1)));
+  }
   P7G_CUDA(cudaMemsetAsync(d_res, 0xff, padded, ctx->stream));
   if (nbytes) P7G_CUDA(cudaMemcpyAsync(d_res, residues, (size_t) nbytes, cudaMemcpyHostToDevice, ctx->stream));
-  P7G_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * std::max<int64_t>(nseq, 1)));
-  P7G_CUDA(cudaMalloc(&d_len, sizeof(int32_t) * std::max<int64_t>(nseq, 1)));
   if (nseq) {
     P7G_CUDA(cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * nseq, cudaMemcpyHostToDevice, ctx->stream));
     P7G_CUDA(cudaMemcpyAsync(d_len, lengths, sizeof(int32_t) * nseq, cudaMemcpyHostToDevice, ctx->stream));
   }
   db->d_res = d_res; db->d_off = d_off; db->d_len = d_len;
   P7G_CUDA(cudaStreamSynchronize(ctx->stream));
-  int st = build_order(ctx, db);
-  if (st != P7GPU_OK) { p7gpu_seqdb_destroy(db); return st; }
+  if (!small) {
+    int st = build_order(ctx, db);
+    if (st != P7GPU_OK) { p7gpu_seqdb_destroy(db); return st; }
+  }
   *ret_db = db;
   return P7GPU_OK;
 }
