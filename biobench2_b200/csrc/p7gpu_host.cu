@@ -442,6 +442,7 @@ int p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value)
   if (!strcmp(name, "fbx_groups"))     { ctx->fbx_groups = value; return P7GPU_OK; }
   if (!strcmp(name, "bias_window_log2")) { ctx->bias_window = value > 0 ? ldexpf(1.0f, -value) : 0.f; return P7GPU_OK; }
   if (!strcmp(name, "fbx_warps"))      { ctx->fbx_warps = value; return P7GPU_OK; }
+  if (!strcmp(name, "ssv_tmem"))       { ctx->ssv_tmem = value; return P7GPU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return P7GPU_EINVAL;
 }
@@ -511,6 +512,22 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
         ts[(size_t) x * g.rowWords + c] = (uint32_t) (uint16_t) gs[(size_t) x * g.P + lo] | ((uint32_t) (uint16_t) gs[(size_t) x * g.P + hi] << 16);
         tm[(size_t) x * g.rowWords + c] = (uint32_t) (uint16_t) gm[(size_t) x * g.P + lo] | ((uint32_t) (uint16_t) gm[(size_t) x * g.P + hi] << 16);
       }
+    // column-stationary layout for the Tensor Memory kernel: lane l, register q, half h <-> node k = 1 + h*32*Q + l*Q + q
+    const int Qt = (M + 63) / 64;
+    if (Qt <= 8) {
+      const int NX = Qt <= 1 ? 1 : Qt <= 2 ? 2 : Qt <= 4 ? 4 : 8;
+      std::vector<uint32_t> tt((size_t) NTABROWS * NX * 32);
+      auto gain = [&](int x, int col) { return (x < Kp && col < M) ? gs[(size_t) x * g.P + col] : (int16_t) SSV_PADGAIN; };   // col = k-1
+      for (int x = 0; x < NTABROWS; x++)
+        for (int q = 0; q < NX; q++)
+          for (int l = 0; l < 32; l++) {
+            const int16_t lo = q < Qt ? gain(x, l * Qt + q) : (int16_t) SSV_PADGAIN, hi = q < Qt ? gain(x, 32 * Qt + l * Qt + q) : (int16_t) SSV_PADGAIN;
+            tt[((size_t) x * NX + q) * 32 + l] = (uint32_t) (uint16_t) lo | ((uint32_t) (uint16_t) hi << 16);
+          }
+      P7G_CUDA(cudaMalloc(&prof->d_ssv_tm, tt.size() * 4));
+      P7G_CUDA(cudaMemcpy(prof->d_ssv_tm, tt.data(), tt.size() * 4, cudaMemcpyHostToDevice));
+      prof->ssv_tm_Q = Qt;
+    }
     P7G_CUDA(cudaMalloc(&prof->d_ssv_tab, ts.size() * 4));
     P7G_CUDA(cudaMalloc(&prof->d_msv_tab, tm.size() * 4));
     P7G_CUDA(cudaMemcpy(prof->d_ssv_tab, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice));
@@ -586,7 +603,7 @@ void p7gpu_profile_destroy(p7gpu_profile *prof)
   if (!prof) return;
   cudaSetDevice(prof->ctx->device);
   cudaStreamSynchronize(prof->ctx->stream);
-  cudaFree(prof->d_ssv_tab); cudaFree(prof->d_msv_tab);
+  cudaFree(prof->d_ssv_tab); cudaFree(prof->d_msv_tab); cudaFree(prof->d_ssv_tm);
   cudaFree(prof->d_rw); cudaFree(prof->d_tw); cudaFree(prof->d_rf); cudaFree(prof->d_tf);
   cudaFree(prof->d_rf_mw); cudaFree(prof->d_tf_mw);
   cudaFree(prof->d_tfx); cudaFree(prof->d_rfx); cudaFree(prof->d_tddx); cudaFree(prof->d_tmdx);

@@ -204,6 +204,210 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// ssv_tm_kernel: the same filter with the gain table in Tensor Memory (M <= 512).
+//
+// ssv_kernel above is bound by shared-memory bandwidth (Q LDS.32 per DP row per warp against 128 B/clk per SM; the integer
+// pipe idles ~16 % of the time).  TMEM is read at 64 B/clk per SM sub-partition (probes/tmem_probe.cu: 237 B/clk per SM), by a
+// single instruction per row: tcgen05.ld.32x32b.xN hands every lane N consecutive columns of its own TMEM lane, and the column
+// offset (residue * N) is a run-time operand.  A lane can only read its own TMEM lane, so the slots cannot follow their
+// diagonals as they do above (that needs a different table column every row); the layout is column-stationary instead:
+// lane l, register q, half h holds node k = 1 + h*32*Q + l*Q + q, a row moves every value one node up — a register rename
+// inside the lane plus ONE warp rotation for the lane boundary (lane 0 takes node 0 = floor into its low half and lane 31's
+// low half, node 32*Q, into its high half: one multiply-add, as in vit.cu).  Per row: 1 TMEM load, 1 SHFL, Q packed add-max,
+// Q/2 three-input max.  Arithmetic and every decision are those of ssv_kernel (same gains, same early exit, same epilogue).
+// TMEM: 30 table rows x N columns, N = 1/2/4/8 >= Q, in each of the four 32-lane quarters (warp w reads quarter w % 4).
+struct SsvTmParams {
+  const uint32_t *tab;          // [NTABROWS][NX][32]
+  const uint8_t *res; const int64_t *off; const int32_t *len; const int32_t *order; const int64_t *idx;
+  long long first;
+  long long n;
+  const LenConst *lc;
+  MsvScalars s;
+  float *sc; int32_t *status;
+  long long *nores_list; unsigned int *nores_count;
+  int32_t *pass_list; unsigned int *pass_count;
+  unsigned long long *work_counter;
+};
+
+// one residue, zero-extended by the load itself (the compiler masks a uint8_t again after widening it)
+__device__ __forceinline__ uint32_t ldg_res1(const uint8_t *ptr)
+{
+  uint32_t x;
+  asm("ld.global.nc.u8 %0, [%1];" : "=r"(x) : "l"(ptr));
+  return x;
+}
+
+template <int NX> struct Tmem;
+template <> struct Tmem<1> {
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&v)[1]) { asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(a), "r"(v[0])); }
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[1]) { asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(a)); }
+};
+template <> struct Tmem<2> {
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&v)[2]) { asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" :: "r"(a), "r"(v[0]), "r"(v[1])); }
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[2]) { asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(a)); }
+};
+template <> struct Tmem<4> {
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&v)[4]) { asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])); }
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[4]) { asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a)); }
+};
+template <> struct Tmem<8> {
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])); }
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(a)); }
+};
+__host__ __device__ constexpr int ssv_tm_nx(int Q)      { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8; }
+__host__ __device__ constexpr int ssv_tm_cols(int NX)   { return NX == 8 ? 256 : NX == 4 ? 128 : NX == 2 ? 64 : 32; }      // power of two >= 30*NX
+__host__ __device__ constexpr int ssv_tm_threads(int NX) { return NX == 8 ? 512 : 256; }
+__host__ __device__ constexpr int ssv_tm_ctas(int NX)   { return NX == 8 ? 2 : 4; }                                       // per SM: TMEM columns and registers allow this many
+
+template <int Q, int NX, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) ssv_tm_kernel(const SsvTmParams p)
+{
+  constexpr int NCOLS = ssv_tm_cols(NX);
+  __shared__ uint32_t s_slot;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "l"((uint64_t) __cvta_generic_to_shared(&s_slot)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tbase = s_slot;
+  const uint32_t mine = tbase + ((uint32_t) ((warp & 3) * 32) << 16);
+  if (warp < 4) {                                                          // one warp per quarter writes the table
+    for (int x = 0; x < NTABROWS; x++) {
+      uint32_t t[NX];
+#pragma unroll
+      for (int q = 0; q < NX; q++) t[q] = __ldg(p.tab + ((size_t) x * NX + q) * 32 + lane);
+      Tmem<NX>::st(mine + x * NX, t);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+
+  const int prevl = (lane + 31) & 31;
+  uint32_t rmul = lane == 0 ? 0x10000u : 1u;
+  asm("" : "+r"(rmul));                                                    // keep the rotation's fix-up a multiply (FMA pipe)
+  const int thresh = 127 - p.s.bias_b;          // u >= thresh  <=>  xE >= 255 - bias
+
+  for (;;) {
+    unsigned long long j = 0;
+    if (lane == 0) j = atomicAdd(p.work_counter, 1ULL);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= (unsigned long long) p.n) break;
+    const long long s   = p.idx ? p.idx[j] : (p.order ? (long long) p.order[j] : p.first + (long long) j);
+    const long long out = p.idx ? (long long) j : s;
+    const int       L   = p.len[s];
+    const long long o   = p.off[s];
+    const LenConst  lc  = p.lc[L];
+    const int       tjb = lc.tjb_b;
+
+    int status; float sc = 0.0f; int xJ = 0;
+    if (tjb + p.s.tbm_b + p.s.tec_b + p.s.bias_b >= 127) {      // ssvfilter.c:884
+      status = P7GPU_ENORESULT;
+    } else {
+      uint32_t v[Q];
+#pragma unroll
+      for (int q = 0; q < Q; q++) v[q] = 0u;
+      uint32_t xE = 0u;
+      // Residues arrive as byte loads (one broadcast LDG.U8 per row on the otherwise idle load pipe) instead of 16-byte vectors
+      // taken apart with PRMT: the integer pipe is what binds this kernel, and the rows then need no alignment or patching.
+      const uint8_t *seq = p.res + o;
+      auto row = [&](const uint32_t (&g)[NX]) {
+        const uint32_t carry = __shfl_sync(0xffffffffu, v[Q - 1], prevl) * rmul;
+        // v >= 0 always, so max(v+g, g, 0) == max(v+g, 0): the .RELU form needs no zero operand register
+#pragma unroll
+        for (int q = Q - 1; q >= 1; q--) v[q] = __viaddmax_s16x2_relu(v[q - 1], g[q], g[q]);
+        v[0] = __viaddmax_s16x2_relu(carry, g[0], g[0]);
+      };
+      int i = 0, since_check = 0;
+      bool over = false;
+      for (; i + DIAG_CHUNK <= L; i += DIAG_CHUNK) {
+        uint32_t xs[DIAG_CHUNK];
+#pragma unroll
+        for (int r = 0; r < DIAG_CHUNK; r++) xs[r] = ldg_res1(seq + i + r);
+        // the table row of DP row r+1 is fetched while row r is computed; tcgen05.wait::ld only orders the loads already issued
+        uint32_t g[NX], gn[NX];
+        Tmem<NX>::ld(mine + xs[0] * NX, g);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t pend = 0u; bool have_pend = false;
+#pragma unroll
+        for (int r = 0; r < DIAG_CHUNK; r++) {
+          if (r + 1 < DIAG_CHUNK) Tmem<NX>::ld(mine + xs[r + 1] * NX, gn);
+          row(g);
+          // running maximum, two cells per VIMNMX3; an odd leftover waits for the next row (flag folds at compile time)
+#pragma unroll
+          for (int q = 0; q < Q; q++) {
+            if (have_pend) { xE = __vimax3_s16x2(xE, pend, v[q]); have_pend = false; }
+            else           { pend = v[q]; have_pend = true; }
+          }
+          if (r + 1 < DIAG_CHUNK) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < NX; q++) g[q] = gn[q];
+          }
+        }
+        if (have_pend) { xE = __vmaxs2(xE, pend); have_pend = false; }
+        // once any cell reaches 255-bias the outcome is fixed (overflow); leaving early also keeps
+        // every int16 lane far from wrap-around (<= thresh + 64*bias < 2^15).
+        if (++since_check == 4) {
+          since_check = 0;
+          if (__any_sync(0xffffffffu, hmax16(xE) >= thresh)) { over = true; break; }
+        }
+      }
+      if (!over)
+        for (; i < L; i++) {                                     // the last L mod 16 rows, one at a time
+          uint32_t g[NX];
+          Tmem<NX>::ld(mine + ldg_res1(seq + i) * NX, g);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          row(g);
+#pragma unroll
+          for (int q = 0; q < Q; q++) xE = __vmaxs2(xE, v[q]);
+        }
+      const int maxu = __reduce_max_sync(0xffffffffu, hmax16(xE));
+      status = ssv_epilogue(maxu, tjb, p.s, &sc, &xJ);
+    }
+    if (lane == 0) {
+      p.sc[out] = sc;
+      p.status[out] = status;
+      if (p.pass_list && L > 0 && (status == P7GPU_ERANGE || (status == P7GPU_OK && xJ >= (int) lc.msv_xj_min)))
+        p.pass_list[atomicAdd(p.pass_count, 1u)] = (int32_t) s;
+      if (status == P7GPU_ENORESULT && p.nores_list) {
+        unsigned int t = atomicAdd(p.nores_count, 1u);
+        p.nores_list[2 * (long long) t]     = s;
+        p.nores_list[2 * (long long) t + 1] = out;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "n"(NCOLS));
+}
+
+template <int Q>
+static int launch_ssv_tm_q(p7gpu_ctx *ctx, cudaStream_t stream, const SsvTmParams &p)
+{
+  constexpr int NX = ssv_tm_nx(Q), THREADS = ssv_tm_threads(NX), CTAS = ssv_tm_ctas(NX);
+  auto kern = ssv_tm_kernel<Q, NX, THREADS, CTAS>;
+  // the grid never asks an SM for more CTAs than its 512 TMEM columns serve: a CTA beyond that would sit in tcgen05.alloc
+  // until another one of this persistent grid has drained the queue
+  long long blocks = (long long) ctx->sm_count * CTAS;
+  long long need_blocks = (p.n + (THREADS / 32) - 1) / (THREADS / 32);
+  if (need_blocks < blocks) blocks = need_blocks;
+  if (blocks < 1) blocks = 1;
+  { LaunchTimer t(ctx, P7GPU_KERNEL_SSV, stream); kern<<<(unsigned) blocks, THREADS, 0, stream>>>(p); }
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return P7GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 struct MsvjParams {
   const uint32_t *tab; int rowWords, P, M;
   const uint8_t *res; const int64_t *off; const int32_t *len;
@@ -331,6 +535,20 @@ int launch_ssv(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   p.work_counter = (unsigned long long *) (ln.counters + CTR_SSV_WORK);
   // work counter (2 words) + the lane's eslENORESULT count (CTR_NORES_COUNT = CTR_SSV_WORK + 2)
   P7G_CUDA(cudaMemsetAsync(ln.counters + CTR_SSV_WORK, 0, 4 * sizeof(unsigned int), ln.stream));
+  // 193 <= M <= 512 (or option ssv_tmem = 2: any M <= 512): gain table in Tensor Memory.  Below Q = 4 the per-row fixed cost
+  // (rotation, address hand-over to the uniform register file) outweighs the saved LDS: measured 8.0 against 9.2 TCUPS at M = 100
+  if (prof->d_ssv_tm && ctx->ssv_tmem && (prof->ssv_tm_Q >= 4 || ctx->ssv_tmem >= 2)) {
+    SsvTmParams t;
+    t.tab = prof->d_ssv_tm; t.res = p.res; t.off = p.off; t.len = p.len; t.order = p.order; t.idx = p.idx; t.first = p.first; t.n = p.n;
+    t.lc = p.lc; t.s = p.s; t.sc = p.sc; t.status = p.status; t.nores_list = p.nores_list; t.nores_count = p.nores_count;
+    t.pass_list = p.pass_list; t.pass_count = p.pass_count; t.work_counter = p.work_counter;
+    switch (prof->ssv_tm_Q) {
+#define X(QV) case QV: return launch_ssv_tm_q<QV>(ctx, ln.stream, t);
+      X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#undef X
+    default: break;
+    }
+  }
   switch (prof->geom.Q) {
 #define X(QV) case QV: return launch_ssv_pick<QV>(ctx, ln.stream, p);
     P7G_ODD_Q_CASES(X)
