@@ -15,7 +15,7 @@ reference's own Mc/s unit (p7_pipeline.c:1791-1792).
 `e2e`    : the same pass through the host-buffer C-ABI call p7gpu_pipeline_run_host5(stop_after_msv=1): the packed
            database is copied host->device (streamed under the kernels) and the survivor records device->host inside the
            timed region.
-`roofline`          : the dominant kernel (ssv_kernel) against its BINDING roof, the packed-int16 issue rate measured live
+`roofline`          : the dominant kernel (ssv_tm_kernel / ssv_kernel) against its BINDING roof, the packed-int16 issue rate measured live
                       (HBM, which the schema asks about and which is not binding, sits in roofline.hbm).
 `roofline_kernels`  : the same fraction for every other kernel of the path (Viterbi, Forward, Backward, bias, the
                       exact-order Forward/Backward): SURVEY.md 8(d) ops per cell x measured cells/s / the live-measured peak.
@@ -568,14 +568,17 @@ def main():
         if tj.get("profile") == args.profile and tj.get("nseq") == args.nseq and tj.get("mean_len") == args.mean_len:
             traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     pk_instr = int_peak / 2.0
-    roofline = {"bound": "int16x2-issue", "kernel": "ssv_kernel",
+    tm_path = 193 <= M <= 512            # ssv_msv.cu: launch_ssv takes the Tensor Memory table there (option ssv_tmem, default on)
+    roofline = {"bound": "int16x2-issue", "kernel": "ssv_tm_kernel (gain table in Tensor Memory, one tcgen05.ld per row)" if tm_path else "ssv_kernel (gain table in shared memory)",
                 "achieved": ssv_gcups * OPS_PER_CELL["ssv"], "peak": pk_instr, "unit": "G packed int16x2 instr/s (VIADDMNMX.S16x2)",
                 "frac": ssv_gcups * OPS_PER_CELL["ssv"] / pk_instr if pk_instr else None,
                 "instr_per_cell": OPS_PER_CELL["ssv"], "int16_ops_per_cell": 2, "kernel_gcups": ssv_gcups, "avg_launch_ms": ssv_avg_ms,
                 "peak_source": "measured live in this run (p7gpu_measure_peaks: dependent-free VIADDMNMX.S16x2 chains; %.1f T int16 ops/s)" % (int_peak / 1e3),
                 "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/ssv_traffic.json)",
                 "smem": {"bound": "smem-lds", "achieved": ssv_gcups * 2.0, "peak": lds_peak, "unit": "GB/s (2 table bytes per cell, LDS.32)",
-                         "frac": ssv_gcups * 2.0 / lds_peak if lds_peak else None},
+                         "frac": ssv_gcups * 2.0 / lds_peak if lds_peak else None,
+                         "note": ("not this kernel's roof: the table is read from Tensor Memory (64 B/clk per SM sub-partition, 3 % busy); shown as the "
+                                  "roof the shared-memory kernel sat on") if tm_path else "binding together with the integer pipe"},
                 "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                         "algorithmic_bytes": alg_bytes, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                         "note": "the path moves 1 byte per M cells: HBM is not the binding roof (0.6 % of peak)"}}

@@ -3,6 +3,7 @@
 // entry launches a CUDA kernel or fails with P7GPU_ESYS.
 #include "p7gpu_internal.h"
 #include <thread>
+#include <unordered_set>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <iterator>
@@ -358,6 +359,17 @@ extern "C" {
 
 const char *p7gpu_last_error(void) { return g_err; }
 
+}  // extern "C"
+// Live contexts: a pipeline result hands its big host buffers back to its context's cache when it is destroyed, and a result
+// may outlive its context (garbage collection order in a host language): p7gpu_result_destroy asks here first.
+namespace p7g {
+static std::mutex g_ctx_mu;
+static std::unordered_set<const p7gpu_ctx *> g_live_ctx;
+std::mutex &ctx_registry_mutex() { return g_ctx_mu; }
+bool ctx_registered_locked(const p7gpu_ctx *ctx) { return g_live_ctx.count(ctx) != 0; }
+}
+extern "C" {
+
 int p7gpu_device_count(void)
 {
   int n = 0;
@@ -398,6 +410,7 @@ int p7gpu_ctx_create(int device, p7gpu_ctx **ret_ctx)
   }
   ctx->stream = ctx->lanes[0].stream;
   ctx->own_stream = true;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); g_live_ctx.insert(ctx); }
   *ret_ctx = ctx;
   return P7GPU_OK;
 }
@@ -405,6 +418,7 @@ int p7gpu_ctx_create(int device, p7gpu_ctx **ret_ctx)
 void p7gpu_ctx_destroy(p7gpu_ctx *ctx)
 {
   if (!ctx) return;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); g_live_ctx.erase(ctx); }
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (int l = 0; l < NLANES; l++) {

@@ -40,6 +40,8 @@ struct DiagGeom {
   int M, Q, P, rowWords;              // rowWords = P + DIAG_CHUNK + Q (odd Q) or P + DIAG_CHUNK + 32*(Q-1) + 1 (even Q): wrap-free reads inside one chunk
   size_t tableBytes() const { return (size_t) NTABROWS * rowWords * 4; }
 };
+std::mutex &ctx_registry_mutex();                 // live contexts (p7gpu_host.cu): results hand buffers back only to a live one
+bool ctx_registered_locked(const p7gpu_ctx *ctx);
 DiagGeom diag_geom(int M);
 int dp_cells_per_lane(int M);
 bool mw_geometry(int M, int *C, int *W);   // Forward/Backward CTA-per-target geometry for long models; false = use one warp

@@ -836,6 +836,20 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
   for (int l = 1; l <= 2; l++) S_CUDA(cudaStreamWaitEvent(ctx->lanes[l].stream, ev_main, 0));
   tr.mark("stream: setup");
 
+  // the per-length constant table is sized once, before anything is queued: growing it in the middle of the stream would
+  // synchronise the device under the copy/compute overlap (the per-chunk call below is then a no-op)
+  {
+    std::vector<int32_t> part(64, 0);
+    parallel_for((size_t) nseq, [&](size_t a, size_t b) {
+      int32_t m = 0;
+      for (size_t k = a; k < b; k++) m = std::max(m, lengths[k]);
+      int32_t &slot = part[(a * 64) / (size_t) std::max<int64_t>(nseq, 1) % 64];
+      slot = std::max(slot, m);
+    });
+    int32_t Lall = 0;
+    for (int32_t m : part) Lall = std::max(Lall, m);
+    S_CHECK(ensure_len_table(prof, Lall, F1));
+  }
   int64_t nres = 0; int32_t Lmax = 0;
   for (size_t c = 0; c < plan.size(); c++) {
     const int64_t s_lo = plan[c].s_lo, s_hi = plan[c].s_hi, cn = s_hi - s_lo;
@@ -1208,7 +1222,8 @@ const p7gpu_msv_survivor *p7gpu_result_msvpass(const p7gpu_pipeline_result *res)
 void p7gpu_result_destroy(p7gpu_pipeline_result *res)
 {
   if (!res) return;
-  if (res->ctx) {
+  std::lock_guard<std::mutex> lk(ctx_registry_mutex());            // the context may be gone already (host-language GC order)
+  if (res->ctx && ctx_registered_locked(res->ctx)) {
     HostScratch &hs = host_scratch(res->ctx);
     if (res->msv_pass.capacity() > hs.msv_cache.capacity()) hs.msv_cache.swap(res->msv_pass);
     if (res->fwd_xmx.cap > hs.xmx_cache[0].cap) hs.xmx_cache[0].swap(res->fwd_xmx);

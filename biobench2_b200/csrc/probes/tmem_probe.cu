@@ -168,6 +168,31 @@ __global__ void __launch_bounds__(THREADS) row_kernel(int rows, uint32_t *out)
   if (TMEM) { __syncthreads(); if ((threadIdx.x >> 5) == 0) tmem_free(s_slot); }
 }
 
+
+// (3) issue rates of the packed integer instructions the filters are made of, dependent-free chains, 16 warps per SM
+template <int KIND>
+__global__ void __launch_bounds__(256) dpx_rate_kernel(uint32_t g, int iters, uint32_t *out)
+{
+  uint32_t v[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) v[q] = threadIdx.x * 3 + q;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      if (KIND == 0) v[q] = __viaddmax_s16x2(v[q], g, 0u);
+      if (KIND == 1) v[q] = __vimax3_s16x2(v[q], g, v[(q + 1) & 7]);
+      if (KIND == 2) v[q] = __vmaxs2(v[q], v[(q + 3) & 7] ^ g);
+      if (KIND == 3) v[q] = __viaddmax_s16x2_relu(v[q], g, g);
+      if (KIND == 4) v[q] = __byte_perm(v[q], g, 0x2103);
+      if (KIND == 5) v[q] = (uint32_t) max((int) v[q] + (int) g, (int) v[(q + 1) & 7]);
+    }
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) acc ^= v[q];
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
 int main()
 {
   int dev = 0; CK(cudaSetDevice(dev));
@@ -202,6 +227,18 @@ int main()
   rw[4] = {"tmem_r1_512", timeit([&] { row_kernel<true, 1, 512><<<sms * 2, 512>>>(rows, d_out); }), 32};
   rw[5] = {"tmem_r2_512", timeit([&] { row_kernel<true, 2, 512><<<sms * 2, 512>>>(rows, d_out); }), 32};
   CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+  double dpx[6];
+  {
+    const int it2 = 8192;
+    dpx[0] = timeit([&] { dpx_rate_kernel<0><<<sms * 2, 256>>>(0xfffdfffeu, it2, d_out); });
+    dpx[1] = timeit([&] { dpx_rate_kernel<1><<<sms * 2, 256>>>(0xfffdfffeu, it2, d_out); });
+    dpx[2] = timeit([&] { dpx_rate_kernel<2><<<sms * 2, 256>>>(0xfffdfffeu, it2, d_out); });
+    dpx[3] = timeit([&] { dpx_rate_kernel<3><<<sms * 2, 256>>>(0xfffdfffeu, it2, d_out); });
+    dpx[4] = timeit([&] { dpx_rate_kernel<4><<<sms * 2, 256>>>(0xfffdfffeu, it2, d_out); });
+    dpx[5] = timeit([&] { dpx_rate_kernel<5><<<sms * 2, 256>>>(0xfffdfffeu, it2, d_out); });
+    CK(cudaGetLastError());
+    for (int k = 0; k < 6; k++) dpx[k] = (double) sms * 16 * it2 * 8 / (dpx[k] * 1e-3);      // warp instructions per second
+  }
   int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
   printf("{\"device\": \"%s\", \"sms\": %d, \"readback_mismatches\": %d, "
          "\"ldtm_x8_gbs\": {\"depth1\": %.1f, \"depth2\": %.1f, \"depth4\": %.1f}, \"ldtm_bytes_per_clk_per_sm_at_%d_mhz\": %.1f, "
@@ -213,6 +250,8 @@ int main()
     printf(", \"%s\": {\"warps_per_sm\": %d, \"tcups_equiv\": %.2f, \"clk_per_row_per_subpartition\": %.1f}", rw[k].name, rw[k].warps,
            wrows * 64 * Q / (rw[k].ms * 1e-3) / 1e12, (double) clk * 1e3 * rw[k].ms * 1e-3 / (wrows / (sms * 4.0)));
   }
-  printf("}}\n");
+  printf("}, \"warp_instr_per_clk_per_subpartition\": {\"viaddmnmx_s16x2\": %.3f, \"vimnmx3_s16x2\": %.3f, \"vimnmx_s16x2\": %.3f, \"viaddmnmx_s16x2_relu\": %.3f, \"prmt\": %.3f, \"viaddmnmx_s32\": %.3f}}\n",
+         dpx[0] / ((double) clk * 1e3 * sms * 4), dpx[1] / ((double) clk * 1e3 * sms * 4), dpx[2] / ((double) clk * 1e3 * sms * 4),
+         dpx[3] / ((double) clk * 1e3 * sms * 4), dpx[4] / ((double) clk * 1e3 * sms * 4), dpx[5] / ((double) clk * 1e3 * sms * 4));
   return 0;
 }

@@ -306,3 +306,21 @@ def test_bias_filter_score_is_exact_by_construction(gpu_ctx, name):
     finally:
         gpu_ctx.set_option("bias_window_log2", 0)
         db.close(); prof.close()
+
+
+@pytest.mark.gpu
+def test_result_may_outlive_its_context():
+    """A pipeline result hands its large host buffers back to its context's cache when it is destroyed; a host language may
+    collect the context first.  p7gpu_result_destroy must notice (live-context registry) instead of touching freed memory."""
+    g = golden_set("globins4")
+    c = engine.Context(0)
+    prof = engine.Profile(c, g.oprofile)
+    db = engine.SeqDB.upload(c, g.db)
+    r1 = engine.pipeline_run(c, prof, db, stop_after_msv=True)                     # keeps an MSV pass list drawn from the cache
+    r2 = engine.pipeline_run(c, prof, db, want_specials=True, region_trigger=False)  # keeps specials drawn from the cache
+    n1, n2 = len(r1.msv_pass), len(r2.survivors)
+    assert n1 > 0 and n2 > 0
+    db.close(); prof.close(); c.close()
+    r1.close(); r2.close()                                                         # after the context: must not crash
+    c2 = engine.Context(0)                                                         # and the library is still usable
+    c2.close()
