@@ -10,6 +10,7 @@
 // no shuffles, no permutes.  The per-profile gain table is staged once per CTA in shared memory as
 // (lo,hi) int16 pairs laid out so that every LDS.32 of a warp is bank-conflict free (lane stride Q odd).
 #include "p7gpu_internal.h"
+#include "tmem.cuh"
 #include <math_constants.h>
 
 namespace p7g {
@@ -237,27 +238,6 @@ __device__ __forceinline__ uint32_t ldg_res1(const uint8_t *ptr)
   return x;
 }
 
-template <int NX> struct Tmem;
-template <> struct Tmem<1> {
-  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&v)[1]) { asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(a), "r"(v[0])); }
-  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[1]) { asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(a)); }
-};
-template <> struct Tmem<2> {
-  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&v)[2]) { asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" :: "r"(a), "r"(v[0]), "r"(v[1])); }
-  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[2]) { asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(a)); }
-};
-template <> struct Tmem<4> {
-  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&v)[4]) { asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])); }
-  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[4]) { asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a)); }
-};
-template <> struct Tmem<8> {
-  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])); }
-  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(a)); }
-};
 __host__ __device__ constexpr int ssv_tm_nx(int Q)      { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8; }
 __host__ __device__ constexpr int ssv_tm_cols(int NX)   { return NX == 8 ? 256 : NX == 4 ? 128 : NX == 2 ? 64 : 32; }      // power of two >= 30*NX
 __host__ __device__ constexpr int ssv_tm_threads(int NX) { return NX == 8 ? 512 : 256; }

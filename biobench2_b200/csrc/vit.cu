@@ -7,6 +7,7 @@
 // The lazy-F test of vitfilter.c:198-199 is evaluated as written; when it fires, the D->D fixed point
 // of :203-226 is obtained with a max-plus prefix scan over the warp (exact: see DESIGN.md).
 #include "dp_common.cuh"
+#include "tmem.cuh"
 #include <math_constants.h>
 
 namespace p7g {
@@ -184,22 +185,44 @@ __device__ __forceinline__ int warp_max16x2(uint32_t v, uint32_t k16)
 // (r * 65536 + floor moves lane 31's low half up; r * 1 + 0 elsewhere), the specials live in the window domain (no
 // int16 re-truncation: max(xC, .) and max(xJ, .) never leave [-32768, 32766], xB >= xN + tNB), and the >> 16 after the warp
 // reductions is a multiply-high.
-constexpr int VITP_BIG_THREADS = 256;   // transitions in shared memory (C2 > 14): one CTA per SM, so more warps share the tables
+constexpr int VITP_BIG_THREADS = 256;   // C2 > 14: few CTAs per SM (the emission table fills shared memory), so more warps share it
+// C2 > 14 (M > 896): the 8 transition vectors of a lane do not fit its registers.  They are row-invariant and lane-private, which
+// is what Tensor Memory holds best: TMEM[lane][8*j + t], one tcgen05.ld.32x32b.x8 per register-row instead of 8 LDS.32 (the
+// shared-memory form was LDS-bound at 86 %, profiles/r2n_vitp_M2000_full.txt); emissions and the lazy-F copy of tDD stay in
+// shared memory.
+__host__ __device__ constexpr int vitp_tm_cols(int C2) { return 8 * C2 <= 128 ? 128 : (8 * C2 <= 256 ? 256 : 512); }
 
 template <int C2, bool TREG>
 __global__ void __launch_bounds__(TREG ? DP_THREADS : VITP_BIG_THREADS, TREG ? (C2 <= 7 ? 4 : 2) : 1) vitp_kernel(const VitpParams p)
 {
   extern __shared__ __align__(16) uint32_t s_vp[];
+  __shared__ uint32_t s_tmslot;
+  constexpr int TCOLS = vitp_tm_cols(C2);
+  uint32_t tbase = 0, mine = 0;
   {
     const int nrw = NTABROWS * C2 * 32;
     for (int i = threadIdx.x; i < nrw; i += blockDim.x) s_vp[i] = __ldg(p.rwp + i);
-    if (!TREG) { const int ntw = 8 * C2 * 32; for (int i = threadIdx.x; i < ntw; i += blockDim.x) s_vp[nrw + i] = __ldg(p.twp + i); }
+    if (!TREG) { for (int i = threadIdx.x; i < C2 * 32; i += blockDim.x) s_vp[nrw + i] = __ldg(p.twp + 7 * C2 * 32 + i); }   // tDD for lazy F
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
+  if (!TREG) {
+    tbase = tmem_alloc_cta<TCOLS>(&s_tmslot);
+    mine = tbase + ((uint32_t) (((threadIdx.x >> 5) & 3) * 32) << 16);
+    if ((threadIdx.x >> 5) < 4) {                                      // one warp per quarter writes the lane-private table
+      for (int j = 0; j < C2; j++) {
+        uint32_t t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = __ldg(p.twp + (k * C2 + j) * 32 + lane);
+        Tmem<8>::st(mine + 8 * j, t);
+      }
+      tmem_wait_st();
+    }
+    tmem_publish();
+  }
   const int prevl = (lane + 31) & 31;
   const uint32_t *s_rw = s_vp + lane;
-  const uint32_t *s_tw = s_vp + NTABROWS * C2 * 32 + lane;
+  const uint32_t *s_dd = s_vp + NTABROWS * C2 * 32 + lane;
   uint32_t rBM[TREG ? C2 : 1], rMM[TREG ? C2 : 1], rIM[TREG ? C2 : 1], rDM[TREG ? C2 : 1], rMD[TREG ? C2 : 1],
            rMI[TREG ? C2 : 1], rII[TREG ? C2 : 1], rDD[TREG ? C2 : 1];
   if (TREG) {
@@ -211,7 +234,8 @@ __global__ void __launch_bounds__(TREG ? DP_THREADS : VITP_BIG_THREADS, TREG ? (
       rII[j] = __ldg(p.twp + (6 * C2 + j) * 32 + lane); rDD[j] = __ldg(p.twp + (7 * C2 + j) * 32 + lane);
     }
   }
-#define TP_(name, t, j) (TREG ? r##name[j] : s_tw[((t) * C2 + (j)) * 32])
+#define TP_(name, t, j) (TREG ? r##name[j] : tr[t])            /* inside the j loop of a row: tr = this register-row's 8 transitions */
+#define TDD_(j) (TREG ? rDD[j] : s_dd[(j) * 32])
   uint32_t wd[5];
 #pragma unroll
   for (int d = 0; d < 5; d++) wd[d] = __ldg(p.scanw + d * 32 + lane);
@@ -225,7 +249,7 @@ __global__ void __launch_bounds__(TREG ? DP_THREADS : VITP_BIG_THREADS, TREG ? (
 #pragma unroll
     for (int j = 0; j < C2; j++) {
       s_ptp[j * 32 + lane] = ((uint32_t) max(lo, -p.w.T) & 0xffffu) | ((uint32_t) max(hi, -p.w.T) << 16);
-      const uint32_t t = TREG ? rDD[j] : s_tw[(7 * C2 + j) * 32];
+      const uint32_t t = TDD_(j);
       lo += (int) (short) (t & 0xffffu); hi += (int) t >> 16;
     }
   }
@@ -265,8 +289,11 @@ __global__ void __launch_bounds__(TREG ? DP_THREADS : VITP_BIG_THREADS, TREG ? (
       uint32_t pi = piN;
       uint32_t pd = ROT_(dp[C2 - 1]);
       uint32_t xEl = FLv, Dml = FLv, dcv = FLv, pendE = 0u, pendD = 0u;
+      uint32_t tr[8], tn[8];
+      if (!TREG) { Tmem<8>::ld(mine, tr); tmem_wait_ld(); }
 #pragma unroll
       for (int j = 0; j < C2; j++) {
+        if (!TREG && j + 1 < C2) Tmem<8>::ld(mine + 8 * (j + 1), tn);  // next register-row's transitions, under this one's arithmetic
         uint32_t sv = __viaddmax_s16x2(xBv, TP_(BM, 0, j), FLv);       // vitfilter.c:146-150
         sv = __viaddmax_s16x2(pm, TP_(MM, 1, j), sv);
         sv = __viaddmax_s16x2(pi, TP_(IM, 2, j), sv);
@@ -281,6 +308,11 @@ __global__ void __launch_bounds__(TREG ? DP_THREADS : VITP_BIG_THREADS, TREG ? (
         if (j == 0) { xEl = sv; Dml = dcv; }
         else if (j & 1) { pendE = sv; pendD = dcv; }
         else { xEl = __vimax3_s16x2(xEl, pendE, sv); Dml = __vimax3_s16x2(Dml, pendD, dcv); }
+        if (!TREG && j + 1 < C2) {
+          tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 8; k++) tr[k] = tn[k];
+        }
       }
       if (C2 > 1 && !(C2 & 1)) { xEl = __vmaxs2(xEl, pendE); Dml = __vmaxs2(Dml, pendD); }
       dp[0] = ROT_(dcv);
@@ -296,8 +328,8 @@ __global__ void __launch_bounds__(TREG ? DP_THREADS : VITP_BIG_THREADS, TREG ? (
         // row-invariant lane-span sums wd[] (both halves at once); (3) the low half's total enters the high half (wh);
         // (4) the carry entering each lane reaches cell j after paying the lane's tDD[0..j-1] (s_pt).
 #pragma unroll
-        for (int j = 1; j < C2; j++) dp[j] = __viaddmax_s16x2(dp[j - 1], TP_(DD, 7, j - 1), dp[j]);
-        uint32_t X = __viaddmax_s16x2(dp[C2 - 1], TP_(DD, 7, C2 - 1), FLv);
+        for (int j = 1; j < C2; j++) dp[j] = __viaddmax_s16x2(dp[j - 1], TDD_(j - 1), dp[j]);
+        uint32_t X = __viaddmax_s16x2(dp[C2 - 1], TDD_(C2 - 1), FLv);
 #pragma unroll
         for (int d = 0; d < 5; d++) X = __viaddmax_s16x2(__shfl_up_sync(0xffffffffu, X, 1 << d), wd[d], X);
         const uint32_t u = __shfl_sync(0xffffffffu, X, 31) * 0x10000u + (FLv & 0xffffu);   // (floor, X_lo(31))
@@ -344,7 +376,9 @@ __global__ void __launch_bounds__(TREG ? DP_THREADS : VITP_BIG_THREADS, TREG ? (
     }
   }
 #undef TP_
+#undef TDD_
 #undef ROT_
+  if (!TREG) tmem_free_cta<TCOLS>(tbase);
 }
 
 template <int C2>
@@ -352,7 +386,7 @@ static int launch_vitp_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitpParams &
 {
   constexpr bool TREG = (C2 <= 14);
   constexpr int NT = TREG ? DP_THREADS : VITP_BIG_THREADS;
-  const size_t smem = (size_t) (NTABROWS + (TREG ? 0 : 8)) * C2 * 32 * sizeof(uint32_t);
+  const size_t smem = (size_t) (NTABROWS + (TREG ? 0 : 1)) * C2 * 32 * sizeof(uint32_t);
   *launched = false;
   if (smem + 1024 > (size_t) ctx->smem_optin) return P7GPU_OK;
   auto kern = vitp_kernel<C2, TREG>;
@@ -362,6 +396,7 @@ static int launch_vitp_c(p7gpu_ctx *ctx, cudaStream_t stream, const VitpParams &
     P7G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     P7G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
     if (occ < 1) { set_error("vitp_kernel<%d>: zero occupancy", C2); return P7GPU_ESYS; }
+    if (!TREG) occ = std::min(occ, 512 / vitp_tm_cols(C2));           // Tensor Memory columns per SM
   }
   long long blocks = (long long) ctx->sm_count * occ;
   long long need = (p.c.n + (NT / 32) - 1) / (NT / 32);
