@@ -223,15 +223,26 @@ static LenConst len_const(const p7gpu_profile *prof, int L, double F1)
   return c;
 }
 
+static void sync_all_lanes(p7gpu_ctx *ctx)
+{
+  for (int l = 0; l < NLANES; l++) if (ctx->lanes[l].stream || l == 0) cudaStreamSynchronize(ctx->lanes[l].stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+}
+
 int ensure_len_table(const p7gpu_profile *prof, int Lmax, double F1)
 {
   std::lock_guard<std::mutex> lock(prof->len_mutex);
   if (F1 < 0) F1 = prof->len_F1 >= 0 ? prof->len_F1 : DEFAULT_F1;
   if (F1 != prof->len_F1) {                                             // thresholds changed: rebuild everything
-    if (prof->d_len) { P7G_CUDA(cudaDeviceSynchronize()); cudaFree(prof->d_len); prof->d_len = nullptr; }
-    prof->len_cap = 0; prof->h_len.clear(); prof->len_F1 = F1;
+    if (prof->d_len) { sync_all_lanes(prof->ctx); cudaFreeAsync(prof->d_len, prof->ctx->stream); prof->d_len = nullptr; }
+    prof->len_cap = 0; prof->h_len.clear(); prof->len_F1 = F1; prof->len_sparse = false;
   }
-  if (Lmax < prof->len_cap) return P7GPU_OK;
+  if (Lmax < prof->len_cap && !prof->len_sparse) return P7GPU_OK;
+  if (prof->len_sparse) {                                               // prepared for a fixed set of lengths (p7gpu_profile_prepare_lengths)
+    if (Lmax < prof->len_cap) return P7GPU_OK;                          // the caller vouched for the lengths; only the bound is checked here
+    prof->len_cap = 0; prof->h_len.clear(); prof->len_sparse = false;   // longer targets than prepared for: build the dense table
+    if (prof->d_len) { sync_all_lanes(prof->ctx); cudaFreeAsync(prof->d_len, prof->ctx->stream); prof->d_len = nullptr; }
+  }
   int cap = std::max(Lmax + 1, std::max(4096, prof->len_cap * 2));
   prof->h_len.resize(cap);
   {                                                                     // ~0.7 us per length (bisection over exp()): all host threads
@@ -244,14 +255,38 @@ int ensure_len_table(const p7gpu_profile *prof, int Lmax, double F1)
     for (auto &x : th) x.join();
   }
   LenConst *d_new = nullptr;
-  P7G_CUDA(cudaMalloc(&d_new, sizeof(LenConst) * cap));
+  P7G_CUDA(cudaMallocAsync((void **) &d_new, sizeof(LenConst) * cap, prof->ctx->stream));
   P7G_CUDA(cudaMemcpyAsync(d_new, prof->h_len.data(), sizeof(LenConst) * cap, cudaMemcpyHostToDevice, prof->ctx->stream));
   P7G_CUDA(cudaStreamSynchronize(prof->ctx->stream));
-  if (prof->d_len) { P7G_CUDA(cudaDeviceSynchronize()); cudaFree(prof->d_len); }
+  if (prof->d_len) { sync_all_lanes(prof->ctx); cudaFreeAsync(prof->d_len, prof->ctx->stream); }
   prof->d_len = d_new;
   prof->len_cap = cap;
   return P7GPU_OK;
 }
+
+}  // namespace p7g
+// hmmscan: the targets (queries) are few and fixed while the profiles stream past, so each profile's per-length constants are
+// needed for the distinct query lengths only — 0.7 us each instead of >= 4096 of them per profile.
+extern "C" int p7gpu_profile_prepare_lengths(p7gpu_profile *prof, const int32_t *lengths, int64_t n, double F1)
+{
+  using namespace p7g;
+  if (!prof || n < 0 || (n > 0 && !lengths)) return P7GPU_EINVAL;
+  std::lock_guard<std::mutex> lock(prof->len_mutex);
+  if (F1 < 0) F1 = DEFAULT_F1;
+  int32_t Lmax = 0;
+  for (int64_t k = 0; k < n; k++) { if (lengths[k] < 0) return P7GPU_EINVAL; Lmax = std::max(Lmax, lengths[k]); }
+  P7G_CUDA(cudaSetDevice(prof->ctx->device));
+  if (prof->d_len) { sync_all_lanes(prof->ctx); cudaFreeAsync(prof->d_len, prof->ctx->stream); prof->d_len = nullptr; }
+  const int cap = Lmax + 1;
+  prof->h_len.assign((size_t) cap, LenConst{});
+  for (int64_t k = 0; k < n; k++) prof->h_len[(size_t) lengths[k]] = len_const(prof, lengths[k], F1);
+  P7G_CUDA(cudaMallocAsync((void **) &prof->d_len, sizeof(LenConst) * (size_t) cap, prof->ctx->stream));
+  P7G_CUDA(cudaMemcpyAsync(prof->d_len, prof->h_len.data(), sizeof(LenConst) * (size_t) cap, cudaMemcpyHostToDevice, prof->ctx->stream));
+  P7G_CUDA(cudaStreamSynchronize(prof->ctx->stream));
+  prof->len_cap = cap; prof->len_F1 = F1; prof->len_sparse = true;
+  return P7GPU_OK;
+}
+namespace p7g {
 
 int dp_cells_per_lane(int M)
 {
@@ -279,6 +314,17 @@ bool mw_geometry(int M, int *C, int *W)
     return true;
   }
   return false;
+}
+
+// profile tables live in the context's stream-ordered pool: an upload is cudaMallocAsync + cudaMemcpyAsync on the main stream
+// (the host vectors are pageable, so the copy has left them when the call returns), a destroy is cudaFreeAsync — hmmscan
+// uploads and drops one profile per model, and cudaMalloc/cudaFree round trips were most of its time per model
+template <class T>
+static int pool_upload(p7gpu_ctx *ctx, T **dptr, const void *src, size_t bytes)
+{
+  P7G_CUDA(cudaMallocAsync((void **) dptr, std::max<size_t>(bytes, 16), ctx->stream));
+  if (bytes) P7G_CUDA(cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return P7GPU_OK;
 }
 
 static int nq_of(int M, int w) { int q = (M - 1) / w + 1; return q < 2 ? 2 : q; }   // impl_sse.h:25-27
@@ -343,9 +389,10 @@ static int build_vit_packed(p7gpu_profile *prof, const p7gpu_oprofile_view *om, 
     long long wh = 0; for (int m = 0; m <= l; m++) wh += TL(1, m);
     scanw[(size_t) 5 * 32 + l] = 0u | (cl((int) std::max<long long>(wh, -T)) << 16);
   }
-  P7G_CUDA(cudaMalloc(&prof->d_rwp, rwp.size() * 4));     P7G_CUDA(cudaMemcpy(prof->d_rwp, rwp.data(), rwp.size() * 4, cudaMemcpyHostToDevice));
-  P7G_CUDA(cudaMalloc(&prof->d_twp, twp.size() * 4));     P7G_CUDA(cudaMemcpy(prof->d_twp, twp.data(), twp.size() * 4, cudaMemcpyHostToDevice));
-  P7G_CUDA(cudaMalloc(&prof->d_scanw, scanw.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_scanw, scanw.data(), scanw.size() * 4, cudaMemcpyHostToDevice));
+  p7gpu_ctx *ctx = prof->ctx;
+  P7G_CHECK(pool_upload(ctx, &prof->d_rwp, rwp.data(), rwp.size() * 4));
+  P7G_CHECK(pool_upload(ctx, &prof->d_twp, twp.data(), twp.size() * 4));
+  P7G_CHECK(pool_upload(ctx, &prof->d_scanw, scanw.data(), scanw.size() * 4));
   vp.enabled = 1;
   return P7GPU_OK;
 }
@@ -538,14 +585,11 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
             const int16_t lo = q < Qt ? gain(x, l * Qt + q) : (int16_t) SSV_PADGAIN, hi = q < Qt ? gain(x, 32 * Qt + l * Qt + q) : (int16_t) SSV_PADGAIN;
             tt[((size_t) x * NX + q) * 32 + l] = (uint32_t) (uint16_t) lo | ((uint32_t) (uint16_t) hi << 16);
           }
-      P7G_CUDA(cudaMalloc(&prof->d_ssv_tm, tt.size() * 4));
-      P7G_CUDA(cudaMemcpy(prof->d_ssv_tm, tt.data(), tt.size() * 4, cudaMemcpyHostToDevice));
+      P7G_CHECK(pool_upload(ctx, &prof->d_ssv_tm, tt.data(), tt.size() * 4));
       prof->ssv_tm_Q = Qt;
     }
-    P7G_CUDA(cudaMalloc(&prof->d_ssv_tab, ts.size() * 4));
-    P7G_CUDA(cudaMalloc(&prof->d_msv_tab, tm.size() * 4));
-    P7G_CUDA(cudaMemcpy(prof->d_ssv_tab, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice));
-    P7G_CUDA(cudaMemcpy(prof->d_msv_tab, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice));
+    P7G_CHECK(pool_upload(ctx, &prof->d_ssv_tab, ts.data(), ts.size() * 4));
+    P7G_CHECK(pool_upload(ctx, &prof->d_msv_tab, tm.data(), tm.size() * 4));
   }
 
   // ---- Viterbi / Forward tables, lane-transposed [row][j][lane], node k = lane*C + j + 1 ----------------
@@ -568,10 +612,10 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
       tw[((size_t) 7 * C + j) * 32 + lane] = om->twv[((size_t) 7 * Q8 + q8) * 8 + z8];
       tf[((size_t) 7 * C + j) * 32 + lane] = om->tfv[((size_t) 7 * Q4 + q4) * 4 + z4];
     }
-    P7G_CUDA(cudaMalloc(&prof->d_rw, rw.size() * 2)); P7G_CUDA(cudaMemcpy(prof->d_rw, rw.data(), rw.size() * 2, cudaMemcpyHostToDevice));
-    P7G_CUDA(cudaMalloc(&prof->d_tw, tw.size() * 2)); P7G_CUDA(cudaMemcpy(prof->d_tw, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
-    P7G_CUDA(cudaMalloc(&prof->d_rf, rf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rf, rf.data(), rf.size() * 4, cudaMemcpyHostToDevice));
-    P7G_CUDA(cudaMalloc(&prof->d_tf, tf.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
+    P7G_CHECK(pool_upload(ctx, &prof->d_rw, rw.data(), rw.size() * 2));
+    P7G_CHECK(pool_upload(ctx, &prof->d_tw, tw.data(), tw.size() * 2));
+    P7G_CHECK(pool_upload(ctx, &prof->d_rf, rf.data(), rf.size() * 4));
+    P7G_CHECK(pool_upload(ctx, &prof->d_tf, tf.data(), tf.size() * 4));
     {                                                                 // exact-order kernels (fbx.cu): striped values, wider loads
       const int Q = Q4, Qp = (Q4 + 3) / 4 * 4;
       std::vector<float> tfx((size_t) Q * 32, 0.0f), rfx((size_t) NTABROWS * 4 * Qp, 0.0f), tddx((size_t) 4 * Qp, 0.0f), tmdx((size_t) 4 * Qp, 0.0f);
@@ -582,10 +626,10 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
           tddx[(size_t) z * Qp + q] = tfx[((size_t) q * 4 + z) * 8 + 7]; tmdx[(size_t) z * Qp + q] = tfx[((size_t) q * 4 + z) * 8 + 4];
           for (int x = 0; x < Kp; x++) rfx[((size_t) x * 4 + z) * Qp + q] = om->rfv[((size_t) x * Q + q) * 4 + z];
         }
-      P7G_CUDA(cudaMalloc(&prof->d_tfx, tfx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tfx, tfx.data(), tfx.size() * 4, cudaMemcpyHostToDevice));
-      P7G_CUDA(cudaMalloc(&prof->d_rfx, rfx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rfx, rfx.data(), rfx.size() * 4, cudaMemcpyHostToDevice));
-      P7G_CUDA(cudaMalloc(&prof->d_tddx, tddx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tddx, tddx.data(), tddx.size() * 4, cudaMemcpyHostToDevice));
-      P7G_CUDA(cudaMalloc(&prof->d_tmdx, tmdx.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tmdx, tmdx.data(), tmdx.size() * 4, cudaMemcpyHostToDevice));
+      P7G_CHECK(pool_upload(ctx, &prof->d_tfx, tfx.data(), tfx.size() * 4));
+      P7G_CHECK(pool_upload(ctx, &prof->d_rfx, rfx.data(), rfx.size() * 4));
+      P7G_CHECK(pool_upload(ctx, &prof->d_tddx, tddx.data(), tddx.size() * 4));
+      P7G_CHECK(pool_upload(ctx, &prof->d_tmdx, tmdx.data(), tmdx.size() * 4));
       prof->fbxQ = Q; prof->fbxQp = Qp;
     }
     int mc = 0, mw = 0;
@@ -598,8 +642,8 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
         for (int t = 0; t < 7; t++)  tfm[((size_t) t * mc + j) * G + gl] = om->tfv[((size_t) 7 * q4 + t) * 4 + z4];
         tfm[((size_t) 7 * mc + j) * G + gl] = om->tfv[((size_t) 7 * Q4 + q4) * 4 + z4];
       }
-      P7G_CUDA(cudaMalloc(&prof->d_rf_mw, rfm.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_rf_mw, rfm.data(), rfm.size() * 4, cudaMemcpyHostToDevice));
-      P7G_CUDA(cudaMalloc(&prof->d_tf_mw, tfm.size() * 4)); P7G_CUDA(cudaMemcpy(prof->d_tf_mw, tfm.data(), tfm.size() * 4, cudaMemcpyHostToDevice));
+      P7G_CHECK(pool_upload(ctx, &prof->d_rf_mw, rfm.data(), rfm.size() * 4));
+      P7G_CHECK(pool_upload(ctx, &prof->d_tf_mw, tfm.data(), tfm.size() * 4));
       prof->mwC = mc; prof->mwW = mw;
     }
     prof->vit.xw_E_move = om->xw[0][0]; prof->vit.xw_E_loop = om->xw[0][1];
@@ -608,6 +652,7 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
     prof->scale_w = om->scale_w;
     prof->fwd.xf_E_move = om->xf[0][0]; prof->fwd.xf_E_loop = om->xf[0][1];
   }
+  P7G_CUDA(cudaStreamSynchronize(ctx->stream));      // the tables are complete before any stream of the context reads them
   *ret_prof = prof;
   return P7GPU_OK;
 }
@@ -615,14 +660,12 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
 void p7gpu_profile_destroy(p7gpu_profile *prof)
 {
   if (!prof) return;
-  cudaSetDevice(prof->ctx->device);
-  cudaStreamSynchronize(prof->ctx->stream);
-  cudaFree(prof->d_ssv_tab); cudaFree(prof->d_msv_tab); cudaFree(prof->d_ssv_tm);
-  cudaFree(prof->d_rw); cudaFree(prof->d_tw); cudaFree(prof->d_rf); cudaFree(prof->d_tf);
-  cudaFree(prof->d_rf_mw); cudaFree(prof->d_tf_mw);
-  cudaFree(prof->d_tfx); cudaFree(prof->d_rfx); cudaFree(prof->d_tddx); cudaFree(prof->d_tmdx);
-  cudaFree(prof->d_rwp); cudaFree(prof->d_twp); cudaFree(prof->d_scanw);
-  cudaFree(prof->d_len);
+  p7gpu_ctx *ctx = prof->ctx;
+  cudaSetDevice(ctx->device);
+  sync_all_lanes(ctx);                         // nothing that reads the tables is still running, on any of the context's streams
+  void *ptrs[] = {prof->d_ssv_tab, prof->d_msv_tab, prof->d_ssv_tm, prof->d_rw, prof->d_tw, prof->d_rf, prof->d_tf, prof->d_rf_mw, prof->d_tf_mw,
+                  prof->d_tfx, prof->d_rfx, prof->d_tddx, prof->d_tmdx, prof->d_rwp, prof->d_twp, prof->d_scanw, prof->d_len};
+  for (void *q : ptrs) if (q) cudaFreeAsync(q, ctx->stream);
   delete prof;
 }
 

@@ -163,6 +163,7 @@ struct p7gpu_profile {
   mutable std::mutex  len_mutex;
   mutable int         len_cap = 0;
   mutable double      len_F1 = -1.0;
+  mutable bool        len_sparse = false;       // built by p7gpu_profile_prepare_lengths: only the prepared lengths are valid
   mutable p7g::LenConst *d_len = nullptr;
   mutable std::vector<p7g::LenConst> h_len;
   float scale_b = 0, scale_w = 0;

@@ -19,7 +19,7 @@ EXPORTS = [
     "p7gpu_ctx_create", "p7gpu_ctx_destroy", "p7gpu_last_error", "p7gpu_device_count", "p7gpu_ctx_set_stream",
     "p7gpu_ctx_launch_count", "p7gpu_ctx_synchronize", "p7gpu_ctx_set_option", "p7gpu_ctx_last_vit_redo", "p7gpu_ctx_bias_recomputed",
     "p7gpu_ctx_set_timing", "p7gpu_ctx_reset_timing", "p7gpu_ctx_kernel_time", "p7gpu_measure_peaks",
-    "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M", "p7gpu_profile_set_biasfilter",
+    "p7gpu_profile_upload", "p7gpu_profile_destroy", "p7gpu_profile_M", "p7gpu_profile_set_biasfilter", "p7gpu_profile_prepare_lengths",
     "p7gpu_seqdb_upload", "p7gpu_seqdb_adopt_device", "p7gpu_seqdb_destroy", "p7gpu_seqdb_nseq", "p7gpu_seqdb_nres",
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
     "p7gpu_backward_batch", "p7gpu_region_trigger_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
@@ -115,6 +115,7 @@ def lib():
         L.p7gpu_backward_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
         L.p7gpu_msvfilter_device.argtypes = [vp, vp, vp, C.c_double, vp, vp, vp, vp]
         L.p7gpu_profile_set_biasfilter.argtypes = [vp, vp, vp, vp]
+        L.p7gpu_profile_prepare_lengths.argtypes = [vp, vp, C.c_int64, C.c_double]
         L.p7gpu_biasfilter_batch.argtypes = [vp, vp, vp, vp, i64, vp]
         L.p7gpu_region_trigger_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
         L.p7gpu_msvfilter_stream.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.c_double, vp, vp, vp, C.POINTER(i64), C.POINTER(vp)]
@@ -267,6 +268,11 @@ class Profile:
         t = np.ascontiguousarray(t, np.float32); pi = np.ascontiguousarray(pi, np.float32); eo = np.ascontiguousarray(eo, np.float32)
         assert t.size == 6 and pi.size == 3 and eo.size == 58
         _check(lib().p7gpu_profile_set_biasfilter(self.h, _p(t), _p(pi), _p(eo)))
+
+    def prepare_lengths(self, lengths, F1=0.02):
+        """Per-length constants for exactly these target lengths (scan mode: few fixed targets, many profiles)."""
+        a = np.ascontiguousarray(lengths, np.int32)
+        _check(lib().p7gpu_profile_prepare_lengths(self.h, _p(a), a.shape[0], float(F1)))
 
     def close(self):
         if self.h:

@@ -126,6 +126,11 @@ int         p7gpu_measure_peaks(p7gpu_ctx *ctx, double *int16x2_gops, double *fp
 int  p7gpu_profile_upload (p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_profile **ret_prof);
 void p7gpu_profile_destroy(p7gpu_profile *prof);
 int  p7gpu_profile_M      (const p7gpu_profile *prof);
+/* Optional, for scans of many profiles against few fixed targets (hmmscan: src/hmmscan.c:1180-1222 streams the models past each
+ * query): build the profile's per-length constants (what p7_oprofile_ReconfigLength / p7_bg_SetLength / the MSV P-value threshold
+ * derive from L, p7_oprofile.c:1085-1127, p7_pipeline.c:690-693) for exactly these target lengths and this F1 (1.0 for --max)
+ * instead of for every length up to the longest.  Later calls with a target of another length rebuild the full table. */
+int  p7gpu_profile_prepare_lengths(p7gpu_profile *prof, const int32_t *lengths, int64_t n, double F1);
 /* the bias-filter HMM as p7_bg_SetFilter() built it (p7_bg.c:430-453): bg->fhmm->t[2][3] (row-major), pi[3], eo[Kp][2].
  * t[0][0], t[0][1] are overwritten per target exactly like p7_bg_SetLength (p7_bg.c:193-196). */
 int  p7gpu_profile_set_biasfilter(p7gpu_profile *prof, const float *t6, const float *pi3, const float *eo);

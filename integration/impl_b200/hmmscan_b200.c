@@ -14,7 +14,7 @@
  *   p7_Pipeline in SCAN mode (replay, p7_b200_engine.c) into that query's own P7_TOPHITS / P7_PIPELINE.
  *
  * Output: per query, in file order, through the reference's own p7_tophits_* / p7_pli_Statistics — byte-identical to hmmscan
- * (tests/test_integration_hmmscan.py).  One GPU; --cpu is accepted for compatibility (the host part is one thread).
+ * (tests/test_integration_hmmscan.py).  One GPU; --cpu host threads finish the Forward survivors of each model (disjoint queries per thread).
  */
 #include "impl_b200.h"
 #include "esl_getopts.h"
@@ -22,7 +22,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include <unistd.h>
+#include "esl_threads.h"
 
 #define REPOPTS     "-E,-T,--cut_ga,--cut_nc,--cut_tc"
 #define DOMREPOPTS  "--domE,--domT,--cut_ga,--cut_nc,--cut_tc"
@@ -62,7 +64,7 @@ static ESL_OPTIONS options[] = {
   { "--domZ",       eslARG_REAL,    FALSE,  NULL,         "x>0",    NULL, NULL, NULL,             "set # of significant seqs, for domain E-value calculation",  12 },
   { "--seed",       eslARG_INT,     "42",   NULL,         "n>=0",   NULL, NULL, NULL,             "set RNG seed to <n> (if 0: one-time arbitrary seed)",        12 },
   { "--qformat",    eslARG_STRING,  NULL,   NULL,         NULL,     NULL, NULL, NULL,             "assert input <seqfile> is in format <s> (fasta only)",       12 },
-  { "--cpu",        eslARG_INT,     NULL,   "HMMER_NCPU", "n>=0",   NULL, NULL, NULL,             "accepted for compatibility (the host part is one thread)",   12 },
+  { "--cpu",        eslARG_INT,     NULL,   "HMMER_NCPU", "n>=0",   NULL, NULL, NULL,             "number of host threads finishing the Forward survivors",     12 },
   { "--fbfast",     eslARG_NONE,    FALSE,  NULL,         NULL,     NULL, NULL, NULL,             "Forward/Backward specials within 1e-4 instead of bit-exact", 13 },
   { "--times",      eslARG_NONE,    FALSE,  NULL,         NULL,     NULL, NULL, NULL,             "report wall time of each phase on stderr",                   13 },
   {  0, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
@@ -76,6 +78,61 @@ typedef struct {                 /* one per query sequence */
   P7_PIPELINE *pli;
   P7_TOPHITS  *th;
 } QUERY;
+
+/* Finishing the Forward survivors of one model (the reference's own p7_Pipeline, fed by replay) is host work that is
+ * independent between queries: worker t takes the survivors whose query index is t modulo the number of workers, so every
+ * query's pipeline and hit list are touched by one thread only and hits arrive in model order as in hmmscan.c:1222. */
+typedef struct {
+  int                     t, nt;
+  const p7gpu_survivor   *sv;
+  int64_t                 ns;
+  p7gpu_pipeline_result  *r;
+  QUERY                  *qs;
+  P7_OPROFILE            *om;       /* this worker's clone: p7_oprofile_ReconfigLength writes into it */
+  P7_BG                  *bg;       /* this worker's own: p7_bg_SetLength / SetFilter write into it */
+  uint64_t                nmodels;
+  int                     status;
+  char                    errbuf[eslERRBUFSIZE];
+} REPLAY_WORKER;
+
+static void *
+replay_worker(void *arg)
+{
+  REPLAY_WORKER *w = (REPLAY_WORKER *) arg;
+  int64_t k;
+  impl_Init();                                                   /* FTZ/DAZ in this thread (hmmscan.c:1167) */
+  w->status = eslOK;
+  for (k = 0; k < w->ns; k++) {
+    const p7gpu_survivor *sv = &w->sv[k];
+    QUERY *Q;  P7_PIPELINE *pli;  P7_B200_REPLAY rec;
+    uint64_t c0, c1, c2, c3;
+    int status;
+    if (sv->seqidx % w->nt != w->t || sv->region_flag == 0) continue;
+    Q = &w->qs[sv->seqidx];  pli = Q->pli;
+    c0 = pli->n_past_msv;  c1 = pli->n_past_bias;  c2 = pli->n_past_vit;  c3 = pli->n_past_fwd;
+    memset(&rec, 0, sizeof(rec));
+    rec.dsq = Q->sq->dsq;  rec.L = sv->L;
+    rec.msv_status = sv->msv_status;  rec.vit_status = sv->vit_status;
+    rec.usc = sv->usc;  rec.vfsc = sv->vfsc;  rec.fwdsc = sv->fwdsc;  rec.bcksc = sv->bcksc;
+    rec.fwd_xmx = (sv->xmx_offset >= 0) ? p7gpu_result_fwd_xmx(w->r) + sv->xmx_offset : NULL;
+    rec.bck_xmx = (sv->xmx_offset >= 0) ? p7gpu_result_bck_xmx(w->r) + sv->xmx_offset : NULL;
+    rec.dec     = (sv->dec_offset >= 0) ? p7gpu_result_decoding(w->r) + sv->dec_offset : NULL;
+    rec.fwd_totscale = sv->fwd_totscale;  rec.bck_totscale = sv->bck_totscale;  rec.bck_own_scales = sv->bck_own_scales;
+    if (pli->Z_setby == p7_ZSETBY_NTARGETS) pli->Z = (double) w->nmodels;    /* p7_pli_NewModel, p7_pipeline.c:498: a lower bound while hits are collected */
+    pli->hfp = NULL;                                             /* <om> is complete already: p7_Pipeline must not read the rest again */
+    p7_b200_ReplayArm(&rec);
+    p7_bg_SetLength(w->bg, Q->sq->n);                            /* hmmscan.c:1187-1188 */
+    p7_oprofile_ReconfigLength(w->om, Q->sq->n);
+    status = p7_Pipeline(pli, w->om, w->bg, Q->sq, Q->th);
+    p7_b200_ReplayArm(NULL);
+    if (status != eslOK && status != eslERANGE) { w->status = status; strncpy(w->errbuf, pli->errbuf, eslERRBUFSIZE - 1); w->errbuf[eslERRBUFSIZE - 1] = 0; return NULL; }
+    p7_pipeline_Reuse(pli);
+    pli->n_past_msv = c0;  pli->n_past_bias = c1;  pli->n_past_vit = c2;  pli->n_past_fwd = c3;   /* counted by the caller from the stage records */
+  }
+  return NULL;
+}
+
+static int cmp_int32(const void *a, const void *b) { const int32_t x = *(const int32_t *) a, y = *(const int32_t *) b; return (x > y) - (x < y); }
 
 int
 main(int argc, char **argv)
@@ -93,7 +150,11 @@ main(int argc, char **argv)
   QUERY         *qs  = NULL;
   ESL_STOPWATCH *w   = esl_stopwatch_Create();
   const uint8_t *residues; const int64_t *offsets; const int32_t *lengths;
-  int64_t        nq = 0, nres = 0, q, k;
+  int64_t        nq = 0, nres = 0, q, k, nqlens = 0;
+  REPLAY_WORKER  workers[64];
+  pthread_t      tids[64];
+  int            ncpus = 1;
+  int32_t       *qlens = NULL;
   uint64_t       nmodels = 0, nnodes = 0, nfull = 0;
   int            textw, times, fb_exact, status, hstatus;
   const char    *dir = getenv("TMPDIR");
@@ -112,6 +173,9 @@ main(int argc, char **argv)
   textw    = esl_opt_GetBoolean(go, "--notextw") ? 0 : esl_opt_GetInteger(go, "--textw");
   times    = esl_opt_GetBoolean(go, "--times");
   fb_exact = esl_opt_GetBoolean(go, "--fbfast") ? 0 : 1;
+  if (esl_opt_IsOn(go, "--cpu")) ncpus = esl_opt_GetInteger(go, "--cpu"); else esl_threads_CPUCount(&ncpus);
+  ncpus = ESL_MAX(1, ESL_MIN(ncpus, 64));
+  memset(workers, 0, sizeof(workers));
   if (esl_opt_IsOn(go, "--qformat") && strcasecmp(esl_opt_GetString(go, "--qformat"), "fasta") != 0) p7_Fail("%s is not a query format this engine reads (fasta)\n", esl_opt_GetString(go, "--qformat"));
 
   /* the pressed profile database (hmmscan.c:413: p7_HMMDBENV; binary .h3m/.h3f/.h3p/.h3i set written by hmmpress) */
@@ -141,6 +205,12 @@ main(int argc, char **argv)
   residues = p7gpu_dbfile_residues(qdb);  offsets = p7gpu_dbfile_offsets(qdb);  lengths = p7gpu_dbfile_lengths(qdb);
   if (p7gpu_seqdb_upload(p7_b200_Ctx(eng), residues, p7gpu_dbfile_nbytes(qdb), offsets, lengths, nq, &gdb) != P7GPU_OK) p7_Fail("%s\n", p7gpu_last_error());
 
+  /* the distinct query lengths: each model's per-length constants are built for these only */
+  ESL_ALLOC(qlens, sizeof(int32_t) * ESL_MAX(nq, 1));
+  for (q = 0; q < nq; q++) qlens[q] = lengths[q];
+  qsort(qlens, (size_t) nq, sizeof(int32_t), cmp_int32);
+  for (q = 0, nqlens = 0; q < nq; q++) if (q == 0 || qlens[q] != qlens[q - 1]) qlens[nqlens++] = qlens[q];
+
   esl_stopwatch_Start(w);
   /* stream the models past the resident queries */
   while ((hstatus = p7_oprofile_ReadMSV(hfp, &abc, &om)) == eslOK) {
@@ -168,6 +238,7 @@ main(int argc, char **argv)
     o.do_biasfilter = qs ? qs[0].pli->do_biasfilter : 1;  o.do_max = qs ? qs[0].pli->do_max : 0;
     o.stop_after_msv = 1;
     if (p7_b200_SetModelMSV(eng, om) != eslOK) p7_Fail("Failed to upload profile %s: %s\n", om->name, p7_b200_ErrorText());
+    if (p7_b200_PrepareLengths(eng, qlens, nqlens, o.do_max ? 1.0 : o.F1) != eslOK) p7_Fail("Failed to prepare profile %s: %s\n", om->name, p7_b200_ErrorText());
     if (p7gpu_pipeline_run(p7_b200_Ctx(eng), p7_b200_Profile(eng), gdb, &o, &r) != P7GPU_OK) p7_Fail("GPU pipeline failed: %s\n", p7gpu_last_error());
     npass = p7gpu_result_nmsvpass(r);
     p7gpu_result_destroy(r);  r = NULL;
@@ -178,6 +249,7 @@ main(int argc, char **argv)
     nfull++;
     if (o.do_biasfilter) p7_bg_SetFilter(bg, om->M, om->compo);  /* what p7_pli_NewModel does for the bias filter (p7_pipeline.c:500) */
     if (p7_b200_SetModel(eng, om, bg) != eslOK) p7_Fail("Failed to upload profile %s: %s\n", om->name, p7_b200_ErrorText());
+    if (p7_b200_PrepareLengths(eng, qlens, nqlens, o.do_max ? 1.0 : o.F1) != eslOK) p7_Fail("Failed to prepare profile %s: %s\n", om->name, p7_b200_ErrorText());
     o.stop_after_msv = 0;  o.want_specials = 1;  o.stage_records = 1;
     o.fb_exact = fb_exact;  o.region_trigger = (fb_exact || o.do_max) ? 1 : 0;  o.decode = o.region_trigger;
     if (p7gpu_pipeline_run(p7_b200_Ctx(eng), p7_b200_Profile(eng), gdb, &o, &r) != P7GPU_OK) p7_Fail("GPU pipeline failed: %s\n", p7gpu_last_error());
@@ -192,30 +264,24 @@ main(int argc, char **argv)
         if (mv[k].stage >= 3) pli->n_past_vit++;
         if (mv[k].stage >= 4) pli->n_past_fwd++;
       }
-      for (k = 0; k < ns; k++) {                                 /* Forward survivors: the reference's p7_Pipeline finishes them (replay) */
-        QUERY *Q = &qs[sv[k].seqidx];
-        P7_PIPELINE *pli = Q->pli;
-        P7_B200_REPLAY rec;
-        uint64_t c0 = pli->n_past_msv, c1 = pli->n_past_bias, c2 = pli->n_past_vit, c3 = pli->n_past_fwd;
-        if (sv[k].region_flag == 0) continue;
-        memset(&rec, 0, sizeof(rec));
-        rec.dsq = Q->sq->dsq;  rec.L = sv[k].L;
-        rec.msv_status = sv[k].msv_status;  rec.vit_status = sv[k].vit_status;
-        rec.usc = sv[k].usc;  rec.vfsc = sv[k].vfsc;  rec.fwdsc = sv[k].fwdsc;  rec.bcksc = sv[k].bcksc;
-        rec.fwd_xmx = (sv[k].xmx_offset >= 0) ? p7gpu_result_fwd_xmx(r) + sv[k].xmx_offset : NULL;
-        rec.bck_xmx = (sv[k].xmx_offset >= 0) ? p7gpu_result_bck_xmx(r) + sv[k].xmx_offset : NULL;
-        rec.dec     = (sv[k].dec_offset >= 0) ? p7gpu_result_decoding(r) + sv[k].dec_offset : NULL;
-        rec.fwd_totscale = sv[k].fwd_totscale;  rec.bck_totscale = sv[k].bck_totscale;  rec.bck_own_scales = sv[k].bck_own_scales;
-        if (pli->Z_setby == p7_ZSETBY_NTARGETS) pli->Z = (double) nmodels;       /* p7_pli_NewModel, p7_pipeline.c:498: a lower bound while hits are collected */
-        pli->hfp = NULL;                                         /* <om> is complete already: p7_Pipeline must not read the rest again */
-        p7_b200_ReplayArm(&rec);
-        p7_bg_SetLength(bg, Q->sq->n);                           /* hmmscan.c:1187-1188 */
-        p7_oprofile_ReconfigLength(om, Q->sq->n);
-        status = p7_Pipeline(pli, om, bg, Q->sq, Q->th);
-        p7_b200_ReplayArm(NULL);
-        if (status != eslOK && status != eslERANGE) p7_Fail("p7_Pipeline failed (%d): %s\n", status, pli->errbuf);
-        p7_pipeline_Reuse(pli);
-        pli->n_past_msv = c0;  pli->n_past_bias = c1;  pli->n_past_vit = c2;  pli->n_past_fwd = c3;   /* counted above */
+      if (ns > 0) {                                              /* Forward survivors: the reference's p7_Pipeline finishes them (replay) */
+        const int nt = (int) ESL_MAX(1, ESL_MIN((int64_t) ncpus, ns / 4));
+        int t;
+        for (t = 0; t < nt; t++) {
+          REPLAY_WORKER *W = &workers[t];
+          W->t = t;  W->nt = nt;  W->sv = sv;  W->ns = ns;  W->r = r;  W->qs = qs;  W->nmodels = nmodels;
+          W->om = (t == 0) ? om : p7_oprofile_Clone(om);
+          if (!W->bg) W->bg = (t == 0) ? bg : p7_bg_Clone(bg);
+          if (!W->om || !W->bg) p7_Fail("allocation failure\n");
+          if (t > 0 && o.do_biasfilter) p7_bg_SetFilter(W->bg, om->M, om->compo);
+        }
+        for (t = 1; t < nt; t++) if (pthread_create(&tids[t], NULL, replay_worker, &workers[t]) != 0) p7_Fail("Failed to start a worker thread\n");
+        replay_worker(&workers[0]);
+        for (t = 1; t < nt; t++) pthread_join(tids[t], NULL);
+        for (t = 0; t < nt; t++) {
+          if (workers[t].status != eslOK) p7_Fail("p7_Pipeline failed (%d): %s\n", workers[t].status, workers[t].errbuf);
+          if (t > 0) p7_oprofile_Destroy(workers[t].om);
+        }
       }
     }
     p7gpu_result_destroy(r);

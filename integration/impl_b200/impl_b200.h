@@ -43,6 +43,8 @@ extern const char *p7_b200_ErrorText(void);                              /* p7gp
 extern int         p7_b200_SetModel(P7_B200 *eng, const P7_OPROFILE *om, const P7_BG *bg);
 /* same for a profile of which only the MSV part has been read (p7_oprofile_ReadMSV, impl_sse/io.c:233): the MSV/SSV stage only */
 extern int         p7_b200_SetModelMSV(P7_B200 *eng, const P7_OPROFILE *om);
+/* scan mode: the targets are few and fixed; per-length constants of the current model for exactly these lengths (F1 = 1.0 under --max) */
+extern int         p7_b200_PrepareLengths(P7_B200 *eng, const int32_t *lengths, int64_t n, double F1);
 extern p7gpu_ctx     *p7_b200_Ctx    (P7_B200 *eng);
 extern p7gpu_profile *p7_b200_Profile(P7_B200 *eng);
 extern void        p7_b200_ViewOf(const P7_OPROFILE *om, p7gpu_oprofile_view *v);

@@ -101,6 +101,17 @@ static int set_model(P7_B200 *e, const P7_OPROFILE *om, const P7_BG *bg, int msv
 int p7_b200_SetModel   (P7_B200 *e, const P7_OPROFILE *om, const P7_BG *bg) { return set_model(e, om, bg, FALSE); }
 int p7_b200_SetModelMSV(P7_B200 *e, const P7_OPROFILE *om)                  { return set_model(e, om, NULL, TRUE); }
 
+int
+p7_b200_PrepareLengths(P7_B200 *e, const int32_t *lengths, int64_t n, double F1)
+{
+  int st;
+  if (!e || !e->prof) return eslEINVAL;
+  pthread_mutex_lock(&e->lock);
+  st = p7gpu_profile_prepare_lengths(e->prof, lengths, n, F1);
+  pthread_mutex_unlock(&e->lock);
+  return st == P7GPU_OK ? eslOK : eslESYS;
+}
+
 static int
 set_model(P7_B200 *e, const P7_OPROFILE *om, const P7_BG *bg, int msv_only)
 {

@@ -324,3 +324,30 @@ def test_result_may_outlive_its_context():
     r1.close(); r2.close()                                                         # after the context: must not crash
     c2 = engine.Context(0)                                                         # and the library is still usable
     c2.close()
+
+
+@pytest.mark.gpu
+def test_prepared_length_table_gives_identical_results(ctx):
+    """p7gpu_profile_prepare_lengths (scan mode): per-length constants for the target lengths only.  Same survivors, scores and
+    counters as the dense table; a later database with other lengths falls back to the dense table by itself."""
+    g = golden_set("Pkinase")
+    db = engine.SeqDB.upload(ctx, g.db)
+    dense = engine.Profile(ctx, g.oprofile)
+    r0 = engine.pipeline_run(ctx, dense, db, want_specials=False)
+    sparse = engine.Profile(ctx, g.oprofile)
+    sparse.prepare_lengths(np.unique(g.db.lengths), F1=0.02)
+    r1 = engine.pipeline_run(ctx, sparse, db, want_specials=False)
+    def same(a, b):                                                  # field by field: Viterbi scores of eslERANGE targets are NaN
+        return a.dtype == b.dtype and a.shape == b.shape and all(
+            np.array_equal(a[f], b[f], equal_nan=a.dtype[f].kind == "f") for f in a.dtype.names)
+    assert list(r0.counters) == list(r1.counters)
+    assert same(r0.survivors, r1.survivors) and len(r0.survivors) > 0
+    m0 = engine.pipeline_run(ctx, dense, db, stop_after_msv=True); m1 = engine.pipeline_run(ctx, sparse, db, stop_after_msv=True)
+    assert same(m0.msv_pass, m1.msv_pass)
+    other = seqdb.synth_db(300, mean=int(g.db.lengths.max()) + 50, seed=5)          # lengths the table was not prepared for
+    odb = engine.SeqDB.upload(ctx, other)
+    a = engine.pipeline_run(ctx, dense, odb, stop_after_msv=True); b = engine.pipeline_run(ctx, sparse, odb, stop_after_msv=True)
+    assert same(a.msv_pass, b.msv_pass)
+    for r in (r0, r1, m0, m1, a, b):
+        r.close()
+    odb.close(); db.close(); dense.close(); sparse.close()
