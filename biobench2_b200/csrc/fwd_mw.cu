@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
 {
   constexpr int G = 32 * W;
   __shared__ long long s_work[2];
-  __shared__ float s_pp[C][G];          // PP[j] per thread
+  __shared__ float s_q[C][G];           // q[j]: what one unit entering the D chain of the lane that owns node k-1 adds to M(i+1,k)
+  __shared__ float s_ppl[G];            // PP[C-1] per thread
   __shared__ float s_kB[5][G], s_kV[5][G];
   __shared__ float s_wB[W], s_wV[W], s_wK[W];      // per warp: B, V of the whole warp; K = Bexc(lane 31) * PP[C-1]
   __shared__ float s_pub[2][W][6];      // per row parity: P, U, M_last, I_last, D_last part (X = 0), pad
@@ -34,13 +35,16 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
     rII[j] = __ldg(p.tf + (6 * C + j) * G + g); rDD[j] = __ldg(p.tf + (7 * C + j) * G + g);
   }
   // ---- row-invariant coefficients of the D->D maps ----
-  float SPP, Bexc;
+  float Bexc, BexcPrev, ppLast;
   {
     float pp = 1.0f, spp = 0.f;
 #pragma unroll
-    for (int j = 0; j < C; j++) { s_pp[j][g] = pp; spp += pp; pp = pp * rDD[j]; }
+    for (int j = 0; j < C; j++) {
+      if (j + 1 < C) s_q[j + 1][g] = pp * rDM[j + 1];                 // D(i,k-1) = D0 + Z PP[j] feeds M(i+1,k) through tDM
+      else { s_ppl[g] = pp; ppLast = pp; }
+      spp += pp; pp = pp * rDD[j];
+    }
     float B = pp, V = spp;
-    SPP = spp;
 #pragma unroll
     for (int d = 0; d < 5; d++) {
       s_kB[d][g] = B; s_kV[d][g] = V;                                 // this lane's segment before step d
@@ -49,7 +53,10 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
     }
     Bexc = __shfl_up_sync(0xffffffffu, B, 1);
     if (lane == 0) Bexc = 1.0f;
-    if (lane == 31) { s_wB[w] = B; s_wV[w] = V; s_wK[w] = Bexc * s_pp[C - 1][g]; }
+    BexcPrev = __shfl_up_sync(0xffffffffu, Bexc, 1);                  // of the lane below (unused by lane 0)
+    if (lane == 31) { s_wB[w] = B; s_wV[w] = V; s_wK[w] = Bexc * ppLast; }
+    __syncthreads();
+    s_q[0][g] = lane ? s_ppl[g - 1] * rDM[0] : 0.0f;                  // first node: the D chain of the lane below (lane 0: see bd)
   }
   const float *rfg = p.rf + g;
   long long s, out;
@@ -58,11 +65,15 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
     const uint8_t *seq = p.c.res + p.c.off[s];
     const float pmove = p.c.lc[L].pmove, ploop = 1.0f - pmove;
     float *xrow = p.xmx ? p.xmx + p.xmx_off[out] : nullptr;
-    float mp[C], ip[C], dp[C], e[C];
+    // Row state, one row ahead of the recursion: part[j] = M tMM + I tIM + D0 tDM of row i-1 into node j (everything of
+    // M(i,j) that does not wait for row i-1's scan), ip[j] = I(i,j), and the two scan results of row i-1: xB and what
+    // entered the lane's D chain (Z; Zp for the lane below).
+    float part[C], ip[C], e[C];
 #pragma unroll
-    for (int j = 0; j < C; j++) mp[j] = ip[j] = dp[j] = e[j] = 0.0f;
+    for (int j = 0; j < C; j++) part[j] = ip[j] = e[j] = 0.0f;
     float xE = 0.f, xN = 1.f, xJ = 0.f, xB = pmove, xC = 0.f, totscale = 0.f;     // fwdback.c:287-294
-    float bm = 0.f, bi = 0.f, bd = 0.f;                   // M, I, D of node k-1 of this lane's first node (row i-1)
+    float Z = 0.f, Zp = 0.f;
+    float bx = 0.f;                                       // lane 0 of warps > 0: M, I, D of the node below, times their transitions
     if (xrow && g == 0) mw_store_specials(xrow, xE, xN, xJ, xB, xC, 1.0f);
     if (L > 0) {
       const float *rfx = rfg + (size_t) __ldg(seq) * (C * G);
@@ -70,54 +81,64 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
       for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
     }
 
-#pragma unroll (C >= 5 ? 2 : 1)
+#pragma unroll 1
     for (int i = 1; i <= L; i++) {
-      float pm = __shfl_up_sync(0xffffffffu, mp[C - 1], 1);
-      float pi = __shfl_up_sync(0xffffffffu, ip[C - 1], 1);
-      float pd = __shfl_up_sync(0xffffffffu, dp[C - 1], 1);
-      if (lane == 0) { pm = bm; pi = bi; pd = bd; }
-      float sumM = 0.f, dcv = 0.f;
+      // ---- behind the scan of row i-1: finish M(i,.) (:318-345) ----
+      float sv[C];
 #pragma unroll
-      for (int j = 0; j < C; j++) {                                   // :318-345
-        float sv = xB * rBM[j];
-        sv = sv + pm * rMM[j];
-        sv = sv + pi * rIM[j];
-        sv = sv + pd * rDM[j];
-        sv = sv * e[j];
-        sumM += sv;
-        pm = mp[j]; pi = ip[j]; pd = dp[j];
-        mp[j] = sv;
-        dp[j] = dcv;                                                  // M(i,k-1) * tMD(k-1); 0 for the lane's first node
-        dcv = sv * rMD[j];
-        ip[j] = pm * rMI[j] + pi * rII[j];
+      for (int j = C - 1; j >= 0; j--) {
+        float v = fmaf(xB, rBM[j], part[j]);
+        v = fmaf(j ? Z : Zp, s_q[j][g], v);
+        if (W > 1 && j == 0) v = v + bx;
+        sv[j] = v * e[j];
       }
-      if (i < L) {                                                    // next row's emissions: in flight during the scan
+      const float pm_b = __shfl_up_sync(0xffffffffu, sv[C - 1], 1);
+      const float pi_b = __shfl_up_sync(0xffffffffu, ip[C - 1], 1);
+      const float ipLast = ip[C - 1];
+      // the lane's own D->D chain with nothing entering (D0), the value leaving the lane (P) and the row-sum part (U)
+      float d0[C];
+      float sumM = sv[0], sumD0 = 0.f;
+      d0[0] = 0.f;
+#pragma unroll
+      for (int j = 1; j < C; j++) {
+        d0[j] = fmaf(d0[j - 1], rDD[j - 1], sv[j - 1] * rMD[j - 1]);   // one FMA per link of the chain
+        sumM += sv[j]; sumD0 += d0[j];
+      }
+      float P = fmaf(d0[C - 1], rDD[C - 1], sv[C - 1] * rMD[C - 1]);
+      float U = sumM + sumD0;
+      const float pd_b = __shfl_up_sync(0xffffffffu, d0[C - 1], 1);
+      // ---- independent of the scan: row i+1's part and I (these fill the scan's shuffle latency) ----
+#pragma unroll
+      for (int j = C - 1; j >= 1; j--) {
+        part[j] = fmaf(d0[j - 1], rDM[j], fmaf(ip[j - 1], rIM[j], sv[j - 1] * rMM[j]));
+        ip[j] = fmaf(ip[j], rII[j], sv[j] * rMI[j]);
+      }
+      {
+        const float v = fmaf(pd_b, rDM[0], fmaf(pi_b, rIM[0], pm_b * rMM[0]));
+        part[0] = lane ? v : 0.f;
+        ip[0] = fmaf(ip[0], rII[0], sv[0] * rMI[0]);
+      }
+      if (i < L) {                                                    // next row's emissions
         const float *rfx = rfg + (size_t) __ldg(seq + i) * (C * G);
 #pragma unroll
         for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
       }
-      // the lane's own D->D chain (nothing entering): dp[j] <- D0[j]
-      float sumD0 = 0.f;
-#pragma unroll
-      for (int j = 1; j < C; j++) { dp[j] = dp[j] + dp[j - 1] * rDD[j - 1]; sumD0 += dp[j]; }
-      float P = dcv + dp[C - 1] * rDD[C - 1];
-      float U = sumM + sumD0;
 #pragma unroll
       for (int d = 0; d < 5; d++) {                                   // lane maps -> inclusive warp prefix
         const float Pl = __shfl_up_sync(0xffffffffu, P, 1 << d), Ul = __shfl_up_sync(0xffffffffu, U, 1 << d);
-        if (lane >= (1 << d)) { U = (Ul + U) + s_kV[d][g] * Pl; P = P + s_kB[d][g] * Pl; }
+        if (lane >= (1 << d)) { U = fmaf(s_kV[d][g], Pl, Ul + U); P = fmaf(s_kB[d][g], Pl, P); }
       }
-      float Z = __shfl_up_sync(0xffffffffu, P, 1);                    // enters this lane when nothing enters the warp
+      Z = __shfl_up_sync(0xffffffffu, P, 1);                          // enters this lane when nothing enters the warp
+      Zp = __shfl_up_sync(0xffffffffu, P, 2);                         // ... and the lane below
       if (lane == 0) Z = 0.f;
+      if (lane <= 1) Zp = 0.f;
       if (W == 1) {                                                   // one warp: lane 31 holds the row sum, nothing enters
         xE = __shfl_sync(0xffffffffu, U, 31);
-#pragma unroll
-        for (int j = 0; j < C; j++) dp[j] = dp[j] + Z * s_pp[j][g];
       } else {
         const int par = i & 1;
         if (lane == 31) {
           float *pub = s_pub[par][w];
-          pub[0] = P; pub[1] = U; pub[2] = mp[C - 1]; pub[3] = ip[C - 1]; pub[4] = dp[C - 1] + Z * s_pp[C - 1][g];
+          pub[0] = P; pub[1] = U; pub[2] = sv[C - 1]; pub[3] = ipLast; pub[4] = fmaf(Z, ppLast, d0[C - 1]);
         }
         __syncthreads();                                              // ---- the row's only barrier ----
         float X = 0.f, Xmine = 0.f, Xprev = 0.f;
@@ -126,25 +147,28 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
         for (int v = 0; v < W; v++) {                                 // X_v = what enters warp v's first node
           if (v == w) Xmine = X;
           if (v + 1 == w) Xprev = X;
-          xE += s_pub[par][v][1] + s_wV[v] * X;
-          X = s_pub[par][v][0] + s_wB[v] * X;
+          xE += fmaf(s_wV[v], X, s_pub[par][v][1]);
+          X = fmaf(s_wB[v], X, s_pub[par][v][0]);
         }
-        Z = Z + Bexc * Xmine;
-#pragma unroll
-        for (int j = 0; j < C; j++) dp[j] = dp[j] + Z * s_pp[j][g];
-        if (w > 0) { const float *pub = s_pub[par][w - 1]; bm = pub[2]; bi = pub[3]; bd = pub[4] + s_wK[w - 1] * Xprev; }
+        Z = fmaf(Bexc, Xmine, Z);
+        if (lane) Zp = fmaf(BexcPrev, Xmine, Zp);
+        bx = 0.f;
+        if (w > 0 && lane == 0) {
+          const float *pub = s_pub[par][w - 1];
+          bx = fmaf(fmaf(s_wK[w - 1], Xprev, pub[4]), rDM[0], fmaf(pub[3], rIM[0], pub[2] * rMM[0]));
+        }
       }
       xN = xN * ploop;                                                // :413-416
-      xC = (xC * ploop) + (xE * p.s.xf_E_move);
-      xJ = (xJ * ploop) + (xE * p.s.xf_E_loop);
-      xB = (xJ * pmove) + (xN * pmove);
+      xC = fmaf(xC, ploop, xE * p.s.xf_E_move);
+      xJ = fmaf(xJ, ploop, xE * p.s.xf_E_loop);
+      xB = fmaf(xJ, pmove, xN * pmove);
       float scale = 1.0f;
-      if (xE > 1.0e4f) {                                              // :420-437
+      if (xE > 1.0e4f) {                                              // :420-437 (everything carried forward is linear in row i)
         const float inv = (float) (1.0 / (double) xE);
         xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
 #pragma unroll
-        for (int j = 0; j < C; j++) { mp[j] *= inv; dp[j] *= inv; ip[j] *= inv; }
-        bm *= inv; bi *= inv; bd *= inv;
+        for (int j = 0; j < C; j++) { part[j] *= inv; ip[j] *= inv; }
+        Z *= inv; Zp *= inv; bx *= inv;
         scale = xE;
         totscale = (float) ((double) totscale + log((double) xE));
         xE = 1.0f;
