@@ -752,11 +752,18 @@ def main():
             e2e_step()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        # one more, untimed step with per-launch CUDA events: how much of the streamed step the SSV launches themselves take
+        ctx.set_timing(True); ctx.reset_timing()
+        t1 = time.perf_counter(); e2e_step(); wall_probe = time.perf_counter() - t1
+        ssv_ms, ssv_n = ctx.kernel_time(engine.KERNEL_SSV); msvj_ms, _ = ctx.kernel_time(engine.KERNEL_MSVJ)
+        ctx.set_timing(False)
         h2d = int(h_p5.numel() + args.nseq * 12)
         e2e = {"value": total_cells * args.e2e_steps / dt / 1e9, "unit": "GCUPS", "steps": args.e2e_steps,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(e2e_out["survivors"] * 24 + 4),
                "ms_per_step": dt / args.e2e_steps * 1e3, "h2d_gbs_per_rank": h2d / (dt / args.e2e_steps) / 1e9,
                "survivors": e2e_out["survivors"], "counters": e2e_out["counters"],
+               "kernel_ms_one_step": {"ssv_sum_over_chunk_launches": ssv_ms, "ssv_launches": ssv_n, "msvj": msvj_ms, "wall_ms": wall_probe * 1e3,
+                                      "note": "launches of consecutive chunks run on two alternating streams and may overlap, so the sum can exceed the busy time"},
                "once_per_database_prep": {"pack5_seconds": pack5_s, "note": "5-bit transfer form built once per database, outside the timed region; "
                                           "digitising FASTA text is a further one-off (see cpu_baseline.hmmsearch_cli.fasta_reader and e2e_app, which include it)"},
                "api": "p7gpu_pipeline_run_host5(stop_after_msv): pinned host packed DB in the 5-bit transfer format (8 residues in 5 bytes, expanded on the device) streamed in 16-256 MB chunks (database order; the last chunk longest-first) under the "

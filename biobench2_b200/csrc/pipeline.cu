@@ -778,7 +778,12 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
   std::vector<Chunk> plan;
   int64_t max_chunk_seqs = 1;
   {
-    int64_t s = 0, bytes = (int64_t) 16 << 20;
+    const char *e0 = getenv("P7GPU_STREAM_CHUNK0_MB"), *e1 = getenv("P7GPU_STREAM_CHUNKMAX_MB"), *e2 = getenv("P7GPU_STREAM_GROWTH_PCT");
+    // (the 5-bit transfer form arrives 1.6x faster per residue, 88 against 40 GB/s of consumption: chunks may double, and fewer,
+    //  larger chunks mean fewer kernel boundaries — 0.12 ms each; measured 96.5 -> 95.0 ms per pass, scripts/e2e_chunk_sweep.sh)
+    const int64_t chunk0 = (int64_t) (e0 ? atoi(e0) : 16) << 20, chunkmax = (int64_t) (e1 ? atoi(e1) : (packed5 ? 1024 : 256)) << 20;
+    const int growth = e2 ? atoi(e2) : (packed5 ? 100 : 33);
+    int64_t s = 0, bytes = chunk0;
     while (s < nseq) {
       const int64_t lim = offsets[s] + bytes;
       int64_t lo = s + 1, hi = nseq;
@@ -786,7 +791,7 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
       plan.push_back({s, lo});
       max_chunk_seqs = std::max(max_chunk_seqs, lo - s);
       s = lo;
-      bytes = std::min<int64_t>(bytes + bytes / 3, (int64_t) 256 << 20);
+      bytes = std::min<int64_t>(bytes + bytes * growth / 100, chunkmax);
     }
   }
   cudaStream_t ms = ctx->stream, cs = ctx->copy_stream;
