@@ -125,9 +125,14 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
     if (w + 1 < W) nm = s_first[w + 1];
 
     // ---- rows L-1 .. 1 (:566-692) ----
+    // the residue whose emissions row i fetches and the Forward scale of row i-1 are read one row ahead: both are dependent
+    // global loads that the row's arithmetic was found waiting for (profiles/r4e_bwd_M400_full.txt)
+    uint32_t xn = L >= 2 ? __ldg(seq + L - 2) : 0u;
+    float fscale_n = L >= 2 ? frow[(size_t) (L - 1) * 6 + 5] : 1.0f;
 #pragma unroll (C >= 5 ? 2 : 1)
     for (int i = L - 1; i >= 1; i--) {
-      const float fscale = frow[(size_t) i * 6 + 5];
+      const float fscale = fscale_n;
+      if (i >= 2) fscale_n = frow[(size_t) (i - 1) * 6 + 5];
       // e[j] <- M(i+1,k) * e_k(x_{i+1})
       float S = 0.f;
 #pragma unroll
@@ -143,10 +148,11 @@ __global__ void __launch_bounds__(32 * W) bwd_mw_kernel(const FbMwParams p)
         mp[j] = ipv * rMI[j] + mpv * nMM[j];
       }
       {                                                               // emissions of x_i for the next row / the termination
-        const float *rfx = rfg + (size_t) __ldg(seq + i - 1) * (C * G);
+        const float *rfx = rfg + (size_t) xn * (C * G);
 #pragma unroll
         for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
         if (has_next) en = __ldg(rfx + 1);
+        if (i >= 2) xn = __ldg(seq + i - 2);
       }
       // the lane's own chain over P alone: dp[j] <- Dploc[j]
 #pragma unroll

@@ -75,10 +75,15 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
     float Z = 0.f, Zp = 0.f;
     float bx = 0.f;                                       // lane 0 of warps > 0: M, I, D of the node below, times their transitions
     if (xrow && g == 0) mw_store_specials(xrow, xE, xN, xJ, xB, xC, 1.0f);
+    // multi-warp CTAs fetch the residue of row i+1 a row before its emissions (the dependent byte load was found on the row's
+    // critical path there: 1.03 -> 1.09 TCUPS at M=2000); one-warp CTAs are faster without the extra live register
+    constexpr bool PF = W > 1;
+    uint32_t xn = 0;
     if (L > 0) {
       const float *rfx = rfg + (size_t) __ldg(seq) * (C * G);
 #pragma unroll
       for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
+      if (PF && L > 1) xn = __ldg(seq + 1);
     }
 
 #pragma unroll 1
@@ -119,9 +124,10 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
         ip[0] = fmaf(ip[0], rII[0], sv[0] * rMI[0]);
       }
       if (i < L) {                                                    // next row's emissions
-        const float *rfx = rfg + (size_t) __ldg(seq + i) * (C * G);
+        const float *rfx = rfg + (size_t) (PF ? xn : (uint32_t) __ldg(seq + i)) * (C * G);
 #pragma unroll
         for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
+        if (PF && i + 1 < L) xn = __ldg(seq + i + 1);
       }
 #pragma unroll
       for (int d = 0; d < 5; d++) {                                   // lane maps -> inclusive warp prefix
