@@ -12,7 +12,7 @@ timeout 600 python bench.py --impl reference > gpurun_out/${R}_bench_ref_n1.json
 Q="--steps 2 --warmup 1 --e2e-steps 0 --no-cpu-baseline --strong-total 0 --config5-passes 0 --no-app"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$R.csv python bench.py $Q > gpurun_out/bench_ncu_list.log 2>&1; echo "ncu list rc=$?"
 python profiles/summarize.py launches gpurun_out/launches_$R.csv > gpurun_out/${R}_launches_bench.txt
-timeout 900 ncu --set full --clock-control none -k regex:ssv_kernel -s 1 -c 1 -o $T/prof_ssv -f python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --no-stages --strong-total 0 --no-app > gpurun_out/bench_ncu_full.log 2>&1; echo "ncu ssv rc=$?"
+timeout 900 ncu --set full --clock-control none -k regex:"ssv_tm_kernel|ssv_kernel" -s 1 -c 1 -o $T/prof_ssv -f python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --no-stages --strong-total 0 --no-app > gpurun_out/bench_ncu_full.log 2>&1; echo "ncu ssv rc=$?"
 python profiles/summarize.py kernel $T/prof_ssv.ncu-rep > gpurun_out/${R}_ssv_kernel_full.txt; grep -E "dram__bytes|time_duration|t_sector_hit" gpurun_out/${R}_ssv_kernel_full.txt
 timeout 900 ncu --set full --clock-control none -k regex:"vitp_kernel|fwd_mw_kernel|bwd_mw_kernel|region_trigger_kernel|bias_kernel" -c 6 -o $T/prof_stages -f python scripts/stage_bench.py synth_M400 30000 > gpurun_out/ncu_stage.log 2>&1; echo rc=$?
 python profiles/summarize.py kernel $T/prof_stages.ncu-rep > gpurun_out/${R}_stage_kernels_M400_full.txt
