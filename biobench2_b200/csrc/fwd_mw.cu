@@ -6,7 +6,8 @@
 //   lane      D[j] = D0[j] + Z * PP[j]            PP[j] = prod_{j'<j} tDD[j'],  D0 = the chain with nothing entering
 //             leaves the lane   P + Bl * Z        P = M_last tMD_last + D0_last tDD_last,  Bl = prod_j tDD[j]
 //             row-sum part      U + SPP * Z       U = sum_j M[j] + D0[j],  SPP = sum_j PP[j]
-//   warp      ONE Kogge-Stone pass over (P, U) composes the lane maps (constants kB/kV per step, built once per CTA)
+//   warp      ONE Kogge-Stone pass over (P, U) composes the lane maps (constants kB/kV per step, built once per CTA); one-warp
+//             CTAs scan P alone and take the row sum as a plain warp sum of U + cU P with row-invariant weights cU
 //   CTA       lane 31 publishes the warp's (P, U) and its last node's M, I, D-part; after the barrier every thread
 //             runs the <= W-step recurrence X_{v+1} = P_v + B_v X_v and xE = sum_v U_v + V_v X_v from shared memory.
 // Arithmetic inside a cell is that of fwdbwd.cu (FTZ; these production kernels allow FMA contraction, csrc/Makefile); only the association order of the D->D sums differs.
@@ -21,7 +22,7 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
   __shared__ long long s_work[2];
   __shared__ float s_q[C][G];           // q[j]: what one unit entering the D chain of the lane that owns node k-1 adds to M(i+1,k)
   __shared__ float s_ppl[G];            // PP[C-1] per thread
-  __shared__ float s_kB[5][G], s_kV[5][G];
+  __shared__ float s_kB[5][G], s_kV[W == 1 ? 1 : 5][G];
   __shared__ float s_wB[W], s_wV[W], s_wK[W];      // per warp: B, V of the whole warp; K = Bexc(lane 31) * PP[C-1]
   __shared__ float s_pub[2][W][6];      // per row parity: P, U, M_last, I_last, D_last part (X = 0), pad
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
     rII[j] = __ldg(p.tf + (6 * C + j) * G + g); rDD[j] = __ldg(p.tf + (7 * C + j) * G + g);
   }
   // ---- row-invariant coefficients of the D->D maps ----
-  float Bexc, BexcPrev, ppLast;
+  float Bexc, BexcPrev, ppLast, cU;
   {
     float pp = 1.0f, spp = 0.f;
 #pragma unroll
@@ -47,9 +48,24 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
     float B = pp, V = spp;
 #pragma unroll
     for (int d = 0; d < 5; d++) {
-      s_kB[d][g] = B; s_kV[d][g] = V;                                 // this lane's segment before step d
+      s_kB[d][g] = B; if (W > 1) s_kV[d][g] = V;                      // this lane's segment before step d
       const float Bl = __shfl_up_sync(0xffffffffu, B, 1 << d), Vl = __shfl_up_sync(0xffffffffu, V, 1 << d);
       if (lane >= (1 << d)) { V = Vl + V * Bl; B = B * Bl; }
+    }
+    // One-warp CTAs: the row sum is linear in the lanes' P with ROW-INVARIANT weights, xE = sum_g U_g + SPP_g Z_g with
+    // Z_g = sum_{h<g} T(g,h) P_h, i.e. xE = sum_g (U_g + cU_g P_g), cU_g = SPP_{g+1} + Bl_{g+1} cU_{g+1} — one plain warp sum
+    // instead of a second value riding through the Kogge-Stone pass (10 instructions fewer per row: M=100 0.61 -> 0.66 TCUPS,
+    // M=400 1.15 -> 1.16; multi-warp CTAs measured slower with it, 1.085 -> 1.05 at M=2000, and keep the pair scan)
+    cU = 0.f;
+    if (W == 1) {
+      float c = 0.f;
+      const float Bl = pp, Sl = spp;                                  // this lane's whole-lane product and sum
+#pragma unroll 1
+      for (int t = 30; t >= 0; t--) {
+        const float cn = __shfl_down_sync(0xffffffffu, c, 1), Bn = __shfl_down_sync(0xffffffffu, Bl, 1), Sn = __shfl_down_sync(0xffffffffu, Sl, 1);
+        if (lane == t) c = fmaf(Bn, cn, Sn);
+      }
+      cU = c;
     }
     Bexc = __shfl_up_sync(0xffffffffu, B, 1);
     if (lane == 0) Bexc = 1.0f;
@@ -129,17 +145,27 @@ __global__ void __launch_bounds__(32 * W) fwd_mw_kernel(const FbMwParams p)
         for (int j = 0; j < C; j++) e[j] = __ldg(rfx + j * G);
         if (PF && i + 1 < L) xn = __ldg(seq + i + 1);
       }
+      if (W == 1) {
+        U = fmaf(cU, P, U);                                           // this lane's share of the row sum
 #pragma unroll
-      for (int d = 0; d < 5; d++) {                                   // lane maps -> inclusive warp prefix
-        const float Pl = __shfl_up_sync(0xffffffffu, P, 1 << d), Ul = __shfl_up_sync(0xffffffffu, U, 1 << d);
-        if (lane >= (1 << d)) { U = fmaf(s_kV[d][g], Pl, Ul + U); P = fmaf(s_kB[d][g], Pl, P); }
+        for (int d = 0; d < 5; d++) {                                 // lane maps -> inclusive warp prefix; the row sum beside it
+          const float Pl = __shfl_up_sync(0xffffffffu, P, 1 << d);
+          U += __shfl_xor_sync(0xffffffffu, U, 1 << d);
+          if (lane >= (1 << d)) P = fmaf(s_kB[d][g], Pl, P);
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < 5; d++) {                                 // lane maps -> inclusive warp prefix, the row sum riding along
+          const float Pl = __shfl_up_sync(0xffffffffu, P, 1 << d), Ul = __shfl_up_sync(0xffffffffu, U, 1 << d);
+          if (lane >= (1 << d)) { U = fmaf(s_kV[d][g], Pl, Ul + U); P = fmaf(s_kB[d][g], Pl, P); }
+        }
       }
       Z = __shfl_up_sync(0xffffffffu, P, 1);                          // enters this lane when nothing enters the warp
       Zp = __shfl_up_sync(0xffffffffu, P, 2);                         // ... and the lane below
       if (lane == 0) Z = 0.f;
       if (lane <= 1) Zp = 0.f;
-      if (W == 1) {                                                   // one warp: lane 31 holds the row sum, nothing enters
-        xE = __shfl_sync(0xffffffffu, U, 31);
+      if (W == 1) {                                                   // one warp: every lane holds the row sum, nothing enters
+        xE = U;
       } else {
         const int par = i & 1;
         if (lane == 31) {
