@@ -838,7 +838,8 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
   S_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
   S_CUDA(cudaEventRecord(ev_main, ms));
   S_CUDA(cudaStreamWaitEvent(cs, ev_main, 0));
-  for (int l = 1; l <= 2; l++) S_CUDA(cudaStreamWaitEvent(ctx->lanes[l].stream, ev_main, 0));
+  for (int l = 1; l <= 3; l++) S_CUDA(cudaStreamWaitEvent(ctx->lanes[l].stream, ev_main, 0));
+  cudaStream_t us = ctx->lanes[3].stream;               // the 5-bit chunks are expanded here: see below
   tr.mark("stream: setup");
 
   // the per-length constant table is sized once, before anything is queued: growing it in the middle of the stream would
@@ -874,11 +875,9 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
     }
     nres += cres; Lmax = std::max(Lmax, cLmax);
     S_CHECK(ensure_len_table(prof, Lmax, F1));
-    if (packed5) {                                                    // 5/8 of the bytes over PCIe, expanded on the copy stream
+    if (packed5) {                                                    // 5/8 of the bytes over PCIe, expanded on the device (below)
       const int64_t g_lo = (offsets[s_lo] - 1) / 64, g_hi = (offsets[s_hi - 1] + lengths[s_hi - 1] + 1 + 63) / 64;
       S_CUDA(cudaMemcpyAsync(d_pack + g_lo * 40, packed5 + g_lo * 40, (size_t) (g_hi - g_lo) * 40, cudaMemcpyHostToDevice, cs));
-      unpack5_kernel<<<(unsigned) ((g_hi - g_lo + 127) / 128), 128, 0, cs>>>((const uint32_t *) (d_pack + g_lo * 40), (uint4 *) (d_res + g_lo * 64), g_hi - g_lo);
-      ctx->launches++;
     } else {
       const int64_t b_lo = (offsets[s_lo] - 1) & ~15LL;
       const int64_t b_hi = std::min<int64_t>(nbytes, (offsets[s_hi - 1] + lengths[s_hi - 1] + 1 + 15) & ~15LL);
@@ -888,6 +887,17 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
     S_CUDA(cudaMemcpyAsync(d_len + s_lo, lengths + s_lo, 4 * (size_t) cn, cudaMemcpyHostToDevice, cs));
     cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
     S_CUDA(cudaEventRecord(ev, cs));
+    if (packed5) {
+      // The expansion kernel needs SM resources, which the persistent SSV grid of the previous chunk may hold until it ends.  On the
+      // copy stream it would hold back every later copy with it (and the copies lead the kernels by little once the chunks
+      // double); on a stream of its own only the chunk it expands waits for it.
+      const int64_t g_lo = (offsets[s_lo] - 1) / 64, g_hi = (offsets[s_hi - 1] + lengths[s_hi - 1] + 1 + 63) / 64;
+      S_CUDA(cudaStreamWaitEvent(us, ev, 0));
+      unpack5_kernel<<<(unsigned) ((g_hi - g_lo + 127) / 128), 128, 0, us>>>((const uint32_t *) (d_pack + g_lo * 40), (uint4 *) (d_res + g_lo * 64), g_hi - g_lo);
+      ctx->launches++;
+      S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
+      S_CUDA(cudaEventRecord(ev, us));
+    }
     const int lane = 1 + (int) (c & 1);
     const Lane &ln = ctx->lanes[lane];
     S_CUDA(cudaStreamWaitEvent(ln.stream, ev, 0));
@@ -910,7 +920,7 @@ static int stream_msv(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *
     if (h_status) S_CUDA(cudaMemcpyAsync(h_status + s_lo, d_st + s_lo, 4 * (size_t) cn, cudaMemcpyDeviceToHost, ln.stream));
   }
   // the main stream continues after both lanes and the copy stream
-  for (int l = 0; l <= 2; l++) {
+  for (int l = 0; l <= 3; l++) {
     cudaEvent_t ev; S_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); events.push_back(ev);
     S_CUDA(cudaEventRecord(ev, l == 0 ? cs : ctx->lanes[l].stream));
     S_CUDA(cudaStreamWaitEvent(ms, ev, 0));
