@@ -235,6 +235,30 @@ def test_five_bit_transfer_format_gives_identical_results(ctx, name):
     prof.close()
 
 
+def test_streamed_search_is_independent_of_the_chunk_plan(ctx, monkeypatch):
+    """The streamed search (bytes and 5-bit form) cut into many small chunks — every chunk boundary, the expansion kernels on
+    their own stream, the copies running ahead — against one chunk and against the resident database."""
+    g = golden_set("synth_M400")
+    prof = engine.Profile(ctx, g.oprofile)
+    hdb = seqdb.concat([g.db, seqdb.synth_db(60000, mean=300, seed=21, degenerate_frac=0.01)])     # ~18 MB of residues
+    p5 = engine.pack5(hdb.residues)
+    db = engine.SeqDB.upload(ctx, hdb)
+    ref = engine.pipeline_run(ctx, prof, db, stop_after_msv=True)
+    want = (list(ref.counters), ref.msv_pass["seqidx"].copy(), bits(ref.msv_pass["usc"]).copy())
+    for chunk0, chunkmax, growth in ((1, 1, 0), (1, 3, 100), (2, 64, 33), (64, 64, 0)):
+        monkeypatch.setenv("P7GPU_STREAM_CHUNK0_MB", str(chunk0)); monkeypatch.setenv("P7GPU_STREAM_CHUNKMAX_MB", str(chunkmax))
+        monkeypatch.setenv("P7GPU_STREAM_GROWTH_PCT", str(growth))
+        for r in (engine.pipeline_run_host5(ctx, prof, p5, hdb, stop_after_msv=True), engine.pipeline_run_host(ctx, prof, hdb, stop_after_msv=True)):
+            assert list(r.counters) == want[0], (chunk0, chunkmax, growth)
+            assert np.array_equal(r.msv_pass["seqidx"], want[1]) and np.array_equal(bits(r.msv_pass["usc"]), want[2])
+            r.close()
+    monkeypatch.setenv("P7GPU_STREAM_CHUNK0_MB", "1"); monkeypatch.setenv("P7GPU_STREAM_CHUNKMAX_MB", "1")
+    full = engine.pipeline_run_host5(ctx, prof, p5, hdb)                      # 1 MB chunks through the whole pipeline
+    whole = engine.pipeline_run(ctx, prof, db)
+    assert list(full.counters) == list(whole.counters) and np.array_equal(full.survivors["seqidx"], whole.survivors["seqidx"])
+    full.close(); whole.close(); ref.close(); db.close(); prof.close()
+
+
 @pytest.mark.parametrize("name", ["synth_M400", "globins4", "Pkinase", "tufa420_sprot", "synth_M100"])
 def test_device_stage_decisions_equal_host_decisions(ctx, name):
     """Default path: the bias and Viterbi P-value tests are float-threshold compares on the device (thresholds found and
