@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(THREADS, CTAS) ssv_tm_kernel(const SsvTmParams
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tbase = s_slot;
-  const uint32_t mine = tbase + ((uint32_t) ((warp & 3) * 32) << 16);
+  // (through a REDUX so that the compiler knows the address is warp-uniform and keeps the per-row address arithmetic on the
+  //  uniform datapath)
+  const uint32_t mine = __reduce_or_sync(0xffffffffu, tbase + ((uint32_t) ((warp & 3) * 32) << 16));
   if (warp < 4) {                                                          // one warp per quarter writes the table
     for (int x = 0; x < NTABROWS; x++) {
       uint32_t t[NX];
@@ -308,10 +310,24 @@ __global__ void __launch_bounds__(THREADS, CTAS) ssv_tm_kernel(const SsvTmParams
       };
       int i = 0, since_check = 0;
       bool over = false;
+      // rows up to the first 4-byte boundary of the residue array, one at a time (none in the 16-byte-aligned layout)
+      for (; i < L && ((o + i) & 3); i++) {
+        uint32_t g[NX];
+        Tmem<NX>::ld(mine + ldg_res1(seq + i) * NX, g);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        row(g);
+#pragma unroll
+        for (int q = 0; q < Q; q++) xE = __vmaxs2(xE, v[q]);
+      }
       for (; i + DIAG_CHUNK <= L; i += DIAG_CHUNK) {
+        // Four residues per 32-bit load, made warp-uniform by a REDUX (all lanes hold the same word): the byte extraction and the
+        // table address then run on the uniform datapath, and the integer pipe — what binds this kernel — loses the per-row R2UR
         uint32_t xs[DIAG_CHUNK];
 #pragma unroll
-        for (int r = 0; r < DIAG_CHUNK; r++) xs[r] = ldg_res1(seq + i + r);
+        for (int r4 = 0; r4 < DIAG_CHUNK / 4; r4++) {
+          const uint32_t w = __reduce_or_sync(0xffffffffu, __ldg(reinterpret_cast<const uint32_t *>(seq + i) + r4));
+          xs[4 * r4] = w & 0xffu; xs[4 * r4 + 1] = (w >> 8) & 0xffu; xs[4 * r4 + 2] = (w >> 16) & 0xffu; xs[4 * r4 + 3] = w >> 24;
+        }
         // the table row of DP row r+1 is fetched while row r is computed; tcgen05.wait::ld only orders the loads already issued
         uint32_t g[NX], gn[NX];
         Tmem<NX>::ld(mine + xs[0] * NX, g);
