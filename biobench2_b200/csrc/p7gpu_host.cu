@@ -575,8 +575,8 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
       }
     // column-stationary layout for the Tensor Memory kernel: lane l, register q, half h <-> node k = 1 + h*32*Q + l*Q + q
     const int Qt = (M + 63) / 64;
-    if (Qt <= 8) {
-      const int NX = Qt <= 1 ? 1 : Qt <= 2 ? 2 : Qt <= 4 ? 4 : 8;
+    if (Qt <= 16) {
+      const int NX = Qt <= 1 ? 1 : Qt <= 2 ? 2 : Qt <= 4 ? 4 : Qt <= 8 ? 8 : 16;
       std::vector<uint32_t> tt((size_t) NTABROWS * NX * 32);
       auto gain = [&](int x, int col) { return (x < Kp && col < M) ? gs[(size_t) x * g.P + col] : (int16_t) SSV_PADGAIN; };   // col = k-1
       for (int x = 0; x < NTABROWS; x++)

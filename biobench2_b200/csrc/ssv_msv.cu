@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// ssv_tm_kernel: the same filter with the gain table in Tensor Memory (M <= 512).
+// ssv_tm_kernel: the same filter with the gain table in Tensor Memory (M <= 1024).
 //
 // ssv_kernel above is bound by shared-memory bandwidth (Q LDS.32 per DP row per warp against 128 B/clk per SM; the integer
 // pipe idles ~16 % of the time).  TMEM is read at 64 B/clk per SM sub-partition (probes/tmem_probe.cu: 237 B/clk per SM), by a
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(THREADS) ssv_kernel(const SsvParams p)
 // inside the lane plus ONE warp rotation for the lane boundary (lane 0 takes node 0 = floor into its low half and lane 31's
 // low half, node 32*Q, into its high half: one multiply-add, as in vit.cu).  Per row: 1 TMEM load, 1 SHFL, Q packed add-max,
 // Q/2 three-input max.  Arithmetic and every decision are those of ssv_kernel (same gains, same early exit, same epilogue).
-// TMEM: 30 table rows x N columns, N = 1/2/4/8 >= Q, in each of the four 32-lane quarters (warp w reads quarter w % 4).
+// TMEM: 30 table rows x N columns, N = 1/2/4/8/16 >= Q, in each of the four 32-lane quarters (warp w reads quarter w % 4).
 struct SsvTmParams {
   const uint32_t *tab;          // [NTABROWS][NX][32]
   const uint8_t *res; const int64_t *off; const int32_t *len; const int32_t *order; const int64_t *idx;
@@ -230,6 +230,11 @@ struct SsvTmParams {
   unsigned long long *work_counter;
 };
 
+#ifndef P7G_SSV_TM16_THREADS
+#define P7G_SSV_TM16_THREADS 768
+#endif
+constexpr int SSV_TM16_THREADS = P7G_SSV_TM16_THREADS;   // 513 <= M <= 1024: the table takes all 512 TMEM columns, one CTA per SM
+
 // one residue, zero-extended by the load itself (the compiler masks a uint8_t again after widening it)
 __device__ __forceinline__ uint32_t ldg_res1(const uint8_t *ptr)
 {
@@ -238,10 +243,10 @@ __device__ __forceinline__ uint32_t ldg_res1(const uint8_t *ptr)
   return x;
 }
 
-__host__ __device__ constexpr int ssv_tm_nx(int Q)      { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8; }
-__host__ __device__ constexpr int ssv_tm_cols(int NX)   { return NX == 8 ? 256 : NX == 4 ? 128 : NX == 2 ? 64 : 32; }      // power of two >= 30*NX
-__host__ __device__ constexpr int ssv_tm_threads(int NX) { return NX == 8 ? 512 : 256; }
-__host__ __device__ constexpr int ssv_tm_ctas(int NX)   { return NX == 8 ? 2 : 4; }                                       // per SM: TMEM columns and registers allow this many
+__host__ __device__ constexpr int ssv_tm_nx(int Q)      { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : Q <= 8 ? 8 : 16; }
+__host__ __device__ constexpr int ssv_tm_cols(int NX)   { return NX == 16 ? 512 : NX == 8 ? 256 : NX == 4 ? 128 : NX == 2 ? 64 : 32; }      // power of two >= 30*NX
+__host__ __device__ constexpr int ssv_tm_threads(int NX) { return NX == 16 ? SSV_TM16_THREADS : NX == 8 ? 512 : 256; }
+__host__ __device__ constexpr int ssv_tm_ctas(int NX)   { return NX == 16 ? 1 : NX == 8 ? 2 : 4; }                         // per SM: TMEM columns and registers allow this many
 
 template <int Q, int NX, int THREADS, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS) ssv_tm_kernel(const SsvTmParams p)
@@ -540,7 +545,7 @@ int launch_ssv(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
     t.pass_list = p.pass_list; t.pass_count = p.pass_count; t.work_counter = p.work_counter;
     switch (prof->ssv_tm_Q) {
 #define X(QV) case QV: return launch_ssv_tm_q<QV>(ctx, ln.stream, t);
-      X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+      X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 #undef X
     default: break;
     }

@@ -1,13 +1,13 @@
 import os, sys, json
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from biobench2_b200 import engine, seqdb
 from biobench2_b200.oprofile import OProfile
 ctx = engine.Context(0); ctx.set_timing(True)
 hdb = seqdb.synth_db(2000000, mean=350, seed=77)
 db = engine.SeqDB.upload(ctx, hdb)
-for name in ("synth_M400", "Pkinase", "synth_M100", "tufa420", "fn3", "globins4"):
-    op = OProfile.load('/root/repo/tests/golden/prof_%s.npz' % name)
+for name in ("synth_M800", "synth_M400", "Pkinase", "synth_M100", "globins4"):
+    op = OProfile.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'prof_%s.npz' % name))
     prof = engine.Profile(ctx, op)
     out = {"profile": name, "M": op.M}
     res = {}
