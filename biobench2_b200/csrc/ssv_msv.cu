@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) ssv_tm_kernel(const SsvTmParams
       int i = 0, since_check = 0;
       bool over = false;
       // rows up to the first 4-byte boundary of the residue array, one at a time (none in the 16-byte-aligned layout)
-      for (; i < L && ((o + i) & 3); i++) {
+      for (; i < L && (reinterpret_cast<uintptr_t>(seq + i) & 3); i++) {
         uint32_t g[NX];
         Tmem<NX>::ld(mine + ldg_res1(seq + i) * NX, g);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
