@@ -575,7 +575,7 @@ def main():
         if tj.get("profile") == args.profile and tj.get("nseq") == args.nseq and tj.get("mean_len") == args.mean_len:
             traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     pk_instr = int_peak / 2.0
-    tm_path = 193 <= M <= 512            # ssv_msv.cu: launch_ssv takes the Tensor Memory table there (option ssv_tmem, default on)
+    tm_path = 193 <= M <= 1024           # ssv_msv.cu: launch_ssv takes the Tensor Memory table there (option ssv_tmem, default on)
     roofline = {"bound": "int16x2-issue", "kernel": "ssv_tm_kernel (gain table in Tensor Memory, one tcgen05.ld per row)" if tm_path else "ssv_kernel (gain table in shared memory)",
                 "achieved": ssv_gcups * OPS_PER_CELL["ssv"], "peak": pk_instr, "unit": "G packed int16x2 instr/s (VIADDMNMX.S16x2)",
                 "frac": ssv_gcups * OPS_PER_CELL["ssv"] / pk_instr if pk_instr else None,

@@ -111,7 +111,7 @@ struct p7gpu_ctx {
   int          fb_one_warp = 0;         // option "fb_one_warp": Forward/Backward with the one-warp kernels even for long models (tests)
   int          fb_exact = 0;            // option "fb_exact": p7gpu_forward_batch/p7gpu_backward_batch run the exact-order kernels (fbx.cu)
   int          fb_fast = 0;             // option "fb_fast": the one-target wrappers p7gpu_ForwardParser/BackwardParser run the fast kernels
-  int          ssv_tmem = 1;            // option "ssv_tmem": SSV gain table in Tensor Memory when M <= 512 (ssv_tm_kernel); 0 = shared memory
+  int          ssv_tmem = 1;            // option "ssv_tmem": SSV gain table in Tensor Memory when 193 <= M <= 1024 (ssv_tm_kernel; 2 = at every M <= 1024); 0 = shared memory
   int          fbx_warps = 0;           // option "fbx_warps": cap on resident one-warp CTAs per SM of the exact-order kernels (0 = occupancy)
   float        bias_window = 0.f;       // option "bias_window_log2": half-width 2^-n of the bias kernel's log() certainty test (tests widen it)
   int64_t      bias_fixed = 0;          // targets whose filtersc the host recomputed so far (diagnostic)
@@ -134,7 +134,7 @@ struct p7gpu_profile {
   // SSV / MSV diagonal tables (device): [NTABROWS][rowWords] words = (int16 gain lo, int16 gain hi)
   p7g::DiagGeom geom;
   uint32_t *d_ssv_tab = nullptr;
-  uint32_t *d_ssv_tm = nullptr;        // SSV gains in the Tensor Memory layout [NTABROWS][NX][32] (M <= 512), see ssv_tm_kernel
+  uint32_t *d_ssv_tm = nullptr;        // SSV gains in the Tensor Memory layout [NTABROWS][NX][32] (M <= 1024), see ssv_tm_kernel
   int ssv_tm_Q = 0;
   uint32_t *d_msv_tab = nullptr;
   // Viterbi (int16) and Forward/Backward (f32) k-space tables (device)

@@ -536,8 +536,8 @@ int launch_ssv(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView
   p.work_counter = (unsigned long long *) (ln.counters + CTR_SSV_WORK);
   // work counter (2 words) + the lane's eslENORESULT count (CTR_NORES_COUNT = CTR_SSV_WORK + 2)
   P7G_CUDA(cudaMemsetAsync(ln.counters + CTR_SSV_WORK, 0, 4 * sizeof(unsigned int), ln.stream));
-  // 193 <= M <= 512 (or option ssv_tmem = 2: any M <= 512): gain table in Tensor Memory.  Below Q = 4 the per-row fixed cost
-  // (rotation, address hand-over to the uniform register file) outweighs the saved LDS: measured 8.0 against 9.2 TCUPS at M = 100
+  // 193 <= M <= 1024 (or option ssv_tmem = 2: any M <= 1024): gain table in Tensor Memory.  Below Q = 4 the per-row fixed cost
+  // (rotation, table address, LDTM) outweighs the saved LDS: measured 8.05 against 9.2 TCUPS at M = 100
   if (prof->d_ssv_tm && ctx->ssv_tmem && (prof->ssv_tm_Q >= 4 || ctx->ssv_tmem >= 2)) {
     SsvTmParams t;
     t.tab = prof->d_ssv_tm; t.res = p.res; t.off = p.off; t.len = p.len; t.order = p.order; t.idx = p.idx; t.first = p.first; t.n = p.n;

@@ -20,7 +20,7 @@ for name in ("synth_M2000", "synth_M800", "synth_M400", "synth_M100"):
     r = engine.pipeline_run_host5(ctx, prof, engine.pack5(hdb.residues), hdb); r.close()
     r = engine.pipeline_run(ctx, prof, db, F1=0.5, F2=0.3, F3=0.2); r.close()
     r = engine.pipeline_run(ctx, prof, db, F1=0.5, F2=0.3, F3=0.2, fb_exact=True, region_trigger=True, decode=True); r.close()   # exact-order kernels + decoding
-    ctx.set_option("ssv_tmem", 2); engine.ssvfilter_batch(ctx, prof, db)                 # Tensor Memory table wherever it fits (M <= 512)
+    ctx.set_option("ssv_tmem", 2); engine.ssvfilter_batch(ctx, prof, db)                 # Tensor Memory table wherever it fits (M <= 1024)
     ctx.set_option("ssv_tmem", 0); engine.ssvfilter_batch(ctx, prof, db); ctx.set_option("ssv_tmem", 1)
     print(name, "ok", float(np.nanmax(fsc)), flush=True)
     db.close(); prof.close()
