@@ -10,7 +10,12 @@
 //             CTAs scan P alone and take the row sum as a plain warp sum of U + cU P with row-invariant weights cU
 //   CTA       lane 31 publishes the warp's (P, U) and its last node's M, I, D-part; after the barrier every thread
 //             runs the <= W-step recurrence X_{v+1} = P_v + B_v X_v and xE = sum_v U_v + V_v X_v from shared memory.
-// Arithmetic inside a cell is that of fwdbwd.cu (FTZ; these production kernels allow FMA contraction, csrc/Makefile); only the association order of the D->D sums differs.
+// The row is PIPELINED: the state carried from row to row is part[j] = M tMM + I tIM + D0 tDM into node j (everything of M(i+1,j)
+// that does not wait for row i's scan) and I(i+1,j), both computed under the scan's shuffle latency; after the scan a cell is
+// finished as ((part + xB tBM) + Z q[j]) e with q[j] = PP[j-1] tDM[j] (row-invariant, shared memory) — the correction pass
+// D += Z PP is gone, and the first cell of a lane takes the chain of the lane below (Zp, q[0]).  DESIGN.md 4.4.
+// Arithmetic: FTZ; every fused multiply-add is written out (fmaf) and the file is built without implicit contraction, so that
+// variants can be compared bit for bit (probes/fwd_tm_experiment.cu); only the association order of the sums differs from fwdbwd.cu.
 #include "fwdbwd_mw.cuh"
 
 namespace p7g {

@@ -10,7 +10,7 @@
 // the only table traffic is one emission load per cell (L1-resident, coalesced [x][j][g]).  Per row the warps meet at
 // two CTA barriers: Forward — (1) the affine D->D maps of the warps are composed in warp order, (2) the row sum xE;
 // Backward — (1) the B-state sum xB and the k+1 neighbour across the warp boundary, (2) the D<-D maps.
-// Arithmetic inside a lane is that of fwdbwd.cu (FTZ; these production kernels allow FMA contraction, csrc/Makefile); the reference's rescaling rule and xmx layout are kept.
+// Arithmetic inside a lane is that of fwdbwd.cu with FMA (FTZ; bwd_mw.cu by contraction, fwd_mw.cu written out — csrc/Makefile); the reference's rescaling rule and xmx layout are kept.
 #pragma once
 #include "dp_common.cuh"
 #include <math_constants.h>
