@@ -223,6 +223,22 @@ static LenConst len_const(const p7gpu_profile *prof, int L, double F1)
   return c;
 }
 
+// hmmscan's block prefilter (scan.cu): tjb_b and the smallest passing xJ of a model that has no p7gpu_profile, for the given
+// target lengths; the same len_const() as every uploaded profile uses, so the decisions are the same
+void scan_len_words(const p7gpu_oprofile_view *om, const int32_t *lengths, int64_t n, double F1, uint32_t *out)
+{
+  p7gpu_profile tmp;
+  tmp.M = om->M; tmp.Kp = om->Kp; tmp.nj = om->nj;
+  memcpy(tmp.evparam, om->evparam, sizeof(tmp.evparam));
+  tmp.msv.tbm_b = om->tbm_b; tmp.msv.tec_b = om->tec_b; tmp.msv.base_b = om->base_b; tmp.msv.bias_b = om->bias_b;
+  tmp.msv.scale_b = om->scale_b; tmp.scale_b = om->scale_b;
+  tmp.scale_w = 1.0f;                                                   // the Viterbi constant of LenConst is not used by the prefilter
+  for (int64_t k = 0; k < n; k++) {
+    const LenConst c = len_const(&tmp, lengths[k], F1);
+    out[k] = (uint32_t) c.tjb_b | ((uint32_t) c.msv_xj_min << 16);
+  }
+}
+
 static void sync_all_lanes(p7gpu_ctx *ctx)
 {
   for (int l = 0; l < NLANES; l++) if (ctx->lanes[l].stream || l == 0) cudaStreamSynchronize(ctx->lanes[l].stream);

@@ -235,6 +235,19 @@ int launch_fbx_bwd(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const Db
 void fbx_host_fwd_score_compact(const float *blk, int L, float pmove, float *totscale, float *sc, int *status);
 void fbx_host_fwd_score(const float *xmx, int L, float pmove, float *totscale, float *sc, int *status);
 void fbx_host_bwd_score(const float *xmx, int L, float *totscale, float *sc, int *status);
+// hmmscan's MSV stage over a block of models (ssv_msv.cu: ssv_scan_kernel; scan.cu builds the tables): work item = (model, query)
+struct ScanModel { uint32_t tab_off; int rowWords, P, npass; MsvScalars s; };      // tab_off: this model's table inside ScanParams::tabs, in words
+struct ScanParams {
+  const ScanModel *models; const uint32_t *tabs;
+  const uint32_t *lc; const int32_t *lenidx; int nlens;      // lc[model * nlens + lenidx[query]] = tjb_b | msv_xj_min << 16
+  const uint8_t *res; const int64_t *off; const int32_t *len; long long nq;
+  long long nitems;                                          // models in the block x nq, model-major
+  int32_t *npossible;                                        // per model: queries that pass MSV or need the J recursion
+  unsigned long long *work_counter;
+};
+int launch_ssv_scan(p7gpu_ctx *ctx, cudaStream_t stream, const ScanParams &p);
+// the two per-length MSV constants of a model that is not uploaded (p7gpu_host.cu): tjb_b | msv_xj_min << 16 for each length
+void scan_len_words(const p7gpu_oprofile_view *om, const int32_t *lengths, int64_t n, double F1, uint32_t *out);
 // decode.cu: the region trigger of p7_domaindef_ByPosteriorHeuristics (max_i mocc[i] >= rt1) and the gather of selected specials
 int launch_region_trigger(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbView &db, const int64_t *d_idx, int64_t n,
                           const float *d_fx, const float *d_bx, const int64_t *d_xoff, const int32_t *d_own,

@@ -595,4 +595,80 @@ int launch_msv_j(p7gpu_ctx *ctx, int lane, const p7gpu_profile *prof, const DbVi
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ssv_scan_kernel: hmmscan's MSV stage for a whole block of models at once.
+//
+// hmmscan streams thousands of models past a few query sequences (hmmscan.c:1176-1198); one launch set per model is launch-
+// bound there.  Here the work item is a (model, query) pair and the gain table is picked per item: the tables of a block of
+// models lie side by side in global memory (L1/L2-resident: a warp re-reads ~1 KB of its model's table per DP row).  One
+// kernel serves every model length, because the SSV recurrence has no coupling between diagonals: a warp walks the query once
+// per group of 256 diagonals ("pass": 4 registers x 32 lanes x 2 halves) and keeps one running maximum over all passes.
+// The scan table of a model is laid out for that (scan.cu): P = 256 * npass >= M + 1 columns, word w of a row holds the gains
+// of columns (w mod P, (w + 128) mod P), rowWords = P + 96 so that a lane's four words c, c+32, c+64, c+96 never wrap.
+// Arithmetic, early exit and the decision tree are those of ssv_kernel (same gains, ssv_epilogue); the output is, per model,
+// the number of queries that pass the MSV threshold or need the J-state recursion (eslENORESULT): a model with none is one
+// for which p7gpu_pipeline_run(stop_after_msv) would report no survivor, so hmmscan never has to upload it.
+constexpr int SCAN_QB = 4, SCAN_THREADS = 128;
+
+__global__ void __launch_bounds__(SCAN_THREADS) ssv_scan_kernel(const ScanParams p)
+{
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long j = 0;
+    if (lane == 0) j = atomicAdd(p.work_counter, 1ULL);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= (unsigned long long) p.nitems) break;
+    const long long m = (long long) (j / (unsigned long long) p.nq), s = (long long) (j - (unsigned long long) m * (unsigned long long) p.nq);
+    const ScanModel md = p.models[m];
+    const int       L   = p.len[s];
+    const long long o   = p.off[s];
+    const uint32_t  lcw = __ldg(p.lc + (size_t) m * p.nlens + p.lenidx[s]);
+    const int       tjb = (int) (lcw & 0xffu), xjmin = (int) (lcw >> 16);
+    int status; float sc = 0.0f; int xJ = 0;
+    if (tjb + md.s.tbm_b + md.s.tec_b + md.s.bias_b >= 127) {    // ssvfilter.c:884
+      status = P7GPU_ENORESULT;
+    } else {
+      const int thresh = 127 - md.s.bias_b;
+      const uint32_t *tab = p.tabs + md.tab_off;
+      const uint8_t *seq = p.res + o;
+      uint32_t xE = 0u;
+      bool over = false;
+      for (int pass = 0; pass < md.npass && !over; pass++) {
+        uint32_t v[SCAN_QB];
+#pragma unroll
+        for (int q = 0; q < SCAN_QB; q++) v[q] = 0u;
+        int c = pass * (64 * SCAN_QB) + lane;
+        for (int i = 0; i < L; i++) {
+          const uint32_t x = __ldg(seq + i);
+          const uint32_t *rowp = tab + x * md.rowWords + c;
+#pragma unroll
+          for (int q = 0; q < SCAN_QB; q++) {
+            const uint32_t g = __ldg(rowp + 32 * q);
+            v[q] = __viaddmax_s16x2_relu(v[q], g, g);
+            xE = __vmaxs2(xE, v[q]);
+          }
+          c += 1; if (c >= md.P) c -= md.P;
+          // as in ssv_kernel: once a cell reaches 255-bias the outcome is fixed, and leaving keeps the int16 lanes from wrapping
+          if ((i & 63) == 63 && __any_sync(0xffffffffu, hmax16(xE) >= thresh)) { over = true; break; }
+        }
+      }
+      const int maxu = __reduce_max_sync(0xffffffffu, hmax16(xE));
+      status = ssv_epilogue(maxu, tjb, md.s, &sc, &xJ);
+    }
+    if (lane == 0 && L > 0 && (status != P7GPU_OK || xJ >= xjmin)) atomicAdd(p.npossible + m, 1);
+  }
+}
+
+int launch_ssv_scan(p7gpu_ctx *ctx, cudaStream_t stream, const ScanParams &p)
+{
+  if (p.nitems <= 0) return P7GPU_OK;
+  long long blocks = (p.nitems + (SCAN_THREADS / 32) - 1) / (SCAN_THREADS / 32);
+  const long long cap = (long long) ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  { LaunchTimer t(ctx, P7GPU_KERNEL_SSV, stream); ssv_scan_kernel<<<(unsigned) blocks, SCAN_THREADS, 0, stream>>>(p); }
+  P7G_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return P7GPU_OK;
+}
+
 }  // namespace p7g

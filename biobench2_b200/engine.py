@@ -24,7 +24,7 @@ EXPORTS = [
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
     "p7gpu_backward_batch", "p7gpu_region_trigger_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
     "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser", "p7gpu_BackwardParser2",
-    "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_stage_threshold", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
+    "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_scan_msv_prefilter", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_stage_threshold", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_decoding", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
     "p7gpu_dbfile_from_fasta", "p7gpu_dbfile_open", "p7gpu_dbfile_close", "p7gpu_dbfile_nseq", "p7gpu_dbfile_nres",
@@ -154,6 +154,7 @@ def lib():
         L.p7gpu_pack5.argtypes = [vp, i64, vp, C.c_int]
         L.p7gpu_pipeline_run_host5.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.POINTER(PipelineOpts), C.POINTER(vp)]
         L.p7gpu_pipeline_run_many.argtypes = [vp, vp, i64, vp, C.POINTER(PipelineOpts), vp]
+        L.p7gpu_scan_msv_prefilter.argtypes = [vp, vp, i64, vp, vp, C.c_double, vp]
         L.p7gpu_result_counters.restype = C.POINTER(PipelineCounters)
         L.p7gpu_result_counters.argtypes = [vp]
         L.p7gpu_result_nsurvivors.restype = i64
@@ -493,6 +494,23 @@ def pipeline_run_many(ctx, profs, db, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=T
     rh = (C.c_void_p * n)()
     _check(lib().p7gpu_pipeline_run_many(ctx.h, ph, n, db.h, C.byref(o), rh))
     return [PipelineResult(C.c_void_p(rh[i])) for i in range(n)]
+
+
+def scan_msv_prefilter(ctx, oprofiles, db, lengths, F1=0.02):
+    """hmmscan's MSV stage for a block of models in one launch (p7gpu_scan_msv_prefilter): per model, the number of targets of
+    `db` that pass F1 by their SSV score or need the J recursion; 0 = pipeline_run(stop_after_msv) would return no survivor.
+    `oprofiles`: objects with .view() -> p7gpu_oprofile_view (not uploaded); `lengths`: the target lengths of `db` (host)."""
+    n = len(oprofiles)
+    views = (OProfileView * max(n, 1))()
+    for k, o in enumerate(oprofiles):
+        v = o.view()
+        if not isinstance(v, OProfileView):
+            v = C.cast(C.pointer(v), C.POINTER(OProfileView)).contents
+        C.memmove(C.byref(views, k * C.sizeof(OProfileView)), C.byref(v), C.sizeof(OProfileView))
+    a = np.ascontiguousarray(lengths, np.int32)
+    out = np.zeros(max(n, 1), np.int32)
+    _check(lib().p7gpu_scan_msv_prefilter(ctx.h, views, n, db.h, _p(a), float(F1), _p(out)))
+    return out[:n]
 
 
 def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,

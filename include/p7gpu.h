@@ -295,6 +295,17 @@ int  p7gpu_pipeline_run(p7gpu_ctx *ctx, const p7gpu_profile *prof, const p7gpu_s
  * hmmsearch.c:471-560 without the per-query rewind and re-read of the sequence file (:480-487).  ret_res: nprof slots. */
 int  p7gpu_pipeline_run_many(p7gpu_ctx *ctx, const p7gpu_profile *const *profs, int64_t nprof, const p7gpu_seqdb *db,
                              const p7gpu_pipeline_opts *opts, p7gpu_pipeline_result **ret_res);
+/* hmmscan's MSV stage for a block of models at once.  hmmscan streams each model past the queries and reads
+ * the rest of a model only when some query gets past its MSV filter (hmmscan.c:1176-1198, p7_pipeline.c:688-713); with a handful
+ * of queries almost every model fails, and one upload + launch + read-back per model is what the time goes into.  This call
+ * takes the MSV parts of `nmodels` profiles as p7_oprofile_ReadMSV delivers them (impl_sse/io.c:233; only the MSV/SSV fields and
+ * evparam of each view are read), runs ONE kernel whose work item is a (model, query) pair with the gain table picked per item,
+ * and reports for each model how many queries either pass the MSV threshold F1 (p7_pipeline.c:691-693) by their SSV score or
+ * need the J-state recursion (eslENORESULT, msvfilter.c:105-106).  ret_npossible[m] == 0 means that
+ * p7gpu_pipeline_run(stop_after_msv) on model m would return no survivor: the model need not be uploaded at all.
+ * `queries` is the resident packed query database, `lengths` its nseq target lengths (host). */
+int  p7gpu_scan_msv_prefilter(p7gpu_ctx *ctx, const p7gpu_oprofile_view *oms, int64_t nmodels, const p7gpu_seqdb *queries,
+                              const int32_t *lengths, double F1, int32_t *ret_npossible);
 /* same for a HOST packed database: the upload is streamed under the MSV stage (p7gpu_msvfilter_stream) */
 int  p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
                              const int64_t *offsets, const int32_t *lengths, int64_t nseq,

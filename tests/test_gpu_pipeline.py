@@ -211,6 +211,45 @@ def test_pipeline_run_many_equals_one_call_per_profile(ctx):
     db.close()
 
 
+@pytest.mark.parametrize("nq,F1", [(1, 0.02), (7, 0.02), (300, 0.02), (300, 0.2), (40, 1e-4)])
+def test_scan_msv_prefilter_flags_every_model_with_an_msv_survivor(ctx, nq, F1):
+    """p7gpu_scan_msv_prefilter (one launch over (model, query) pairs, gain table picked per item) against the per-model path
+    hmmscan_b200 ran before it: for every model, the count must equal the number of queries whose SSV score passes F1 or whose
+    SSV status is eslERANGE/eslENORESULT in p7gpu_ssvfilter_batch, and a model the MSV stage of the pipeline finds a survivor
+    for is never reported as 0.  Models M = 1 .. 2000 (1 to 8 passes of 256 diagonals), queries with homologs and degenerates."""
+    import glob
+    from biobench2_b200.oprofile import OProfile
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "scan", "prof_scan_M*.npz"))) + \
+        [os.path.join(GOLDEN, "prof_%s.npz" % n) for n in ("synth_M1", "synth_M33", "synth_M2000", "globins4", "Pkinase", "fn3")]
+    ops = [OProfile.load(p) for p in paths]
+    parts = [seqdb.synth_db(max(1, nq - 12), mean=280, seed=100 + nq, degenerate_frac=0.01)]
+    if nq >= 40:
+        parts += [golden_set(n).db.subset(np.arange(4)) for n in ("globins4", "Pkinase", "fn3")]     # planted homologs (high scores, overflow)
+    hdb = seqdb.concat(parts) if len(parts) > 1 else parts[0]
+    db = engine.SeqDB.upload(ctx, hdb)
+    got = engine.scan_msv_prefilter(ctx, ops, db, hdb.lengths, F1=F1)
+    nflag = 0
+    for o, g in zip(ops, got):
+        prof = engine.Profile(ctx, o)
+        sc, st = engine.ssvfilter_batch(ctx, prof, db)
+        L_ = engine.lib()
+        nullsc = np.array([L_.p7gpu_nullsc(int(L)) for L in hdb.lengths], np.float32)
+        mu, lam = prof.evparam[0], prof.evparam[1]
+        ok = st == 0
+        passes = np.array([ok[k] and not (L_.p7gpu_msv_pvalue(float(sc[k]), float(nullsc[k]), mu, lam) > F1) for k in range(hdb.nseq)])
+        expect = int(np.sum((hdb.lengths > 0) & (passes | ~ok)))
+        assert int(g) == expect, (o.M, int(g), expect)
+        r = engine.pipeline_run(ctx, prof, db, F1=F1, stop_after_msv=True)
+        assert int(r.counters[2]) <= int(g)
+        if int(r.counters[2]) > 0:
+            assert g > 0
+        nflag += int(g > 0)
+        prof.close()
+    if nq >= 40 and F1 >= 0.02:
+        assert nflag >= 3
+    db.close()
+
+
 @pytest.mark.parametrize("name", ["globins4", "Pkinase", "tufa420_sprot"])
 def test_five_bit_transfer_format_gives_identical_results(ctx, name):
     """p7gpu_pipeline_run_host5: residues cross PCIe as eight 5-bit codes in five bytes and are expanded on the device;

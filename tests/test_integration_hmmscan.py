@@ -95,3 +95,58 @@ def test_hmmscan_b200_identical_to_reference(tmp_path, extra):
         if la != lb:
             diff = [(x, y) for x, y in zip(la, lb) if x != y]
             pytest.fail("hmmscan %s %s: %d of %d lines differ; first: %r" % (" ".join(extra), label, len(diff) + abs(len(la) - len(lb)), len(la), diff[:3]))
+
+
+def run_both(tmp_path, db, fa, extra_b200, extra=()):
+    res = {}
+    err = ""
+    for name, exe in (("ref", REFSCAN), ("b200", SCAN)):
+        o = tmp_path / (name + ".out"); t = tmp_path / (name + ".tbl"); d = tmp_path / (name + ".dom")
+        args = [exe, "-o", str(o), "--tblout", str(t), "--domtblout", str(d)] + list(extra) + (list(extra_b200) if name == "b200" else [])
+        p = subprocess.run(args + [str(db), str(fa)], capture_output=True, text=True, timeout=1800)
+        assert p.returncode == 0, (name, p.stdout[-1500:], p.stderr[-1500:])
+        res[name] = (str(o), str(t), str(d))
+        if name == "b200":
+            err = p.stderr
+    return res, err
+
+
+def assert_identical(res, what):
+    sr, sb = stats_blocks(res["ref"][0]), stats_blocks(res["b200"][0])
+    assert sr == sb, (what, len(sr), len(sb), [x for x in zip(sr, sb) if x[0] != x[1]][:5])
+    for label, a, b in (("--tblout", res["ref"][1], res["b200"][1]), ("--domtblout", res["ref"][2], res["b200"][2]),
+                        ("main output", res["ref"][0], res["b200"][0])):
+        la, lb = payload(a), payload(b)
+        if la != lb:
+            diff = [(x, y) for x, y in zip(la, lb) if x != y]
+            pytest.fail("hmmscan %s %s: %d of %d lines differ; first: %r" % (what, label, len(diff) + abs(len(la) - len(lb)), len(la), diff[:3]))
+    return sr
+
+
+@pytest.mark.gpu
+@need_bins
+@pytest.mark.parametrize("nq,opts", [(6, []), (1, []), (45, ["--prefilter", "5"]), (420, ["--prefilter", "3"])])
+def test_hmmscan_b200_block_prefilter_identical_to_reference(tmp_path, nq, opts):
+    """Few queries against many models: the (model, query) block prefilter (p7gpu_scan_msv_prefilter) decides which models are
+    uploaded at all.  Output must stay byte-identical to the reference's hmmscan, with block sizes that do and do not divide the
+    number of models, and some models must actually end in the prefilter when the queries are few."""
+    synth = tuple((M, 100 + M) for M in (40, 60, 85, 110, 140, 180, 215, 250, 290, 330, 400, 520))
+    db = build_pressed_db(tmp_path, synth=synth)
+    if nq >= 45:
+        fa = queries(tmp_path, nq, seed=11)
+    else:                                              # a planted homolog of one tutorial model + iid queries
+        full = queries(tmp_path, 45, seed=13)
+        recs = open(full, "rb").read().split(b">")[1:]
+        hom = [r for r in recs if r.startswith(b"Pkinase_hom")][:1]
+        iid = [r for r in recs if b"_seq" in r.split(b"\n", 1)[0]][:max(0, nq - 1)]
+        fa = tmp_path / "few.fa"
+        fa.write_bytes(b"".join(b">" + r for r in (iid + hom)))
+    res, err = run_both(tmp_path, db, fa, ["--times"] + opts)
+    sr = assert_identical(res, "nq=%d %s" % (nq, " ".join(opts)))
+    m = re.search(r"(\d+) ended in the block prefilter \(blocks of (\d+)\)", err)
+    assert m, err
+    if nq <= 6:
+        assert int(m.group(2)) == 512 and int(m.group(1)) >= 5, err         # most of the 15 models never reach the device on their own
+        assert sum(v for k, v, _ in sr if k == "Passed Fwd filter") >= 1
+    else:
+        assert int(m.group(2)) == int(opts[1])
