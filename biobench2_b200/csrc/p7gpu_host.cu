@@ -335,11 +335,38 @@ bool mw_geometry(int M, int *C, int *W)
 // profile tables live in the context's stream-ordered pool: an upload is cudaMallocAsync + cudaMemcpyAsync on the main stream
 // (the host vectors are pageable, so the copy has left them when the call returns), a destroy is cudaFreeAsync — hmmscan
 // uploads and drops one profile per model, and cudaMalloc/cudaFree round trips were most of its time per model
+// All tables of one profile travel as ONE block: every pool_upload() of a p7gpu_profile_upload() call appends its bytes to a
+// host arena (256-byte aligned) and remembers where the device pointer has to go; arena_commit() then does one cudaMallocAsync,
+// one cudaMemcpyAsync and fixes the pointers up.  (Seventeen allocate + copy pairs per profile were most of what a model costs
+// hmmscan once the block prefilter has decided that it must be uploaded.)
+struct UploadArena {
+  std::vector<char> bytes;
+  std::vector<std::pair<void **, size_t>> fix;       // (where the device pointer is stored, offset inside the block)
+};
+static thread_local UploadArena *g_arena = nullptr;
+
 template <class T>
 static int pool_upload(p7gpu_ctx *ctx, T **dptr, const void *src, size_t bytes)
 {
+  if (g_arena) {
+    const size_t off = (g_arena->bytes.size() + 255) & ~(size_t) 255;
+    g_arena->bytes.resize(off + std::max<size_t>(bytes, 16));
+    if (bytes) memcpy(g_arena->bytes.data() + off, src, bytes);
+    g_arena->fix.emplace_back((void **) dptr, off);
+    return P7GPU_OK;
+  }
   P7G_CUDA(cudaMallocAsync((void **) dptr, std::max<size_t>(bytes, 16), ctx->stream));
   if (bytes) P7G_CUDA(cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return P7GPU_OK;
+}
+
+static int arena_commit(p7gpu_ctx *ctx, UploadArena &a, void **d_block)
+{
+  *d_block = nullptr;
+  if (a.bytes.empty()) return P7GPU_OK;
+  P7G_CUDA(cudaMallocAsync(d_block, a.bytes.size(), ctx->stream));
+  P7G_CUDA(cudaMemcpyAsync(*d_block, a.bytes.data(), a.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
+  for (auto &f : a.fix) *f.first = (char *) *d_block + f.second;
   return P7GPU_OK;
 }
 
@@ -556,6 +583,9 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
   const int M = om->M, Kp = om->Kp;
   const int Q16 = nq_of(M, 16), Q8 = nq_of(M, 8), Q4 = nq_of(M, 4);
   p7gpu_profile *prof = new p7gpu_profile();
+  static thread_local UploadArena arena;                // kept between calls: its buffer is reused profile after profile
+  arena.bytes.clear(); arena.fix.clear();
+  struct ArenaScope { ArenaScope(UploadArena *a) { g_arena = a; } ~ArenaScope() { g_arena = nullptr; } } arena_scope(&arena);
   prof->ctx = ctx; prof->M = M; prof->Kp = Kp; prof->nj = om->nj;
   memcpy(prof->evparam, om->evparam, sizeof(prof->evparam));
   prof->msv.tbm_b = om->tbm_b; prof->msv.tec_b = om->tec_b; prof->msv.base_b = om->base_b; prof->msv.bias_b = om->bias_b;
@@ -668,6 +698,7 @@ int p7gpu_profile_upload(p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_pr
     prof->scale_w = om->scale_w;
     prof->fwd.xf_E_move = om->xf[0][0]; prof->fwd.xf_E_loop = om->xf[0][1];
   }
+  P7G_CHECK(arena_commit(ctx, arena, &prof->d_block));
   P7G_CUDA(cudaStreamSynchronize(ctx->stream));      // the tables are complete before any stream of the context reads them
   *ret_prof = prof;
   return P7GPU_OK;
@@ -679,9 +710,8 @@ void p7gpu_profile_destroy(p7gpu_profile *prof)
   p7gpu_ctx *ctx = prof->ctx;
   cudaSetDevice(ctx->device);
   sync_all_lanes(ctx);                         // nothing that reads the tables is still running, on any of the context's streams
-  void *ptrs[] = {prof->d_ssv_tab, prof->d_msv_tab, prof->d_ssv_tm, prof->d_rw, prof->d_tw, prof->d_rf, prof->d_tf, prof->d_rf_mw, prof->d_tf_mw,
-                  prof->d_tfx, prof->d_rfx, prof->d_tddx, prof->d_tmdx, prof->d_rwp, prof->d_twp, prof->d_scanw, prof->d_len};
-  for (void *q : ptrs) if (q) cudaFreeAsync(q, ctx->stream);
+  if (prof->d_block) cudaFreeAsync(prof->d_block, ctx->stream);      // every table lives inside this one block (arena_commit)
+  if (prof->d_len)   cudaFreeAsync(prof->d_len, ctx->stream);
   delete prof;
 }
 

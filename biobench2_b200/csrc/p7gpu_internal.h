@@ -133,6 +133,7 @@ struct p7gpu_profile {
   p7g::FwdScalars fwd;
   // SSV / MSV diagonal tables (device): [NTABROWS][rowWords] words = (int16 gain lo, int16 gain hi)
   p7g::DiagGeom geom;
+  void     *d_block = nullptr;         // the one device allocation all tables below point into (p7gpu_profile_upload)
   uint32_t *d_ssv_tab = nullptr;
   uint32_t *d_ssv_tm = nullptr;        // SSV gains in the Tensor Memory layout [NTABROWS][NX][32] (M <= 1024), see ssv_tm_kernel
   int ssv_tm_Q = 0;

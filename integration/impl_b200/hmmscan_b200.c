@@ -223,14 +223,15 @@ main(int argc, char **argv)
   qsort(qlens, (size_t) nq, sizeof(int32_t), cmp_int32);
   for (q = 0, nqlens = 0; q < nq; q++) if (q == 0 || qlens[q] != qlens[q - 1]) qlens[nqlens++] = qlens[q];
 
-  /* The block prefilter pays when most models fail MSV for every query: it costs ~25 us per model and saves the ~200 us upload +
-   * launch + read-back of each model that no query gets past MSV of; a model is flagged with probability >= 1 - (1-F1)^nq
-   * (measured on sampled models: 27 % at 10 queries, 93 % at 40), so it is on by default up to nq * F1 <= 0.5 (25 queries at the
-   * default F1) and off under --max, which passes everything. */
+  /* The block prefilter answers "does any query get past MSV of this model" for 512 models in one launch (~30 us per model with
+   * the table building) where the per-model MSV stage costs an upload + launch + read-back (~200 us); flagged models go
+   * straight to the full upload, so it pays at any number of queries (measured, 2000 models: 1 query 0.32 -> 0.11 s, 10 queries
+   * 0.74 -> 0.52 s, 25 queries 1.53 -> 1.17 s).  Off under --max, which passes everything, and beyond 2000 queries, where the
+   * per-model kernel (table in shared / Tensor Memory) is the faster way through the cells. */
   do_max = esl_opt_GetBoolean(go, "--max");
   F1     = ESL_MIN(1.0, esl_opt_GetReal(go, "--F1"));                 /* p7_pipeline_Create, p7_pipeline.c:141 */
   blkmax = esl_opt_GetInteger(go, "--prefilter");
-  if (blkmax < 0) blkmax = (!do_max && F1 < 1.0 && nq > 0 && (double) nq * F1 <= 0.5) ? 512 : 0;
+  if (blkmax < 0) blkmax = (!do_max && F1 < 1.0 && nq > 0 && nq <= 2000) ? 512 : 0;
   if (do_max || blkmax < 2) blkmax = 1;
   blkmax = ESL_MIN(blkmax, 4096);
   ESL_ALLOC(blk,       sizeof(P7_OPROFILE *) * blkmax);
@@ -255,7 +256,7 @@ main(int argc, char **argv)
    for (b = 0; b < nb; b++) {
     p7gpu_pipeline_opts o;
     p7gpu_pipeline_result *r = NULL;
-    int64_t npass;
+    int64_t npass = 0;
 
     om = blk[b];
     if (!qs) {                                                   /* the alphabet is known now: per-query pipeline + hit list */
@@ -277,14 +278,17 @@ main(int argc, char **argv)
     o.F1 = qs ? qs[0].pli->F1 : 0.02;  o.F2 = qs ? qs[0].pli->F2 : 1e-3;  o.F3 = qs ? qs[0].pli->F3 : 1e-5;
     o.do_biasfilter = qs ? qs[0].pli->do_biasfilter : 1;  o.do_max = qs ? qs[0].pli->do_max : 0;
     o.stop_after_msv = 1;
-    t0 = now_s();
-    if (p7_b200_SetModelMSV(eng, om) != eslOK) p7_Fail("Failed to upload profile %s: %s\n", om->name, p7_b200_ErrorText());
-    if (p7_b200_PrepareLengths(eng, qlens, nqlens, o.do_max ? 1.0 : o.F1) != eslOK) p7_Fail("Failed to prepare profile %s: %s\n", om->name, p7_b200_ErrorText());
-    if (p7gpu_pipeline_run(p7_b200_Ctx(eng), p7_b200_Profile(eng), gdb, &o, &r) != P7GPU_OK) p7_Fail("GPU pipeline failed: %s\n", p7gpu_last_error());
-    npass = p7gpu_result_nmsvpass(r);
-    p7gpu_result_destroy(r);  r = NULL;
-    t_msv += now_s() - t0;
-    if (npass == 0) { p7_oprofile_Destroy(om); continue; }       /* nothing passed: the .h3p part of this model is never read */
+    if (blkmax == 1) {                                           /* (with the block prefilter this question is answered already: a flagged
+                                                                  *  model has a query past MSV, or one that needs the J recursion — rare) */
+      t0 = now_s();
+      if (p7_b200_SetModelMSV(eng, om) != eslOK) p7_Fail("Failed to upload profile %s: %s\n", om->name, p7_b200_ErrorText());
+      if (p7_b200_PrepareLengths(eng, qlens, nqlens, o.do_max ? 1.0 : o.F1) != eslOK) p7_Fail("Failed to prepare profile %s: %s\n", om->name, p7_b200_ErrorText());
+      if (p7gpu_pipeline_run(p7_b200_Ctx(eng), p7_b200_Profile(eng), gdb, &o, &r) != P7GPU_OK) p7_Fail("GPU pipeline failed: %s\n", p7gpu_last_error());
+      npass = p7gpu_result_nmsvpass(r);
+      p7gpu_result_destroy(r);  r = NULL;
+      t_msv += now_s() - t0;
+      if (npass == 0) { p7_oprofile_Destroy(om); continue; }     /* nothing passed: the .h3p part of this model is never read */
+    }
 
     /* stage 2: the rest of the model (p7_pipeline.c:708-713), then the rest of the pipeline for the survivors */
     t0 = now_s();

@@ -125,7 +125,7 @@ def assert_identical(res, what):
 
 @pytest.mark.gpu
 @need_bins
-@pytest.mark.parametrize("nq,opts", [(6, []), (1, []), (45, ["--prefilter", "5"]), (420, ["--prefilter", "3"])])
+@pytest.mark.parametrize("nq,opts", [(6, []), (1, []), (45, ["--prefilter", "5"]), (45, ["--prefilter", "0"]), (420, ["--prefilter", "3"])])
 def test_hmmscan_b200_block_prefilter_identical_to_reference(tmp_path, nq, opts):
     """Few queries against many models: the (model, query) block prefilter (p7gpu_scan_msv_prefilter) decides which models are
     uploaded at all.  Output must stay byte-identical to the reference's hmmscan, with block sizes that do and do not divide the
