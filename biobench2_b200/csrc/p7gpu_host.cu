@@ -547,6 +547,7 @@ int p7gpu_ctx_set_option(p7gpu_ctx *ctx, const char *name, int value)
   if (!strcmp(name, "bias_window_log2")) { ctx->bias_window = value > 0 ? ldexpf(1.0f, -value) : 0.f; return P7GPU_OK; }
   if (!strcmp(name, "fbx_warps"))      { ctx->fbx_warps = value; return P7GPU_OK; }
   if (!strcmp(name, "ssv_tmem"))       { ctx->ssv_tmem = value; return P7GPU_OK; }
+  if (!strcmp(name, "bias_warp"))      { ctx->bias_warp = value; return P7GPU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return P7GPU_EINVAL;
 }

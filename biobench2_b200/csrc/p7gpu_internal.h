@@ -113,6 +113,7 @@ struct p7gpu_ctx {
   int          fb_fast = 0;             // option "fb_fast": the one-target wrappers p7gpu_ForwardParser/BackwardParser run the fast kernels
   int          ssv_tmem = 1;            // option "ssv_tmem": SSV gain table in Tensor Memory when 193 <= M <= 1024 (ssv_tm_kernel; 2 = at every M <= 1024); 0 = shared memory
   int          fbx_warps = 0;           // option "fbx_warps": cap on resident one-warp CTAs per SM of the exact-order kernels (0 = occupancy)
+  int          bias_warp = 1;           // option "bias_warp": one warp per target in the bias kernel (0 never, 1 when the launch is small, 2 always)
   float        bias_window = 0.f;       // option "bias_window_log2": half-width 2^-n of the bias kernel's log() certainty test (tests widen it)
   int64_t      bias_fixed = 0;          // targets whose filtersc the host recomputed so far (diagnostic)
   int          fbx_groups = 0;          // option "fbx_groups": targets per warp of the exact-order kernels, 1/2/4/8 (0 = auto)

@@ -371,6 +371,38 @@ def test_bias_filter_score_is_exact_by_construction(gpu_ctx, name):
         db.close(); prof.close()
 
 
+@pytest.mark.parametrize("name", ["globins4", "Pkinase", "synth_M400", "tufa420_sprot"])
+def test_bias_warp_kernel_equals_thread_kernel(gpu_ctx, name):
+    """bias.cu has a throughput form (one thread per target) and a latency form (one warp per target, the logarithms of 32 rows
+    in parallel, added in row order): both must give the reference's filtersc bit for bit — on the golden targets and on 3000
+    seeded ones of every length class (L = 1, L < 32, L = 32k, long), with the certainty window at its default and widened."""
+    from conftest import golden_set, bits
+    g = golden_set(name)
+    prof = engine.Profile(gpu_ctx, g.oprofile)
+    extra = seqdb.pack([np.full(L, (7 * L) % 20, np.uint8) for L in (1, 2, 31, 32, 33, 64, 65, 1000)])
+    hdb = seqdb.concat([g.db, seqdb.synth_db(3000, mean=220, seed=9, degenerate_frac=0.02), extra])
+    db = engine.SeqDB.upload(gpu_ctx, hdb)
+    idx = np.nonzero(hdb.lengths > 0)[0].astype(np.int64)
+    gi = np.nonzero(g.db.lengths > 0)[0].astype(np.int64)
+    try:
+        out = {}
+        for mode in (0, 2):
+            gpu_ctx.set_option("bias_warp", mode)
+            out[mode] = engine.biasfilter_batch(gpu_ctx, prof, db, idx)
+            assert np.array_equal(bits(engine.biasfilter_batch(gpu_ctx, prof, db, gi)), bits(g.vec["filtersc"][gi])), mode
+        assert np.array_equal(bits(out[0]), bits(out[2]))
+        gpu_ctx.set_option("bias_window_log2", 16)
+        for mode in (0, 2):                                   # the host recomputation behind either form
+            gpu_ctx.set_option("bias_warp", mode)
+            before = gpu_ctx.bias_recomputed
+            f = engine.biasfilter_batch(gpu_ctx, prof, db, idx)
+            assert np.array_equal(bits(f), bits(out[0])) and gpu_ctx.bias_recomputed - before >= len(idx) // 20, mode
+    finally:
+        gpu_ctx.set_option("bias_window_log2", 0)
+        gpu_ctx.set_option("bias_warp", 1)
+        db.close(); prof.close()
+
+
 @pytest.mark.gpu
 def test_result_may_outlive_its_context():
     """A pipeline result hands its large host buffers back to its context's cache when it is destroyed; a host language may
