@@ -122,6 +122,9 @@ int         p7gpu_measure_peaks(p7gpu_ctx *ctx, double *int16x2_gops, double *fp
  * 3. Profile: replaces the consumer side of p7_oprofile_Convert()/p7_oprofile_Clone()
  *    (impl_sse/p7_oprofile.c:1004-1041, :403-420).  Per-target p7_oprofile_ReconfigLength()
  *    (:1061-1127) is folded into per-L tables built on the host with the host libm.
+ *    Ownership: a profile belongs to the context it was uploaded through and, like the reference's per-worker om clone
+ *    (hmmsearch.c:505-516), to one host thread at a time — its per-L table is rebuilt in place when a call brings a longer
+ *    target or another F1.  All of its tables live in one device allocation made on the context's stream.
  * ---------------------------------------------------------------------------------------------- */
 int  p7gpu_profile_upload (p7gpu_ctx *ctx, const p7gpu_oprofile_view *om, p7gpu_profile **ret_prof);
 void p7gpu_profile_destroy(p7gpu_profile *prof);
