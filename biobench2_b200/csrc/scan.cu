@@ -55,6 +55,16 @@ void build_scan_table(const p7gpu_oprofile_view *om, const ScanGeom &g, uint32_t
 
 }  // namespace
 
+extern "C" int p7gpu_scan_table_build(const p7gpu_oprofile_view *om, int32_t geom[3], uint32_t *table, int32_t L, double F1, uint32_t *len_word)
+{
+  if (!om || !geom || om->M < 1 || om->Kp != P7GPU_KP || !om->rbv || om->M > 64 * MAX_Q - 1 || L < 0) return P7GPU_EINVAL;
+  const ScanGeom g = scan_geom(om->M);
+  geom[0] = g.P; geom[1] = g.rowWords; geom[2] = g.npass;
+  if (table) build_scan_table(om, g, table);
+  if (len_word) scan_len_words(om, &L, 1, F1 < 0 ? DEFAULT_F1 : F1, len_word);
+  return P7GPU_OK;
+}
+
 extern "C" int p7gpu_scan_msv_prefilter(p7gpu_ctx *ctx, const p7gpu_oprofile_view *oms, int64_t nmodels, const p7gpu_seqdb *queries,
                                         const int32_t *lengths, double F1, int32_t *ret_npossible)
 {

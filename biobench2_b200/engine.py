@@ -24,7 +24,7 @@ EXPORTS = [
     "p7gpu_msvfilter_batch", "p7gpu_ssvfilter_batch", "p7gpu_vitfilter_batch", "p7gpu_forward_batch",
     "p7gpu_backward_batch", "p7gpu_region_trigger_batch", "p7gpu_msvfilter_device", "p7gpu_biasfilter_batch", "p7gpu_msvfilter_stream",
     "p7gpu_SSVFilter", "p7gpu_MSVFilter", "p7gpu_ViterbiFilter", "p7gpu_ForwardParser", "p7gpu_BackwardParser", "p7gpu_BackwardParser2",
-    "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_scan_msv_prefilter", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_stage_threshold", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
+    "p7gpu_pipeline_run", "p7gpu_pipeline_run_many", "p7gpu_scan_msv_prefilter", "p7gpu_scan_table_build", "p7gpu_pipeline_run_host", "p7gpu_pipeline_run_host5", "p7gpu_pack5", "p7gpu_pack5_bytes", "p7gpu_stage_threshold", "p7gpu_result_nmsvpass", "p7gpu_result_msvpass", "p7gpu_result_stage_residues", "p7gpu_result_counters", "p7gpu_result_nsurvivors", "p7gpu_result_survivors",
     "p7gpu_result_fwd_xmx", "p7gpu_result_bck_xmx", "p7gpu_result_decoding", "p7gpu_result_destroy",
     "p7gpu_nullsc", "p7gpu_msv_pvalue",
     "p7gpu_dbfile_from_fasta", "p7gpu_dbfile_open", "p7gpu_dbfile_close", "p7gpu_dbfile_nseq", "p7gpu_dbfile_nres",
@@ -155,6 +155,7 @@ def lib():
         L.p7gpu_pipeline_run_host5.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.POINTER(PipelineOpts), C.POINTER(vp)]
         L.p7gpu_pipeline_run_many.argtypes = [vp, vp, i64, vp, C.POINTER(PipelineOpts), vp]
         L.p7gpu_scan_msv_prefilter.argtypes = [vp, vp, i64, vp, vp, C.c_double, vp]
+        L.p7gpu_scan_table_build.argtypes = [vp, vp, vp, C.c_int32, C.c_double, vp]
         L.p7gpu_result_counters.restype = C.POINTER(PipelineCounters)
         L.p7gpu_result_counters.argtypes = [vp]
         L.p7gpu_result_nsurvivors.restype = i64
@@ -511,6 +512,20 @@ def scan_msv_prefilter(ctx, oprofiles, db, lengths, F1=0.02):
     out = np.zeros(max(n, 1), np.int32)
     _check(lib().p7gpu_scan_msv_prefilter(ctx.h, views, n, db.h, _p(a), float(F1), _p(out)))
     return out[:n]
+
+
+def scan_table(oprofile, L, F1=0.02):
+    """Host-only diagnostic (p7gpu_scan_table_build): the block prefilter's table of one model -> (table[29][rowWords] uint32,
+    P, npass, tjb_b, msv_xj_min for target length L).  Needs no device."""
+    v = oprofile.view()
+    if not isinstance(v, OProfileView):
+        v = C.cast(C.pointer(v), C.POINTER(OProfileView)).contents
+    geom = np.zeros(3, np.int32)
+    _check(lib().p7gpu_scan_table_build(C.byref(v), _p(geom), None, int(L), float(F1), None))
+    tab = np.zeros((29, int(geom[1])), np.uint32)          # P7GPU_KP rows
+    w = np.zeros(1, np.uint32)
+    _check(lib().p7gpu_scan_table_build(C.byref(v), _p(geom), _p(tab), int(L), float(F1), _p(w)))
+    return tab, int(geom[0]), int(geom[2]), int(w[0] & 0xff), int(w[0] >> 16)
 
 
 def pipeline_run_host(ctx, prof, packed, F1=0.02, F2=1e-3, F3=1e-5, do_biasfilter=True, do_max=False, want_specials=True,

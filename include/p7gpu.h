@@ -309,6 +309,12 @@ int  p7gpu_pipeline_run_many(p7gpu_ctx *ctx, const p7gpu_profile *const *profs, 
  * `queries` is the resident packed query database, `lengths` its nseq target lengths (host). */
 int  p7gpu_scan_msv_prefilter(p7gpu_ctx *ctx, const p7gpu_oprofile_view *oms, int64_t nmodels, const p7gpu_seqdb *queries,
                               const int32_t *lengths, double F1, int32_t *ret_npossible);
+/* diagnostic (host code, no device needed): the scan table p7gpu_scan_msv_prefilter builds for one model and the per-length
+ * word (tjb_b | msv_xj_min << 16) it hands the kernel for target length L.  geom[0..2] = columns P (256 * passes >= M + 1),
+ * words per row (P + 96), passes; `table` (may be NULL to ask for the geometry only) receives 29 rows of geom[1] words, word w =
+ * the int16 SSV gains of columns (w mod P, (w + 128) mod P), pad columns -20000.  tests/test_cabi.py walks it the way the
+ * kernel does and compares the outcome with the CPU oracle's p7_SSVFilter. */
+int  p7gpu_scan_table_build(const p7gpu_oprofile_view *om, int32_t geom[3], uint32_t *table, int32_t L, double F1, uint32_t *len_word);
 /* same for a HOST packed database: the upload is streamed under the MSV stage (p7gpu_msvfilter_stream) */
 int  p7gpu_pipeline_run_host(p7gpu_ctx *ctx, const p7gpu_profile *prof, const uint8_t *residues, int64_t nbytes,
                              const int64_t *offsets, const int32_t *lengths, int64_t nseq,

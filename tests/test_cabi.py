@@ -121,3 +121,74 @@ def test_stage_thresholds_reproduce_the_p_value_tests():
                     n += 1
     assert n > 9000
     assert engine.stage_threshold("gumbel", 0.02, -10.0, 0.7) is not None
+
+
+def _scan_walk(tab, P, npass, seq, thresh):
+    """ssv_scan_kernel's walk over the product's scan table (ssv_msv.cu), in numpy: per pass 32 lanes x 4 words x 2 halves follow
+    their diagonals from word 256*pass + lane (+32q), one column per row, wrapping at P; running maximum over all passes;
+    leave once a cell reaches the overflow threshold (checked every 64 rows)."""
+    xE = 0
+    for p in range(npass):
+        v = np.zeros((32, 4, 2), np.int64)
+        c = p * 256 + np.arange(32)
+        for i, x in enumerate(seq):
+            w = tab[x][c[:, None] + 32 * np.arange(4)[None, :]]
+            g = np.stack([(w & 0xffff).astype(np.uint16).view(np.int16), (w >> 16).astype(np.uint16).view(np.int16)], -1).astype(np.int64)
+            v = np.maximum(v + g, 0)
+            assert v.max() < 32768
+            xE = max(xE, int(v.max()))
+            c = c + 1
+            c[c >= P] -= P
+            if (i & 63) == 63 and xE >= thresh:
+                return xE
+    return xE
+
+
+def _ssv_epilogue(maxu, tjb, v):
+    """the decision tree of p7_SSVFilter after get_xE (ssvfilter.c:884-925) -> (status, score bits or None, xJ)"""
+    xE = min(128 + maxu, 255)
+    if xE >= 255 - v.bias_b:
+        return (engine.ENORESULT if v.base_b - tjb - v.tbm_b < 128 else engine.ERANGE), None, 0
+    xE16 = ((xE + v.base_b - tjb - v.tbm_b) & 0xffff) - 128 & 0xffff
+    if xE16 >= 255 - v.bias_b:
+        return engine.ERANGE, None, 0
+    xJ = (xE16 - v.tec_b) & 0xffff
+    if xJ > v.base_b:
+        return engine.ENORESULT, None, 0
+    sc = np.float32(np.float32(np.float32(xJ - tjb) - np.float32(v.base_b)) / np.float32(v.scale_b)) - np.float32(3.0)
+    return 0, np.float32(sc), xJ
+
+
+@pytest.mark.parametrize("name", ["synth_M1", "synth_M33", "synth_M100", "globins4", "fn3", "Pkinase", "synth_M400", "synth_M800"])
+def test_scan_table_walk_equals_oracle_ssv(name):
+    """Host logic of the hmmscan block prefilter, no device: the table p7gpu_scan_table_build lays out for a model, walked the way
+    ssv_scan_kernel walks it (pass by pass over groups of 256 diagonals), must give the CPU oracle's p7_SSVFilter status and
+    score bits on seeded targets and on the reference-generated golden targets (homologs, overflow, degenerate residues)."""
+    from conftest import golden_set, bits, GOLDEN
+    from biobench2_b200.oprofile import OProfile
+    from oracle import port
+    op = OProfile.load(os.path.join(GOLDEN, "prof_%s.npz" % name))
+    v = op.view()
+    o = port.OracleProfile(v, op)
+    g = golden_set(name)
+    pick = np.argsort(-g.vec["msv_sc"] if "msv_sc" in g.vec else np.arange(g.db.nseq))[:6]
+    hdb = seqdb.concat([g.db.subset(pick), seqdb.synth_db(10 if op.M > 300 else 30, mean=120, seed=op.M, degenerate_frac=0.03),
+                        seqdb.pack([np.zeros(1, np.uint8), np.arange(70, dtype=np.uint8) % 29])])
+    osc, ost = o.stage_batch("ssv", hdb)
+    nchecked = 0
+    for s in range(hdb.nseq):
+        L = int(hdb.lengths[s])
+        seq = hdb.residues[int(hdb.offsets[s]): int(hdb.offsets[s]) + L]
+        tab, P, npass, tjb, xjmin = engine.scan_table(op, L)
+        assert P == 256 * npass and P >= op.M + 1 and P - 256 < op.M + 1 and tab.shape == (29, P + 96)
+        assert 0 <= xjmin <= 256
+        if tjb + v.tbm_b + v.tec_b + v.bias_b >= 127:
+            assert ost[s] == engine.ENORESULT
+            continue
+        st, sc, xJ = _ssv_epilogue(_scan_walk(tab, P, npass, seq, 127 - v.bias_b), tjb, v)
+        assert st == ost[s], (name, s, L, st, ost[s])
+        if st == 0:
+            assert bits(sc) == bits(osc[s]), (name, s, L, sc, osc[s])
+            nchecked += 1
+    assert nchecked >= 5
+    o.close()
